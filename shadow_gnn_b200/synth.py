@@ -1,0 +1,93 @@
+"""Synthetic stand-ins for the OGB graphs (no network => no datasets), SURVEY.md 8(d).
+
+`powerlaw_graph` follows the recipe fixed there: out-degree min(floor(pareto(1.6)*c)+1, dmax),
+uniform random endpoints, self loops dropped, symmetrised, rows sorted + unique, uint32 CSR --
+the invariants `to_undirected_csr` guarantees for the graphs the reference samples from
+(para_graph_sampler/graph_engine/frontend/graph_utils.py:19-45).
+"""
+import numpy as np
+
+# name -> (N, nnz_target, dmax, F, C, n_train, seed)      (public OGB sizes)
+PRESETS = {
+    "S-arxiv":    (169_343,     2_320_000,    13_161, 128, 40,   90_941, 0),
+    "S-products": (2_449_029, 123_700_000,    17_481, 100, 47,  196_615, 1),
+    "S-papers":   (111_059_956, 3_230_000_000, 100_000, 128, 172, 1_207_179, 2),
+}
+
+
+def _coo_to_csr_sym(src, dst, n):
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    key = np.concatenate([src.astype(np.int64) * n + dst, dst.astype(np.int64) * n + src])
+    key = np.unique(key)
+    rows = (key // n).astype(np.int64)
+    indices = (key % n).astype(np.uint32)
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=n), out=indptr[1:])
+    assert indptr[-1] < 2 ** 32
+    return indptr.astype(np.uint32), indices
+
+
+def powerlaw_graph(n, nnz_target, seed, dmax=None, tail=False):
+    """Undirected power-law CSR (uint32).  tail=True appends the disconnected 2-node component
+    (n, n+1) that keeps the reference's out-of-bounds read away from sampled rows."""
+    rng = np.random.default_rng(seed)
+    dmax = dmax or max(8, n // 4)
+    raw = rng.pareto(1.6, n)
+    c = 1.0
+    for _ in range(30):      # tune c so the directed edge count is ~ nnz_target / 2
+        deg = np.minimum(np.floor(raw * c) + 1, dmax)
+        c *= (nnz_target / 2) / deg.sum()
+    deg = np.minimum(np.floor(raw * c) + 1, dmax).astype(np.int64)
+    src = np.repeat(np.arange(n, dtype=np.int64), deg)
+    dst = rng.integers(0, n, src.size, dtype=np.int64)
+    if tail:
+        src = np.concatenate([src, [n]])
+        dst = np.concatenate([dst, [n + 1]])
+        n += 2
+    return _coo_to_csr_sym(src, dst, n)
+
+
+def powerlaw_graph_torch(n, nnz_target, seed, dmax, device):
+    """Same recipe on the GPU with torch ops (setup only, not part of any timed region):
+    the S-products graph (124 M edges) takes seconds instead of a minute of host sorting."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = torch.rand(n, generator=g, device=device, dtype=torch.float64).clamp_min(1e-12)
+    raw = u.pow(-1.0 / 1.6) - 1.0          # pareto(1.6), numpy's (Lomax) convention
+    c = 1.0
+    for _ in range(30):
+        deg = torch.clamp(torch.floor(raw * c) + 1, max=dmax)
+        c *= (nnz_target / 2) / float(deg.sum())
+    deg = torch.clamp(torch.floor(raw * c) + 1, max=dmax).long()
+    src = torch.repeat_interleave(torch.arange(n, device=device), deg)
+    dst = torch.randint(0, n, (src.numel(),), generator=g, device=device)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    key = torch.cat([src * n + dst, dst * n + src])
+    del src, dst
+    key = torch.unique(key)
+    rows = torch.div(key, n, rounding_mode="floor")
+    indices = (key - rows * n).to(torch.int32)      # bit pattern of uint32 (n < 2^31 here)
+    counts = torch.bincount(rows, minlength=n)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    assert int(indptr[-1]) < 2 ** 32
+    return indptr, indices
+
+
+def small_parity_graph(n=2000, avg_deg=12, seed=0, self_loops=0):
+    """Small graph for parity tests: power-law + optional pre-existing self loops + tail component."""
+    indptr, indices = powerlaw_graph(n, n * avg_deg, seed, dmax=max(8, n // 10), tail=True)
+    if self_loops:
+        rng = np.random.default_rng(seed + 1)
+        loops = rng.choice(n, self_loops, replace=False)
+        rows = np.repeat(np.arange(indptr.size - 1), np.diff(indptr.astype(np.int64)))
+        key = np.unique(np.concatenate([rows.astype(np.int64) * (n + 2) + indices, loops.astype(np.int64) * (n + 2) + loops]))
+        r = key // (n + 2)
+        indices = (key % (n + 2)).astype(np.uint32)
+        ip = np.zeros(n + 3, np.int64)
+        np.cumsum(np.bincount(r, minlength=n + 2), out=ip[1:])
+        indptr = ip.astype(np.uint32)
+    return indptr, indices
