@@ -1,0 +1,149 @@
+/*
+ * shadow_b200.h -- C ABI of the B200-native shaDow-GNN hot path (libshadow_b200.so).
+ *
+ * Plain pointers and sizes only; no torch / pybind types.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference tree; PS.cpp / PS.h =
+ * para_graph_sampler/graph_engine/backend/ParallelSampler.{cpp,h}, G.h = backend/Graph.h,
+ * layers.py = shaDow/layers.py, graph_utils.py = para_graph_sampler/graph_engine/frontend/graph_utils.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SHADOW_E* code on failure;
+ *     shadow_last_error() gives the message of the last failure on the calling thread.
+ *   - "dev" pointers are CUDA device pointers on the sampler's device; "host" pointers are host memory.
+ *   - all kernels are enqueued on the stream given (a cudaStream_t passed as void*; NULL = default stream).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with SHADOW_ECUDA.
+ */
+#ifndef SHADOW_B200_H
+#define SHADOW_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHADOW_EINVAL   (-1)   /* bad argument (the reference would throw std::out_of_range / invalid_argument) */
+#define SHADOW_ECUDA    (-2)   /* CUDA runtime error / no device */
+#define SHADOW_EIO      (-3)   /* file missing / short */
+#define SHADOW_ESTATE   (-4)   /* call order violated (e.g. sampling ppr before tables are installed) */
+#define SHADOW_ECAP     (-5)   /* a size exceeded a 31-bit offset; use a smaller super-batch */
+
+const char *shadow_last_error(void);
+int shadow_version(void);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* sampler object  == class ParallelSampler (PS.h:25-158; python surface PS.cpp:707-734)          */
+/* ---------------------------------------------------------------------------------------------- */
+typedef struct shadow_sampler shadow_sampler;
+
+/* sampler methods: cfg.at("method") dispatch in parallel_sampler_ensemble (PS.cpp:685-693) */
+enum { SHADOW_KHOP = 0, SHADOW_PPR = 1, SHADOW_PPR_ST = 2, SHADOW_NODEIID = 3 };
+/* feature-augmentation flags: configs_aug sets {"hops","pprs","drnls"} (PS.cpp:433-451) */
+enum { SHADOW_AUG_HOPS = 1, SHADOW_AUG_PPRS = 2, SHADOW_AUG_DRNLS = 4 };
+/* random streams for khop / ppr_st */
+enum { SHADOW_RNG_GLIBC = 0,    /* replays glibc rand() in the reference's single-thread order (PS.cpp:534, PS.h:49-53) */
+       SHADOW_RNG_PHILOX = 1 }; /* counter-based Philox4x32-10 keyed (seed, call, root slot, level, node, draw): parallel */
+
+/* one entry of `configs_samplers` (std::unordered_map<string,string>, PS.cpp:662-664) parsed to numbers */
+typedef struct {
+  int32_t method;               /* "method" */
+  int32_t num_roots;            /* "num_roots" (1 node task, 2 link task) */
+  int32_t depth, budget;        /* khop: "depth", "budget" (budget < 0 => all neighbours) */
+  int32_t k;                    /* ppr / ppr_st: "k" */
+  float   threshold;            /* ppr / ppr_st: "threshold" (stod narrowed to float, PS.cpp:571) */
+  int32_t add_self_edge;        /* "add_self_edge" */
+  int32_t include_target_conn;  /* "include_target_conn" */
+  int32_t return_target_only;   /* "return_target_only" => dummy_sampler (PS.cpp:653-659) */
+  int32_t aug;                  /* SHADOW_AUG_* bits */
+  int32_t fixed_mode;           /* 0 = bug-compatible with the always-true compare at PS.cpp:401 (default),
+                                   1 = row bound repaired */
+  int32_t rng_mode;             /* SHADOW_RNG_* */
+} shadow_sampler_cfg;
+
+/* ParallelSampler ctor (PS.h:27-69).  indptr/indices are HOST arrays (copied to HBM) or NULL to load the raw
+ * little-endian uint32 files path_indptr/path_indices (read_array_from_bin, PS.cpp:70-86).  `data`,
+ * `edge_reweighted` of the reference are unused by it (PS.h:48) and have no counterpart.
+ * num_ring >= 1 result buffers are kept alive: the output of call i stays valid until call i + num_ring. */
+int shadow_sampler_create(const uint32_t *indptr_host, const uint32_t *indices_host,
+                          uint32_t num_nodes, uint32_t num_edges,
+                          const char *path_indptr, const char *path_indices,
+                          int num_sampler_per_batch, int num_subgraphs_ensemble, int seed,
+                          int device, int num_ring, shadow_sampler **out);
+/* variant for a CSR that is already resident in HBM (the sampler borrows the pointers) */
+int shadow_sampler_create_dev(const uint32_t *indptr_dev, const uint32_t *indices_dev,
+                              uint32_t num_nodes, uint32_t num_edges,
+                              int num_sampler_per_batch, int num_subgraphs_ensemble, int seed,
+                              int device, int num_ring, shadow_sampler **out);
+int shadow_sampler_destroy(shadow_sampler *s);
+int shadow_sampler_set_stream(shadow_sampler *s, void *cuda_stream);
+
+uint32_t shadow_sampler_num_nodes(const shadow_sampler *s);            /* PS.cpp:49  */
+uint32_t shadow_sampler_num_edges(const shadow_sampler *s);            /* PS.cpp:51  */
+uint32_t shadow_sampler_num_nodes_target(const shadow_sampler *s);     /* PS.cpp:53  */
+uint32_t shadow_sampler_get_idx_root(const shadow_sampler *s);         /* PS.cpp:45  */
+int shadow_sampler_set_num_per_batch(shadow_sampler *s, int num_sampler_per_batch);
+/* shuffle_targets (PS.cpp:36-43), pre-shuffled branch: installs the epoch's target order. idx_root is not reset. */
+int shadow_sampler_shuffle_targets(shadow_sampler *s, const uint32_t *targets_host, uint32_t n);
+int shadow_sampler_shuffle_targets_dev(shadow_sampler *s, const uint32_t *targets_dev, uint32_t n);
+/* srand() of the ctor (PS.h:49-53): restart the replayed glibc stream */
+int shadow_sampler_reseed(shadow_sampler *s, int seed);
+/* drop_full_graph_info (PS.cpp:22-34) */
+int shadow_sampler_drop_full_graph_info(shadow_sampler *s);
+
+/* PPR tables == top_ppr_neighs / top_ppr_scores (PS.h:145-146), CSR-flattened by node id:
+ * row of node v = [ptr[v], ptr[v+1]).  Host arrays; copied to HBM. */
+int shadow_sampler_set_ppr_tables(shadow_sampler *s, const uint64_t *ptr_host, const uint32_t *neighs_host,
+                                  const float *scores_host);
+/* preproc_ppr_approximate (PS.cpp:237-344): loads the binary cache if its header matches (PS.cpp:145-231),
+ * otherwise runs the float32 forward push on the GPU (bit-exact with the reference order of operations)
+ * and writes the cache (PS.cpp:94-139).  Empty / NULL file names => no cache. */
+int shadow_sampler_preproc_ppr_approximate(shadow_sampler *s, const uint32_t *targets_host, uint64_t num_targets,
+                                           int k, float alpha, float epsilon,
+                                           const char *fname_neighs, const char *fname_scores);
+/* read back the installed tables (row of node v) -- for tests and cache inspection */
+int shadow_sampler_get_ppr_row(shadow_sampler *s, uint32_t v, uint32_t cap, uint32_t *neighs_host, float *scores_host,
+                               uint32_t *len_out);
+
+/* parallel_sampler_ensemble (PS.cpp:662-704): advances the root cursor (_get_roots_p, PS.cpp:456-468), samples
+ * every ensemble branch on the same roots and leaves the results in HBM.  Asynchronous w.r.t. the host. */
+int shadow_sampler_sample(shadow_sampler *s, const shadow_sampler_cfg *cfgs, int num_cfgs);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* results == SubgraphStructVec (G.h:59-97) of the latest call, one per ensemble branch, kept in   */
+/* HBM as ONE block-diagonal batch (what Subgraph.cat_to_block_diagonal, frontend/graph.py:280-320, */
+/* builds on the host in the reference):                                                           */
+/*   node_ptr[P+1], edge_ptr[P+1]   exclusive prefix sums of |V_s|, |E_s|                          */
+/*   rowptr[N_tot+1]                CSR row pointer of the whole batch (== concatenated indptr)     */
+/*   indices[E_tot]                 BATCH-global column ids (local id + node_ptr[s])                */
+/*   orig_node[N_tot], orig_edge[E_tot], ppr[N_tot], hop[N_tot], drnl[N_tot]                        */
+/*   target[P*num_roots]            BATCH-global row of each root                                  */
+/* ---------------------------------------------------------------------------------------------- */
+enum { SHADOW_F_NODE_PTR = 0, SHADOW_F_EDGE_PTR = 1, SHADOW_F_ROWPTR = 2, SHADOW_F_INDICES = 3,
+       SHADOW_F_ORIG_NODE = 4, SHADOW_F_ORIG_EDGE = 5, SHADOW_F_TARGET = 6, SHADOW_F_PPR = 7,
+       SHADOW_F_HOP = 8, SHADOW_F_DRNL = 9, SHADOW_F_NUM_TARGET = 10, SHADOW_NUM_FIELDS = 11 };
+
+typedef struct {
+  int32_t num_subg;        /* get_num_valid_subg() (G.cpp:92-94) */
+  int32_t num_roots;
+  int64_t total_nodes, total_edges;
+  int32_t has_csr;         /* 0 for return_target_only */
+  int32_t has_hop, has_ppr, has_drnl;
+  int64_t rand_draws;      /* rand() outputs consumed by this branch (glibc mode) */
+} shadow_batch_info;
+
+/* synchronises the sampler's stream, validates capacities (re-running with larger buffers if needed) */
+int shadow_sampler_batch_info(shadow_sampler *s, int branch, shadow_batch_info *info);
+/* device pointer + element count of one field of the latest batch (valid until num_ring further calls) */
+int shadow_sampler_batch_field_dev(shadow_sampler *s, int branch, int field, void **ptr_dev, int64_t *count);
+/* copy one field to the host; 4 bytes per element */
+int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, int field, void *dst_host, int64_t count);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* feature gather: feat_full[subgs.node] (shaDow/minibatch.py:469).  out[i,:] = feat[ids[i],:]      */
+/* ---------------------------------------------------------------------------------------------- */
+int shadow_gather_rows_f32(const float *feat_dev, int64_t num_rows, int32_t dim, const uint32_t *ids_dev,
+                           int64_t n, float *out_dev, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHADOW_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of libshadow_b200.so (C ABI: include/shadow_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at import time, and every
+compute entry point of the library fails with SHADOW_ECUDA when no device is visible.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshadow_b200.so")
+
+
+class ShadowError(RuntimeError):
+    pass
+
+
+class SamplerCfg(C.Structure):
+    """shadow_sampler_cfg"""
+    _fields_ = [("method", C.c_int32), ("num_roots", C.c_int32), ("depth", C.c_int32), ("budget", C.c_int32),
+                ("k", C.c_int32), ("threshold", C.c_float), ("add_self_edge", C.c_int32),
+                ("include_target_conn", C.c_int32), ("return_target_only", C.c_int32), ("aug", C.c_int32),
+                ("fixed_mode", C.c_int32), ("rng_mode", C.c_int32)]
+
+
+class BatchInfo(C.Structure):
+    """shadow_batch_info"""
+    _fields_ = [("num_subg", C.c_int32), ("num_roots", C.c_int32), ("total_nodes", C.c_int64),
+                ("total_edges", C.c_int64), ("has_csr", C.c_int32), ("has_hop", C.c_int32), ("has_ppr", C.c_int32),
+                ("has_drnl", C.c_int32), ("rand_draws", C.c_int64)]
+
+
+METHOD = {"khop": 0, "ppr": 1, "ppr_st": 2, "nodeIID": 3}
+AUG = {"hops": 1, "pprs": 2, "drnls": 4}
+RNG_GLIBC, RNG_PHILOX = 0, 1
+(F_NODE_PTR, F_EDGE_PTR, F_ROWPTR, F_INDICES, F_ORIG_NODE, F_ORIG_EDGE, F_TARGET, F_PPR, F_HOP, F_DRNL,
+ F_NUM_TARGET) = range(11)
+
+# every symbol include/shadow_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "shadow_last_error", "shadow_version",
+    "shadow_sampler_create", "shadow_sampler_create_dev", "shadow_sampler_destroy", "shadow_sampler_set_stream",
+    "shadow_sampler_num_nodes", "shadow_sampler_num_edges", "shadow_sampler_num_nodes_target",
+    "shadow_sampler_get_idx_root", "shadow_sampler_set_num_per_batch", "shadow_sampler_shuffle_targets",
+    "shadow_sampler_shuffle_targets_dev", "shadow_sampler_reseed", "shadow_sampler_drop_full_graph_info",
+    "shadow_sampler_set_ppr_tables", "shadow_sampler_preproc_ppr_approximate", "shadow_sampler_get_ppr_row",
+    "shadow_sampler_sample", "shadow_sampler_batch_info", "shadow_sampler_batch_field_dev",
+    "shadow_sampler_batch_field_host", "shadow_gather_rows_f32",
+]
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(shadow_gnn_b200/csrc/build.sh).  shadow_gnn_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+_vp, _i, _u32, _u64, _i64, _f, _cp = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, C.c_float, C.c_char_p
+
+lib.shadow_last_error.restype = _cp
+lib.shadow_sampler_create.argtypes = [_vp, _vp, _u32, _u32, _cp, _cp, _i, _i, _i, _i, _i, C.POINTER(_vp)]
+lib.shadow_sampler_create_dev.argtypes = [_vp, _vp, _u32, _u32, _i, _i, _i, _i, _i, C.POINTER(_vp)]
+lib.shadow_sampler_destroy.argtypes = [_vp]
+lib.shadow_sampler_set_stream.argtypes = [_vp, _vp]
+for _n in ("num_nodes", "num_edges", "num_nodes_target", "get_idx_root"):
+    getattr(lib, f"shadow_sampler_{_n}").argtypes = [_vp]
+    getattr(lib, f"shadow_sampler_{_n}").restype = _u32
+lib.shadow_sampler_set_num_per_batch.argtypes = [_vp, _i]
+lib.shadow_sampler_shuffle_targets.argtypes = [_vp, _vp, _u32]
+lib.shadow_sampler_shuffle_targets_dev.argtypes = [_vp, _vp, _u32]
+lib.shadow_sampler_reseed.argtypes = [_vp, _i]
+lib.shadow_sampler_drop_full_graph_info.argtypes = [_vp]
+lib.shadow_sampler_set_ppr_tables.argtypes = [_vp, _vp, _vp, _vp]
+lib.shadow_sampler_preproc_ppr_approximate.argtypes = [_vp, _vp, _u64, _i, _f, _f, _cp, _cp]
+lib.shadow_sampler_get_ppr_row.argtypes = [_vp, _u32, _u32, _vp, _vp, C.POINTER(_u32)]
+lib.shadow_sampler_sample.argtypes = [_vp, C.POINTER(SamplerCfg), _i]
+lib.shadow_sampler_batch_info.argtypes = [_vp, _i, C.POINTER(BatchInfo)]
+lib.shadow_sampler_batch_field_dev.argtypes = [_vp, _i, _i, C.POINTER(_vp), C.POINTER(_i64)]
+lib.shadow_sampler_batch_field_host.argtypes = [_vp, _i, _i, _vp, _i64]
+lib.shadow_gather_rows_f32.argtypes = [_vp, _i64, C.c_int32, _vp, _i64, _vp, _vp]
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib.shadow_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(msg)
+        raise ShadowError(f"libshadow_b200 error {rc}: {msg}")
+    return rc

@@ -1,0 +1,521 @@
+// sampler_kernels.cuh -- fused subgraph extraction + node-induced CSR relabelling for sm_100a.
+//
+// One CTA builds one subgraph (root group) end to end, entirely on-chip except for the full-graph
+// reads and the final output writes:
+//   A. node-set selection     ppr: top-k row of the PPR table + relative threshold      (PS.cpp:565-595)
+//                             khop: level-by-level expansion with per-level dedup        (PS.cpp:510-556)
+//                             nodeIID: the roots                                         (PS.cpp:498-508)
+//   B. sort ids, build the orig->sub hash in shared memory                               (PS.cpp:359-377)
+//   C. count pass over the full-graph rows of the selected nodes (warp per row, coalesced),
+//      block scan -> local indptr, decoupled look-back across CTAs -> batch-global offsets,
+//      fill pass (rows re-read from L2) writing the block-diagonal CSR in place           (PS.cpp:379-431)
+//   D. optional in-subgraph BFS for the hop / drnl labels                                (G.cpp:32-73)
+// CTAs are persistent and take subgraphs from a ticket counter, so the look-back never waits on a
+// CTA that has not started.  The batch layout written here is what the reference assembles on the host
+// in Subgraph.cat_to_block_diagonal (frontend/graph.py:280-320).
+#pragma once
+#include "common.cuh"
+
+#define SHADOW_MAX_ROOTS 4
+#define SAMPLER_BLOCK 128
+
+struct WsLayout {          // byte offsets of the per-CTA workspace (shared memory, or global for huge scopes)
+  uint32_t keys, cval, nodes, pprv, hkeys, hvals, row_s, row_e, row_cnt, row_ins, level, all, dist, fr_a, fr_b;
+  uint32_t bytes;
+};
+
+struct SampleParams {
+  // full graph (a1: GraphStruct, G.h:19-39)
+  const uint32_t *indptr, *indices;
+  uint32_t num_nodes, num_edges;
+  // roots of this call: nodes_target[idx_start .. idx_end)
+  const uint32_t *roots;
+  int num_root_ids, num_subg;
+  // config
+  int method, num_roots, depth, budget, k;
+  float threshold;
+  int add_self, tconn, aug, fixed_mode, rng_mode;
+  int count_only_last;               // glibc prepass: build levels < depth-1, only count the draws of the last
+  // PPR tables (a7)
+  const unsigned long long *ppr_ptr;
+  const uint32_t *ppr_neighs;
+  const float *ppr_scores;
+  // random streams
+  const uint32_t *rand_stream;       // glibc replay: pre-generated rand() outputs
+  long long *rand_off;               // [num_subg+1] stream offset of each subgraph (written by the prepass)
+  uint32_t philox_seed, philox_epoch, root_slot_base;
+  // per-subgraph capacities
+  int ncap, ccap, ccap2, acap, acap2, hcap, hshift;
+  WsLayout L;
+  unsigned char *gws;                // global workspace (GWS variant)
+  unsigned long long gws_stride;
+  // outputs (batch-global block-diagonal CSR)
+  long long cap_nodes, cap_edges;
+  int *node_ptr, *edge_ptr, *rowptr, *indices_out, *target, *num_target;
+  uint32_t *orig_node, *orig_edge, *hop, *drnl;
+  float *ppr_out;
+  // inter-CTA state
+  unsigned long long *status_n, *status_m;   // decoupled look-back words: flag<<62 | value
+  uint32_t *ticket;
+  long long *totals;                 // [0]=nodes [1]=edges [2]=error bits
+};
+
+enum { ERR_WS_OVERFLOW = 1, ERR_OUT_OVERFLOW = 2 };
+
+struct Ws {
+  unsigned long long *keys; float *cval; uint32_t *nodes; float *pprv; uint32_t *hkeys, *hvals, *row_s, *row_e, *row_cnt,
+      *row_ins, *level, *all, *dist, *fr_a, *fr_b;
+};
+__device__ __forceinline__ Ws make_ws(unsigned char *b, const WsLayout &L) {
+  Ws w;
+  w.keys = (unsigned long long *)(b + L.keys); w.cval = (float *)(b + L.cval);
+  w.nodes = (uint32_t *)(b + L.nodes); w.pprv = (float *)(b + L.pprv);
+  w.hkeys = (uint32_t *)(b + L.hkeys); w.hvals = (uint32_t *)(b + L.hvals);
+  w.row_s = (uint32_t *)(b + L.row_s); w.row_e = (uint32_t *)(b + L.row_e);
+  w.row_cnt = (uint32_t *)(b + L.row_cnt); w.row_ins = (uint32_t *)(b + L.row_ins);
+  w.level = (uint32_t *)(b + L.level); w.all = (uint32_t *)(b + L.all);
+  w.dist = (uint32_t *)(b + L.dist); w.fr_a = (uint32_t *)(b + L.fr_a); w.fr_b = (uint32_t *)(b + L.fr_b);
+  return w;
+}
+
+// ordered stream compaction over i in [0,n): emit(i, rank) for every i with pred(i); returns the count
+template <class Pred, class Emit>
+__device__ inline uint32_t block_ordered_compact(int n, Pred pred, Emit emit, uint32_t *warp_sums) {
+  const int lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+  uint32_t carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    bool f = (i < n) && pred(i);
+    uint32_t mask = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_sums[w] = __popc(mask);
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+    for (int j = 0; j < nw; j++) { uint32_t c = warp_sums[j]; if (j < w) woff += c; tot += c; }
+    if (f) emit(i, carry + woff + __popc(mask & lanemask_lt()));
+    carry += tot;
+    __syncthreads();
+  }
+  return carry;
+}
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
+__device__ __forceinline__ uint32_t hash_lookup(const uint32_t *hk, const uint32_t *hv, uint32_t mask, int shift, uint32_t key) {
+  uint32_t h = hash_slot(key, shift);
+  for (;;) {
+    uint32_t k = hk[h];
+    if (k == key) return hv[h];
+    if (k == NONE32) return NONE32;
+    h = (h + 1) & mask;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A. node-set builders.  On return ws.nodes[0..n) is sorted ascending & unique, ws.pprv holds the ppr column.
+// ------------------------------------------------------------------------------------------------
+__device__ inline int finish_sorted_pairs(const Ws &ws, int ncand, int cap, uint32_t *warp_sums) {
+  // ws.keys[0..ncand) = (id << 32 | seq); last write wins (unordered_map operator[]=, PS.cpp:574-587)
+  int np2 = next_pow2(ncand);
+  for (int i = ncand + threadIdx.x; i < np2; i += blockDim.x) ws.keys[i] = ~0ull;
+  __syncthreads();
+  block_bitonic_sort(ws.keys, np2);
+  const unsigned long long *keys = ws.keys;
+  return (int)block_ordered_compact(
+      ncand, [&](int i) { return i == ncand - 1 || (uint32_t)(keys[i + 1] >> 32) != (uint32_t)(keys[i] >> 32); },
+      [&](int i, uint32_t r) { if ((int)r < cap) { ws.nodes[r] = (uint32_t)(keys[i] >> 32); ws.pprv[r] = ws.cval[(uint32_t)keys[i]]; } }, warp_sums);
+}
+
+__device__ inline int build_nodes_ppr(const SampleParams &P, const Ws &ws, const uint32_t *roots, int nt, uint32_t *s_cut,
+                                      uint32_t *warp_sums) {
+  int ncand = 0;
+  for (int it = 0; it < nt; it++) {
+    const uint32_t t = roots[it];
+    const unsigned long long off = P.ppr_ptr[t];
+    const long long len_all = (long long)(P.ppr_ptr[t + 1] - off);
+    const int size_neigh = (int)(len_all < (long long)P.k ? len_all : (long long)P.k);            // PS.cpp:576
+    const float max_ppr = size_neigh > 1 ? P.ppr_scores[off + 1] : 0.f;                          // :578-579
+    if (threadIdx.x == 0) {
+      ws.keys[ncand] = ((unsigned long long)t << 32) | (uint32_t)ncand; ws.cval[ncand] = -1.f;   // :574
+      *s_cut = (uint32_t)size_neigh;
+    }
+    ncand++;
+    if (size_neigh <= 1 && len_all > 0) {                                                        // :581
+      if (threadIdx.x == 0) { ws.keys[ncand] = ((unsigned long long)t << 32) | (uint32_t)ncand; ws.cval[ncand] = P.ppr_scores[off]; }
+      ncand++;
+    }
+    __syncthreads();
+    // first index that fails the relative threshold (:584); evaluated per entry, min over entries
+    for (int i = threadIdx.x; i < size_neigh; i += blockDim.x) {
+      float s = P.ppr_scores[off + i];
+      if (max_ppr == 0.f || __fdiv_rn(s, max_ppr) < P.threshold) atomicMin(s_cut, (uint32_t)i);
+    }
+    __syncthreads();
+    const int cut = (int)*s_cut;
+    for (int i = threadIdx.x; i < cut; i += blockDim.x) {                                        // :587
+      ws.keys[ncand + i] = ((unsigned long long)P.ppr_neighs[off + i] << 32) | (uint32_t)(ncand + i);
+      ws.cval[ncand + i] = P.ppr_scores[off + i];
+    }
+    ncand += cut;
+    __syncthreads();
+  }
+  return finish_sorted_pairs(ws, ncand, P.ncap, warp_sums);
+}
+
+// sort + unique of a[0..n) (uint32), result written to out[0..cap); returns the (uncapped) count
+__device__ inline int sort_unique_u32(uint32_t *a, int n, uint32_t *out, int cap, uint32_t *warp_sums) {
+  int np2 = next_pow2(n);
+  for (int i = n + threadIdx.x; i < np2; i += blockDim.x) a[i] = NONE32;
+  __syncthreads();
+  block_bitonic_sort(a, np2);
+  return (int)block_ordered_compact(
+      n, [&](int i) { return i == 0 || a[i - 1] != a[i]; }, [&](int i, uint32_t r) { if ((int)r < cap) out[r] = a[i]; }, warp_sums);
+}
+
+// khop (PS.cpp:510-556).  Returns n (or -1 on workspace overflow); *draws_out = rand() outputs consumed.
+__device__ inline int build_nodes_khop(const SampleParams &P, const Ws &ws, const uint32_t *roots, int nt, int p,
+                                       long long rand_base, long long *draws_out, uint32_t *warp_sums, int *s_n) {
+  uint32_t *raw = (uint32_t *)ws.keys;     // the 64-bit sort buffer doubles as the raw frontier buffer
+  if (threadIdx.x == 0) {                  // level 0 = std::set of the roots (:518-522)
+    int n = 0;
+    for (int i = 0; i < nt; i++) {
+      uint32_t v = roots[i]; int j = 0;
+      while (j < n && ws.level[j] < v) j++;
+      if (j < n && ws.level[j] == v) continue;
+      for (int q = n; q > j; q--) ws.level[q] = ws.level[q - 1];
+      ws.level[j] = v; n++;
+    }
+    for (int i = 0; i < n; i++) ws.all[i] = ws.level[i];
+    *s_n = n;
+  }
+  __syncthreads();
+  int n_level = *s_n, n_all = n_level;
+  long long rcur = rand_base, draws = 0;
+  const uint32_t ubudget = (uint32_t)P.budget;
+  const uint32_t root_slot = P.root_slot_base + (uint32_t)p;
+  for (int lvl = 0; lvl < P.depth; lvl++) {                                                      // :524-540
+    for (int i = threadIdx.x; i < n_level; i += blockDim.x) {
+      uint32_t v = ws.level[i], s = P.indptr[v], deg = P.indptr[v + 1] - s;
+      bool take_all = (P.budget < 0) || (deg <= ubudget);                                        // :528 (unsigned compare)
+      ws.row_s[i] = s; ws.row_e[i] = deg;
+      ws.row_cnt[i] = take_all ? deg : ubudget;
+      ws.row_ins[i] = take_all ? 0u : ubudget;
+    }
+    __syncthreads();
+    uint32_t total_raw = block_exclusive_scan(ws.row_cnt, n_level, warp_sums);
+    uint32_t total_draws = block_exclusive_scan(ws.row_ins, n_level, warp_sums);
+    draws += total_draws;
+    if (P.count_only_last && lvl == P.depth - 1) break;
+    if (total_raw > (uint32_t)P.ccap) return -1;
+    for (int i = warp_id(); i < n_level; i += (blockDim.x >> 5)) {
+      const uint32_t v = ws.level[i], s = ws.row_s[i], deg = ws.row_e[i], o = ws.row_cnt[i];
+      const uint32_t cnt = ((i + 1 < n_level) ? ws.row_cnt[i + 1] : total_raw) - o;
+      const bool take_all = (P.budget < 0) || (deg <= ubudget);
+      for (uint32_t j = lane_id(); j < cnt; j += 32) {
+        uint32_t idx = j;
+        if (!take_all) {
+          if (P.rng_mode == SHADOW_RNG_GLIBC) idx = P.rand_stream[rcur + ws.row_ins[i] + j] % deg;   // rand()%deg (:534)
+          else idx = __umulhi(philox4x32_10_x(v, (uint32_t)lvl, j, root_slot, P.philox_seed, P.philox_epoch), deg);
+        }
+        raw[o + j] = P.indices[s + idx];
+      }
+    }
+    rcur += total_draws;
+    __syncthreads();
+    n_level = sort_unique_u32(raw, (int)total_raw, ws.level, P.ncap, warp_sums);                          // std::set frontier
+    if (n_level > P.ncap || n_all + n_level > P.acap) return -1;
+    for (int i = threadIdx.x; i < n_level; i += blockDim.x) ws.all[n_all + i] = ws.level[i];
+    n_all += n_level;
+    __syncthreads();
+  }
+  *draws_out = draws;
+  if (P.count_only_last) return 0;
+  int n = sort_unique_u32(ws.all, n_all, ws.nodes, P.ncap, warp_sums);                                    // union of the levels (:542-547)
+  if (n > P.ncap) return -1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ws.pprv[i] = -1.f;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoupled look-back over subgraph tickets: exclusive prefix of (n, m)
+// ------------------------------------------------------------------------------------------------
+#define LB_AGG  (1ull << 62)
+#define LB_INCL (2ull << 62)
+#define LB_VAL  ((1ull << 62) - 1)
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// called by warp 0; returns the exclusive prefix in all lanes of warp 0
+__device__ inline unsigned long long lookback_exclusive(unsigned long long *status, int p, unsigned long long mine) {
+  const int lane = lane_id();
+  if (p == 0) {
+    if (lane == 0) st_volatile_u64(&status[0], LB_INCL | mine);
+    return 0;
+  }
+  if (lane == 0) st_volatile_u64(&status[p], LB_AGG | mine);
+  unsigned long long excl = 0;
+  int idx = p - 1;
+  for (;;) {
+    const int q = idx - lane;
+    unsigned long long st = LB_INCL;     // lanes past the beginning act as a zero inclusive prefix
+    if (q >= 0) { do { st = ld_volatile_u64(&status[q]); } while ((st >> 62) == 0); }
+    const uint32_t incl_mask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+    const int first = incl_mask ? __ffs(incl_mask) - 1 : 32;    // nearest predecessor with an inclusive prefix
+    unsigned long long v = (lane <= first) ? (st & LB_VAL) : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    excl += v;
+    if (incl_mask) break;
+    idx -= 32;
+  }
+  if (lane == 0) st_volatile_u64(&status[p], LB_INCL | (excl + mine));
+  return excl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// D. BFS inside the just-written subgraph CSR (compute_hops, G.cpp:32-64); level-synchronous
+// ------------------------------------------------------------------------------------------------
+__device__ inline void subgraph_bfs(const SampleParams &P, const Ws &ws, int n, uint32_t src, long long node_base,
+                                    const uint32_t *loc_indptr, long long edge_base, uint32_t *dist, uint32_t *s_cnt) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dist[i] = NONE32;
+  __syncthreads();
+  if (threadIdx.x == 0) { dist[src] = 0; ws.fr_a[0] = src; *s_cnt = 0; }
+  __syncthreads();
+  uint32_t *cur = ws.fr_a, *nxt = ws.fr_b;
+  int ncur = 1;
+  for (uint32_t lvl = 0; ncur > 0; lvl++) {
+    for (int i = warp_id(); i < ncur; i += (blockDim.x >> 5)) {
+      const uint32_t u = cur[i];
+      const uint32_t s = loc_indptr[u], e = loc_indptr[u + 1];
+      for (uint32_t j = s + lane_id(); j < e; j += 32) {
+        uint32_t c = (uint32_t)(P.indices_out[edge_base + j] - (int)node_base);
+        if (atomicCAS(&dist[c], NONE32, lvl + 1) == NONE32) nxt[atomicAdd(s_cnt, 1u)] = c;
+      }
+    }
+    __syncthreads();
+    ncur = (int)*s_cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) *s_cnt = 0;
+    uint32_t *t = cur; cur = nxt; nxt = t;
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ uint32_t drnl_single(uint32_t dx, uint32_t dy) {      // G.cpp:66-73, uint32 arithmetic
+  if (dx >= 255u || dy >= 255u) return 255u;
+  uint32_t d = dx + dy, mn = dx < dy ? dx : dy;
+  return 1u + mn + (d / 2u) * ((d / 2u) + (d % 2u) - 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused kernel
+// ------------------------------------------------------------------------------------------------
+template <bool GWS>
+__global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const SampleParams P) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __shared__ uint32_t s_warp_sums[33];
+  __shared__ int s_p, s_n;
+  __shared__ uint32_t s_cnt, s_cut;
+  __shared__ long long s_base[2];
+  __shared__ uint32_t s_roots[SHADOW_MAX_ROOTS], s_tl[SHADOW_MAX_ROOTS];
+
+  unsigned char *wsb = GWS ? (P.gws + (size_t)blockIdx.x * P.gws_stride) : smem_dyn;
+  const Ws ws = make_ws(wsb, P.L);
+  const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
+  const uint32_t hmask = (uint32_t)P.hcap - 1u;
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_p = (int)atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const int p = s_p;
+    if (p >= P.num_subg) break;
+    const int r0 = p * P.num_roots;
+    const int nt = min(P.num_roots, P.num_root_ids - r0);
+    if (threadIdx.x < nt) s_roots[threadIdx.x] = P.roots[r0 + threadIdx.x];
+    __syncthreads();
+
+    // ---------------- A: node set ----------------
+    int n = 0;
+    long long draws = 0;
+    if (P.method == SHADOW_PPR) {
+      n = build_nodes_ppr(P, ws, s_roots, nt, &s_cut, s_warp_sums);
+    } else if (P.method == SHADOW_KHOP) {
+      long long rb = (P.rng_mode == SHADOW_RNG_GLIBC && P.rand_off) ? P.rand_off[p] : 0;
+      n = build_nodes_khop(P, ws, s_roots, nt, p, rb, &draws, s_warp_sums, &s_n);
+    } else {   // nodeIID (PS.cpp:498-508)
+      if (threadIdx.x == 0) {
+        int m = 0;
+        for (int i = 0; i < nt; i++) {
+          uint32_t v = s_roots[i]; int j = 0;
+          while (j < m && ws.nodes[j] < v) j++;
+          if (j < m && ws.nodes[j] == v) continue;
+          for (int q = m; q > j; q--) ws.nodes[q] = ws.nodes[q - 1];
+          ws.nodes[j] = v; m++;
+        }
+        for (int i = 0; i < m; i++) ws.pprv[i] = -1.f;
+        s_n = m;
+      }
+      __syncthreads();
+      n = s_n;
+    }
+    bool ws_overflow = (n < 0) || (n > P.ncap);
+    if (ws_overflow) n = 0;
+    __syncthreads();
+
+    // ---------------- B: orig -> sub hash, targets, row extents ----------------
+    for (int i = threadIdx.x; i < P.hcap; i += blockDim.x) ws.hkeys[i] = NONE32;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t v = ws.nodes[i];
+      uint32_t h = hash_slot(v, P.hshift);
+      while (atomicCAS(&ws.hkeys[h], NONE32, v) != NONE32) h = (h + 1) & hmask;
+      ws.hvals[h] = (uint32_t)i;
+      const uint32_t s = P.indptr[v];
+      ws.row_s[i] = s; ws.row_e[i] = P.indptr[v + 1];
+    }
+    __syncthreads();
+    if (threadIdx.x < nt) {
+      uint32_t t = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, s_roots[threadIdx.x]);
+      s_tl[threadIdx.x] = (t == NONE32) ? 0u : t;          // operator[] default-inserts 0 (PS.cpp:375)
+    }
+    const bool tconn = P.tconn || nt == 1;                 // PS.cpp:356-358
+    const bool add_self = P.add_self != 0;
+
+    // ---------------- C1: count pass (warp per row) ----------------
+    for (int r = warp; r < n; r += nwarp) {
+      const uint32_t v = ws.nodes[r], s = ws.row_s[r], e = ws.row_e[r];
+      bool v_is_t = false;
+      if (!tconn) for (int j = 0; j < nt; j++) v_is_t |= (s_roots[j] == v);
+      uint32_t kept = 0, kept_less = 0;
+      bool present = false;
+      for (uint32_t base = s; base < e; base += 32) {
+        const uint32_t c = base + lane;
+        bool keep = false, less = false, self = false;
+        if (c < e) {
+          const uint32_t nb = ldg_stream_u32(P.indices + c);
+          keep = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb) != NONE32;
+          if (keep && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); keep = !nb_t; }   // :412-418
+          less = keep && nb < v; self = (nb == v);
+        }
+        kept += __popc(__ballot_sync(0xffffffffu, keep));
+        if (add_self) { kept_less += __popc(__ballot_sync(0xffffffffu, less)); present |= __any_sync(0xffffffffu, self); }
+      }
+      const bool inserting = add_self && !present;         // :386-400
+      if (!inserting && !P.fixed_mode && e < P.num_edges) {
+        // PS.cpp:401: the row bound is idx_end + 1 even without an insertion => slot `e` (first slot of the next row) is tested too
+        const uint32_t nb = P.indices[e];
+        bool keep = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb) != NONE32;
+        if (keep && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); keep = !nb_t; }
+        kept += keep ? 1u : 0u;
+      }
+      if (lane == 0) { ws.row_cnt[r] = kept + (inserting ? 1u : 0u); ws.row_ins[r] = inserting ? kept_less : NONE32; }
+    }
+    __syncthreads();
+    const uint32_t m = block_exclusive_scan(ws.row_cnt, n, s_warp_sums);      // local indptr (:428-431)
+    if (threadIdx.x == 0) ws.row_cnt[n] = m;
+
+    // ---------------- look-back: batch-global offsets ----------------
+    if (warp == 0) {
+      unsigned long long nb = lookback_exclusive(P.status_n, p, (unsigned long long)n);
+      unsigned long long eb = lookback_exclusive(P.status_m, p, (unsigned long long)m);
+      if (lane == 0) { s_base[0] = (long long)nb; s_base[1] = (long long)eb; }
+    }
+    __syncthreads();
+    const long long node_base = s_base[0], edge_base = s_base[1];
+    const bool out_overflow = (node_base + n > P.cap_nodes) || (edge_base + (long long)m > P.cap_edges);
+    if (threadIdx.x == 0) {
+      if (ws_overflow) atomicOr((unsigned long long *)&P.totals[2], (unsigned long long)ERR_WS_OVERFLOW);
+      if (out_overflow) atomicOr((unsigned long long *)&P.totals[2], (unsigned long long)ERR_OUT_OVERFLOW);
+      if (p == P.num_subg - 1) { P.totals[0] = node_base + n; P.totals[1] = edge_base + (long long)m; }
+    }
+    if (!out_overflow) {
+      if (threadIdx.x == 0) {
+        P.node_ptr[p] = (int)node_base; P.edge_ptr[p] = (int)edge_base; P.num_target[p] = nt;
+        if (p == P.num_subg - 1) { P.node_ptr[p + 1] = (int)(node_base + n); P.edge_ptr[p + 1] = (int)(edge_base + m); P.rowptr[node_base + n] = (int)(edge_base + m); }
+      }
+      if (threadIdx.x < P.num_roots) P.target[r0 + threadIdx.x] = (threadIdx.x < nt) ? (int)(node_base + s_tl[threadIdx.x]) : -1;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        P.orig_node[node_base + i] = ws.nodes[i];
+        P.ppr_out[node_base + i] = ws.pprv[i];
+        P.rowptr[node_base + i] = (int)(edge_base + ws.row_cnt[i]);
+      }
+      // ---------------- C2: fill pass (rows come back from L2) ----------------
+      for (int r = warp; r < n; r += nwarp) {
+        const uint32_t v = ws.nodes[r], s = ws.row_s[r], e = ws.row_e[r];
+        bool v_is_t = false;
+        if (!tconn) for (int j = 0; j < nt; j++) v_is_t |= (s_roots[j] == v);
+        const uint32_t ins = ws.row_ins[r];
+        const bool inserting = ins != NONE32;
+        const long long obase = edge_base + ws.row_cnt[r];
+        uint32_t kept = 0;
+        for (uint32_t base = s; base < e; base += 32) {
+          const uint32_t c = base + lane;
+          uint32_t sub = NONE32, nb = 0;
+          if (c < e) {
+            nb = P.indices[c];
+            sub = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb);
+            if (sub != NONE32 && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); if (nb_t) sub = NONE32; }
+          }
+          const uint32_t mask = __ballot_sync(0xffffffffu, sub != NONE32);
+          if (sub != NONE32) {
+            const uint32_t pos = kept + __popc(mask & lanemask_lt()) + ((inserting && nb > v) ? 1u : 0u);
+            P.indices_out[obase + pos] = (int)(node_base + sub);
+            P.orig_edge[obase + pos] = c;                                                        // :422
+          }
+          kept += __popc(mask);
+        }
+        if (inserting) {
+          if (lane == 0) { P.indices_out[obase + ins] = (int)(node_base + r); P.orig_edge[obase + ins] = NONE32; }   // :406-411
+        } else if (!P.fixed_mode && e < P.num_edges) {
+          const uint32_t nb = P.indices[e];
+          uint32_t sub = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb);
+          if (sub != NONE32 && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); if (nb_t) sub = NONE32; }
+          if (sub != NONE32 && lane == 0) { P.indices_out[obase + kept] = (int)(node_base + sub); P.orig_edge[obase + kept] = e; }
+        }
+      }
+      // ---------------- D: hop / drnl labels ----------------
+      if ((P.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) && n > 0) {
+        __syncthreads();       // this CTA's CSR writes are visible to the whole CTA
+        if (P.aug & SHADOW_AUG_DRNLS) {                                                          // PS.cpp:438-451
+          subgraph_bfs(P, ws, n, s_tl[0], node_base, ws.row_cnt, edge_base, ws.dist, &s_cnt);
+          for (int i = threadIdx.x; i < n; i += blockDim.x) ws.pprv[i] = __uint_as_float(ws.dist[i]);   // dx parked in pprv (already written out)
+          __syncthreads();
+          subgraph_bfs(P, ws, n, s_tl[nt > 1 ? 1 : 0], node_base, ws.row_cnt, edge_base, ws.dist, &s_cnt);
+          for (int i = threadIdx.x; i < n; i += blockDim.x)
+            P.drnl[node_base + i] = drnl_single(__float_as_uint(ws.pprv[i]), ws.dist[i]);
+        } else {                                                                                 // PS.cpp:433-436
+          subgraph_bfs(P, ws, n, s_tl[0], node_base, ws.row_cnt, edge_base, ws.dist, &s_cnt);
+          for (int i = threadIdx.x; i < n; i += blockDim.x) P.hop[node_base + i] = ws.dist[i];
+        }
+      }
+    }
+  }
+}
+
+// glibc-replay prepass: ONE CTA walks the subgraphs in order and fixes the rand() offset of each
+// (the stream position of subgraph p+1 depends on how many high-degree nodes subgraph p met)
+__global__ void __launch_bounds__(SAMPLER_BLOCK) khop_rand_offsets_kernel(const SampleParams P) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __shared__ uint32_t s_warp_sums[33];
+  __shared__ int s_n;
+  __shared__ uint32_t s_roots[SHADOW_MAX_ROOTS];
+  unsigned char *wsb = P.gws ? P.gws : smem_dyn;
+  const Ws ws = make_ws(wsb, P.L);
+  long long cursor = 0;
+  for (int p = 0; p < P.num_subg; p++) {
+    __syncthreads();
+    const int r0 = p * P.num_roots;
+    const int nt = min(P.num_roots, P.num_root_ids - r0);
+    if (threadIdx.x < nt) s_roots[threadIdx.x] = P.roots[r0 + threadIdx.x];
+    if (threadIdx.x == 0) P.rand_off[p] = cursor;
+    __syncthreads();
+    long long draws = 0;
+    int n = build_nodes_khop(P, ws, s_roots, nt, p, cursor, &draws, s_warp_sums, &s_n);
+    if (n < 0) { if (threadIdx.x == 0) atomicOr((unsigned long long *)&P.totals[2], (unsigned long long)ERR_WS_OVERFLOW); }
+    cursor += draws;
+  }
+  if (threadIdx.x == 0) P.rand_off[P.num_subg] = cursor;
+}

@@ -1,0 +1,270 @@
+"""GPU parity tests (-m gpu): the CUDA sampler, called through the C ABI (ctypes), against
+ (1) the golden vectors produced by the unmodified reference, (2) the CPU oracle on seeded random inputs,
+ (3) size-independent properties at larger sizes.   Integer / index outputs: bit-exact.  ppr column: bit pattern."""
+import itertools
+
+import numpy as np
+import pytest
+
+from tests.common import Golden, assert_subgraph_equal, FIELDS
+
+pytestmark = pytest.mark.gpu
+
+
+def _product():
+    import shadow_gnn_b200.ParallelSampler as PS
+    return PS
+
+
+def _subgraphs(vec):
+    return [{f: vec.numpy(f)[p] for f in FIELDS} for p in range(vec.get_num_valid_subg())]
+
+
+G = Golden()
+
+
+@pytest.mark.parametrize("ci", range(G.num_cases))
+def test_cuda_matches_reference_golden(ci):
+    PS = _product()
+    cfg, aug, targets, calls, want = G.case(ci)
+    if cfg["method"] == "ppr_st":
+        pytest.skip("ppr_st not implemented yet")
+    s = PS.ParallelSampler(G.indptr, G.indices, [], G.meta["P"], 1, True, True, [], 1, "", "", "", G.meta["seed"])
+    s.shuffle_targets(targets)
+    if cfg["method"] in ("ppr", "ppr_st"):
+        s.set_ppr_tables(G.ppr_ptr, G.ppr_neighs, G.ppr_scores)
+    got = []
+    for ncall in calls:
+        vec = s.parallel_sampler_ensemble([cfg], [set(aug)])[0]
+        assert vec.get_num_valid_subg() == ncall
+        got.extend(_subgraphs(vec))
+    assert s.get_idx_root() == 0
+    for i, (a, b) in enumerate(zip(want, got)):
+        assert_subgraph_equal(a, b, f"case {ci} subgraph {i}")
+
+
+def test_pybind_list_api_shapes():
+    """getters return list[list] of capacity num_sampler_per_batch like the pybind module (G.h:62-72)"""
+    PS = _product()
+    cfg, aug, targets, calls, want = G.case(1)
+    s = PS.ParallelSampler(G.indptr.tolist(), G.indices.tolist(), [], G.meta["P"], 1, True, True, [], 1, "", "", "", G.meta["seed"])
+    s.shuffle_targets(targets.tolist())
+    vec = s.parallel_sampler_ensemble([cfg], [set(aug)])[0]
+    clip = vec.get_num_valid_subg()
+    assert len(vec.get_subgraph_indptr()) == G.meta["P"]
+    assert vec.get_subgraph_node()[0] == want[0]["node"].tolist()
+    assert vec.get_subgraph_data()[0] == [1.0] * want[0]["indices"].size
+    assert vec.get_subgraph_hop()[clip - 1] == want[clip - 1]["hop"].tolist()
+    assert s.num_nodes() == G.indptr.size - 1 and s.num_edges() == G.indices.size and s.is_seq_root_traversal()
+
+
+def test_config_errors_match_pybind_exceptions():
+    PS = _product()
+    s = PS.ParallelSampler(G.indptr, G.indices, [], 4, 1, True, True, [], 1, "", "", "", 1)
+    s.shuffle_targets(np.arange(8, dtype=np.uint32))
+    with pytest.raises(IndexError):        # config.at("depth") -> std::out_of_range
+        s.parallel_sampler_ensemble([dict(method="khop", budget="3", num_roots="1")], [set()])
+    with pytest.raises(ValueError):        # std::stoi("x") -> std::invalid_argument
+        s.parallel_sampler_ensemble([dict(method="khop", depth="x", budget="3", num_roots="1")], [set()])
+    with pytest.raises(ValueError):
+        s.parallel_sampler_ensemble([dict(depth="1", budget="3", num_roots="1")], [set()])
+    with pytest.raises(Exception):         # ppr before the tables exist
+        s.parallel_sampler_ensemble([dict(method="ppr", k="3", threshold="0", num_roots="1")], [set()])
+
+
+def _oracle_vs_cuda(indptr, indices, targets, P, seed, cfg, aug, ppr_tables=None, fixed=False):
+    from oracle import oracle as O
+    PS = _product()
+    o = O.OracleSampler(indptr, indices, P, 1, seed)
+    o.shuffle_targets(targets)
+    s = PS.ParallelSampler(indptr, indices, [], P, 1, True, True, [], 1, "", "", "", seed, strict_reference_compat=not fixed)
+    s.shuffle_targets(targets)
+    if ppr_tables is not None:
+        o.set_ppr(*ppr_tables)
+        s.set_ppr_tables(*ppr_tables)
+    n = 0
+    for _ in range(1000):
+        want = o.sample(O.cfg_from_cpp_config(cfg, aug=aug, fixed_mode=fixed)).subgraphs()
+        got = _subgraphs(s.parallel_sampler_ensemble([cfg], [set(aug)])[0])
+        assert len(want) == len(got)
+        for i, (a, b) in enumerate(zip(want, got)):
+            assert_subgraph_equal(a, b, f"{cfg} {aug} subgraph {n + i}")
+        n += len(want)
+        assert o.get_idx_root() == s.get_idx_root()
+        if o.get_idx_root() == 0:
+            break
+    return n
+
+
+def test_khop_grid_vs_oracle():
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(4000, 14, 21, self_loops=60)
+    N = indptr.size - 1
+    rng = np.random.default_rng(3)
+    for depth, budget, se, nr, tc, aug in itertools.product([1, 2, 3], [-1, 5, 20], [False, True], [1, 2], [False, True],
+                                                            [(), ("hops",), ("drnls",)]):
+        if (aug == ("drnls",) and nr == 1) or (depth == 3 and budget != 5) or (tc and nr == 1):
+            continue
+        cfg = dict(method="khop", depth=str(depth), budget=str(budget), num_roots=str(nr),
+                   add_self_edge="true" if se else "false", include_target_conn="true" if tc else "false")
+        T = (130 if budget != -1 else 40) * nr
+        _oracle_vs_cuda(indptr, indices, rng.permutation(N - 2)[:T].astype(np.uint32), 50, 9, cfg, aug)
+
+
+def test_khop_fixed_mode_and_stream_persistence_vs_oracle():
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(3000, 12, 5)
+    N = indptr.size - 1
+    t = np.random.default_rng(0).permutation(N - 2)[:700].astype(np.uint32)
+    cfg = dict(method="khop", depth="2", budget="10", num_roots="1", add_self_edge="false", include_target_conn="false")
+    assert _oracle_vs_cuda(indptr, indices, t, 100, 1, cfg, ("hops",), fixed=True) == 700
+    assert _oracle_vs_cuda(indptr, indices, t, 500, 1, cfg, ("hops",)) == 700      # two calls: the rand() stream continues
+
+
+def test_ppr_grid_vs_oracle():
+    from oracle import oracle as O
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(5000, 16, 8, self_loops=50)
+    N = indptr.size - 1
+    rng = np.random.default_rng(4)
+    alln = np.arange(N, dtype=np.uint32)
+    nb, sc, ln = O.ppr_push(indptr, indices, alln, 200, 0.85, 1e-5, 8)
+    tables = O.ppr_rows_to_csr(N, alln, nb, sc, ln)
+    for k, thr, se, nr, aug in itertools.product([1, 30, 150, 200], [0, 0.002, 0.01], [False, True], [1, 2], [(), ("hops",), ("drnls",)]):
+        if aug == ("drnls",) and nr == 1:
+            continue
+        cfg = dict(method="ppr", k=str(k), threshold=str(thr), num_roots=str(nr), add_self_edge="true" if se else "false",
+                   include_target_conn="false")
+        _oracle_vs_cuda(indptr, indices, rng.permutation(N - 2)[:90 * nr].astype(np.uint32), 64, 2, cfg, aug, ppr_tables=tables)
+
+
+def test_edge_cases_vs_oracle():
+    """degree-0 roots, epoch tail shorter than a batch, odd root count for 2-root groups, P larger than the epoch"""
+    indptr = np.array([0, 0, 2, 3, 5, 5, 6, 7], dtype=np.uint32)       # nodes 0 and 4 are isolated; (5,6) is the tail component
+    indices = np.array([2, 3, 1, 1, 3, 6, 5], dtype=np.uint32)         # node 3 carries a self loop
+    t = np.array([0, 1, 2, 3, 4, 1, 0], dtype=np.uint32)
+    for nr, se in itertools.product([1, 2], [False, True]):
+        for m in ("khop", "nodeIID"):
+            cfg = dict(method=m, depth="2", budget="1", num_roots=str(nr), add_self_edge="true" if se else "false",
+                       include_target_conn="false")
+            _oracle_vs_cuda(indptr, indices, t, 4, 3, cfg, ("hops",) if nr == 1 else ("drnls",))
+            _oracle_vs_cuda(indptr, indices, t, 64, 3, cfg, ())
+
+
+def test_return_target_only_and_ensemble():
+    PS = _product()
+    cfg_a = dict(method="khop", depth="1", budget="-1", num_roots="1", add_self_edge="true", include_target_conn="false")
+    cfg_b = dict(method="nodeIID", num_roots="1", add_self_edge="false", include_target_conn="false", return_target_only="true")
+    s = PS.ParallelSampler(G.indptr, G.indices, [], 8, 1, True, True, [], 2, "", "", "", 1)
+    t = np.arange(20, dtype=np.uint32)
+    s.shuffle_targets(t)
+    a, b = s.parallel_sampler_ensemble([cfg_a, cfg_b], [set(), set()])
+    assert a.get_num_valid_subg() == b.get_num_valid_subg() == 8
+    for p in range(8):                              # both branches saw the same roots (PS.cpp:672)
+        assert b.numpy("node")[p].tolist() == [t[p]]
+        assert a.numpy("node")[p][a.numpy("target")[p][0]] == t[p]
+        assert b.numpy("indptr")[p].size == 0
+    s.drop_full_graph_info()
+    with pytest.raises(Exception):
+        s.parallel_sampler_ensemble([cfg_a, cfg_b], [set(), set()])
+
+
+def test_device_batch_is_block_diagonal_collation():
+    """sample_to_device == Subgraph.cat_to_block_diagonal of the per-subgraph results (frontend/graph.py:280-320)"""
+    import torch
+    from oracle import oracle as O
+    PS = _product()
+    cfg, aug, targets, calls, want = G.case(2)
+    s = PS.ParallelSampler(G.indptr, G.indices, [], 64, 1, True, True, [], 1, "", "", "", G.meta["seed"])
+    s.shuffle_targets(targets)
+    b = s.sample_to_device([cfg], [set(aug)])[0]
+    col = O.cat_to_block_diagonal(want[:b.num_subg])
+    assert np.array_equal(b.rowptr.cpu().numpy(), col["indptr"])
+    assert np.array_equal(b.indices.cpu().numpy(), col["indices"])
+    assert np.array_equal(b.orig_node.cpu().numpy().view(np.uint32), col["node"])
+    assert np.array_equal(b.orig_edge.cpu().numpy().view(np.uint32), col["edge_index"])
+    assert np.array_equal(b.target.cpu().numpy().ravel(), col["target"])
+    assert np.array_equal(torch.diff(b.node_ptr).cpu().numpy(), col["size_subg"])
+
+
+def test_ppr_push_gpu_bit_exact_vs_reference_golden():
+    PS = _product()
+    N = G.indptr.size - 1
+    p = G.meta["ppr"]
+    s = PS.ParallelSampler(G.indptr, G.indices, [], 4, 1, True, True, [], 1, "", "", "", 1)
+    s.preproc_ppr_approximate(np.arange(N, dtype=np.uint32), p["k"], p["alpha"], p["epsilon"], "", "")
+    for v in range(N):
+        nb, sc = s.get_ppr_row(v)
+        a, b = int(G.ppr_ptr[v]), int(G.ppr_ptr[v + 1])
+        assert np.array_equal(nb, G.ppr_neighs[a:b]), v
+        assert sc.tobytes() == G.ppr_scores[a:b].tobytes(), v
+
+
+def test_ppr_bin_cache_roundtrip(tmp_path):
+    """cache written by the CUDA path has the reference's layout (PS.cpp:94-139) and is re-read with its validity rule"""
+    PS = _product()
+    N = G.indptr.size - 1
+    fn, fs = str(tmp_path / "neighs.bin"), str(tmp_path / "scores.bin")
+    s = PS.ParallelSampler(G.indptr, G.indices, [], 4, 1, True, True, [], 1, "", "", "", 1)
+    s.preproc_ppr_approximate(np.arange(N, dtype=np.uint32), 48, 0.85, 1e-4, fn, fs)
+    raw = np.fromfile(fn, np.uint32)
+    assert np.frombuffer(raw[:2].tobytes(), np.float32)[0] == np.float32(1 - np.float32(0.85))
+    assert raw[2] == 48 and raw[3] == N
+    s2 = PS.ParallelSampler(G.indptr, G.indices, [], 4, 1, True, True, [], 1, "", "", "", 1)
+    s2.preproc_ppr_approximate(np.zeros(0, np.uint32), 20, 0.85, 1.05e-4, fn, fs)      # smaller k, eps within 10 %: loads
+    nb, sc = s2.get_ppr_row(7)
+    a = int(G.ppr_ptr[7])
+    assert np.array_equal(nb, G.ppr_neighs[a:a + nb.size]) and nb.size == min(20, int(G.ppr_ptr[8]) - a)
+
+
+def test_gather_rows():
+    import torch
+    PS = _product()
+    for F in (100, 128, 7):
+        feat = torch.randn(5000, F, device="cuda")
+        ids = torch.randint(0, 5000, (12345,), device="cuda", dtype=torch.int32)
+        out = PS.gather_rows(feat, ids)
+        assert torch.equal(out, feat[ids.long()])
+
+
+def test_superbatch_properties_philox():
+    """larger scale, production RNG: structural invariants that do not need the oracle"""
+    import torch
+    from shadow_gnn_b200.synth import powerlaw_graph
+    PS = _product()
+    indptr, indices = powerlaw_graph(200_000, 3_000_000, 5, dmax=2000)
+    N = indptr.size - 1
+    P = 4096
+    s = PS.ParallelSampler(indptr, indices, [], P, 1, True, True, [], 1, "", "", "", 7, rng="philox", strict_reference_compat=False)
+    t = np.random.default_rng(1).permutation(N)[:P].astype(np.uint32)
+    s.shuffle_targets(t)
+    cfg = dict(method="khop", depth="2", budget="10", num_roots="1", add_self_edge="true", include_target_conn="false")
+    b = s.sample_to_device([cfg], [{"hops"}])[0]
+    assert b.num_subg == P
+    node_ptr, rowptr, idx = b.node_ptr.long(), b.rowptr.long(), b.indices.long()
+    n = torch.diff(node_ptr)
+    assert int(n.max()) <= 111 and int(n.min()) >= 1
+    assert int(rowptr[-1]) == b.total_edges and bool((torch.diff(rowptr) >= 1).all())        # self edge => no empty row
+    sub_of_row = torch.repeat_interleave(torch.arange(P, device="cuda"), n)
+    row_of_edge = torch.repeat_interleave(torch.arange(b.total_nodes, device="cuda"), torch.diff(rowptr))
+    assert bool((sub_of_row[idx] == sub_of_row[row_of_edge]).all())                          # block diagonal
+    on = b.orig_node.long() & 0xFFFFFFFF
+    assert bool((on[b.target.long().ravel()] == torch.as_tensor(t.astype(np.int64), device="cuda")).all())
+    # every edge is a real edge of the full graph or the inserted self loop; rows are sorted (fixed mode)
+    oe = b.orig_edge.long() & 0xFFFFFFFF
+    real = oe != 0xFFFFFFFF
+    full_idx = torch.as_tensor(indices.astype(np.int64), device="cuda")
+    assert bool((full_idx[oe[real]] == on[idx[real]]).all())
+    assert bool((on[idx[~real]] == on[row_of_edge[~real]]).all())
+    same_row = row_of_edge[1:] == row_of_edge[:-1]
+    assert bool((idx[1:][same_row] > idx[:-1][same_row]).all())
+    # hop label of the root is 0 and every 1-hop neighbour has label 1
+    hop = b.hop.long() & 0xFFFFFFFF
+    assert bool((hop[b.target.long().ravel()] == 0).all()) and int(hop.max()) <= 2
+    # same seed => same sample (idempotence); different epoch => different sample
+    s2 = PS.ParallelSampler(indptr, indices, [], P, 1, True, True, [], 1, "", "", "", 7, rng="philox", strict_reference_compat=False)
+    s2.shuffle_targets(t)
+    b2 = s2.sample_to_device([cfg], [{"hops"}])[0]
+    assert torch.equal(b.orig_node, b2.orig_node) and torch.equal(b.indices, b2.indices)
+    b3 = s2.sample_to_device([cfg], [{"hops"}])[0]
+    assert not torch.equal(b3.orig_node[:1000], b.orig_node[:1000])
