@@ -221,6 +221,27 @@ class ParallelSampler:
         self._h = h
         self.num_ensemble = int(num_subgraphs_ensemble)
 
+    @classmethod
+    def from_device_csr(cls, indptr, indices, num_sampler_per_batch, num_subgraphs_ensemble=1, seed=-1, *,
+                        strict_reference_compat=True, rng="glibc", num_ring=2):
+        """Sampler over a CSR that already lives in HBM (int32/uint32 CUDA tensors, borrowed -- the sampler keeps them alive)."""
+        self = cls.__new__(cls)
+        assert indptr.is_cuda and indices.is_cuda and indptr.element_size() == 4 and indices.element_size() == 4
+        assert indptr.is_contiguous() and indices.is_contiguous()
+        self.device = indptr.device.index
+        self.num_sampler_per_batch = int(num_sampler_per_batch)
+        self.fixed_mode = not strict_reference_compat
+        self.rng_mode = {"glibc": _lib.RNG_GLIBC, "philox": _lib.RNG_PHILOX}[rng]
+        self._sequential = True
+        self._graph_keepalive = (indptr, indices)
+        h = C.c_void_p()
+        check(lib.shadow_sampler_create_dev(C.c_void_p(indptr.data_ptr()), C.c_void_p(indices.data_ptr()), indptr.numel() - 1,
+                                            indices.numel(), self.num_sampler_per_batch, int(num_subgraphs_ensemble), int(seed),
+                                            self.device, int(num_ring), C.byref(h)))
+        self._h = h
+        self.num_ensemble = int(num_subgraphs_ensemble)
+        return self
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:

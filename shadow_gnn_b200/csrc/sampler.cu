@@ -3,6 +3,7 @@
 // list and the results all resident in HBM.
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <vector>
@@ -99,7 +100,7 @@ struct shadow_sampler {
 
 static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-struct Caps { int ncap, ccap, ccap2, acap, acap2, hcap, hshift; WsLayout L; long long max_draws; };
+struct Caps { int ncap, ccap, ccap2, acap, acap2, hcap, hshift, ecap; WsLayout L; long long max_draws; };
 
 static int graph_dmax(shadow_sampler *s, long long *out);
 
@@ -146,12 +147,25 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
   L.row_e = take((size_t)o->ncap * 4);
   L.row_cnt = take(((size_t)o->ncap + 1) * 4);
   L.row_ins = take((size_t)o->ncap * 4);
+  L.row_off = take(((size_t)o->ncap + 1) * 4);
+  L.row_kept = take(((size_t)o->ncap + 1) * 4);
+  L.row_less = take((size_t)o->ncap * 4);
+  L.row_bug = take((size_t)o->ncap * 4);
   L.level = take((size_t)o->ncap * 4);
   L.all = take((size_t)o->acap2 * 4);
   const bool bfs = (c.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) != 0;
   L.dist = take(bfs ? (size_t)o->ncap * 4 : 0);
   L.fr_a = take(bfs ? (size_t)o->ncap * 4 : 0);
   L.fr_b = take(bfs ? (size_t)o->ncap * 4 : 0);
+  // staged-edge capacity of the single-pass path (16-bit sub ids); 0 => generic two-pass path
+  {
+    const char *env = getenv("SHADOW_ECAP_MULT");
+    const int mult = env ? atoi(env) : 8;
+    o->ecap = (o->ncap <= 32767 && mult > 0) ? std::min(16384, std::max(512, mult * o->ncap)) : 0;
+    const uint32_t base_bytes = off;
+    L.st = take((size_t)o->ecap * 8);
+    if (off > 200 * 1024) { o->ecap = 0; off = base_bytes; L.st = 0; }
+  }
   L.bytes = off;
   return 0;
 }
@@ -388,6 +402,7 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   K.aug = c.aug; K.fixed_mode = c.fixed_mode; K.rng_mode = c.rng_mode;
   K.ppr_ptr = (const unsigned long long *)s->ppr_ptr.p; K.ppr_neighs = (const uint32_t *)s->ppr_neighs.p; K.ppr_scores = (const float *)s->ppr_scores.p;
   K.philox_seed = (uint32_t)s->seed; K.philox_epoch = r.philox_epoch; K.root_slot_base = r.idx_start / (uint32_t)c.num_roots;
+  K.ecap = caps.ecap;
   K.ncap = caps.ncap; K.ccap = caps.ccap; K.ccap2 = caps.ccap2; K.acap = caps.acap; K.acap2 = caps.acap2; K.hcap = caps.hcap; K.hshift = caps.hshift;
   K.L = caps.L;
   K.cap_nodes = r.cap_nodes; K.cap_edges = r.cap_edges;

@@ -20,7 +20,7 @@
 #define SAMPLER_BLOCK 128
 
 struct WsLayout {          // byte offsets of the per-CTA workspace (shared memory, or global for huge scopes)
-  uint32_t keys, cval, nodes, pprv, hkeys, hvals, row_s, row_e, row_cnt, row_ins, level, all, dist, fr_a, fr_b;
+  uint32_t keys, cval, nodes, pprv, hkeys, hvals, row_s, row_e, row_cnt, row_ins, row_off, row_kept, row_less, row_bug, level, all, dist, fr_a, fr_b, st;
   uint32_t bytes;
 };
 
@@ -46,6 +46,7 @@ struct SampleParams {
   uint32_t philox_seed, philox_epoch, root_slot_base;
   // per-subgraph capacities
   int ncap, ccap, ccap2, acap, acap2, hcap, hshift;
+  int ecap;                          // staged edges per subgraph (0 = two-pass generic path)
   WsLayout L;
   unsigned char *gws;                // global workspace (GWS variant)
   unsigned long long gws_stride;
@@ -64,7 +65,8 @@ enum { ERR_WS_OVERFLOW = 1, ERR_OUT_OVERFLOW = 2 };
 
 struct Ws {
   unsigned long long *keys; float *cval; uint32_t *nodes; float *pprv; uint32_t *hkeys, *hvals, *row_s, *row_e, *row_cnt,
-      *row_ins, *level, *all, *dist, *fr_a, *fr_b;
+      *row_ins, *row_off, *row_kept, *row_less, *row_bug, *level, *all, *dist, *fr_a, *fr_b;
+  uint2 *st;
 };
 __device__ __forceinline__ Ws make_ws(unsigned char *b, const WsLayout &L) {
   Ws w;
@@ -75,6 +77,8 @@ __device__ __forceinline__ Ws make_ws(unsigned char *b, const WsLayout &L) {
   w.row_cnt = (uint32_t *)(b + L.row_cnt); w.row_ins = (uint32_t *)(b + L.row_ins);
   w.level = (uint32_t *)(b + L.level); w.all = (uint32_t *)(b + L.all);
   w.dist = (uint32_t *)(b + L.dist); w.fr_a = (uint32_t *)(b + L.fr_a); w.fr_b = (uint32_t *)(b + L.fr_b);
+  w.row_off = (uint32_t *)(b + L.row_off); w.row_kept = (uint32_t *)(b + L.row_kept); w.row_less = (uint32_t *)(b + L.row_less);
+  w.row_bug = (uint32_t *)(b + L.row_bug); w.st = (uint2 *)(b + L.st);
   return w;
 }
 
@@ -309,6 +313,84 @@ __device__ __forceinline__ uint32_t drnl_single(uint32_t dx, uint32_t dy) {     
   return 1u + mn + (d / 2u) * ((d / 2u) + (d % 2u) - 1u);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// C (fast path): ONE pass over the full-graph rows, flat and chunk-granular.
+// Every row is cut into "items" = the 128-byte lines of `indices` it touches (slot e, the PS.cpp:401 bug slot,
+// included).  The item space of the subgraph is split evenly over the warps; a warp walks its range SCAN_U items
+// at a time, issuing all SCAN_U coalesced 128-byte requests before the first use, probes the shared-memory hash
+// and appends the kept edges -- in slot order, hence already in CSR order -- to its staging region.  Hub rows are
+// simply many items, shared by all warps; no row is read twice and no warp waits on a row-sized latency chain.
+// ------------------------------------------------------------------------------------------------
+#define SCAN_U 8
+#define ST_GT 0x8000u
+struct KeepCtx { const uint32_t *hk, *hv; uint32_t hmask; int hshift; const uint32_t *roots; int nt; };
+__device__ __forceinline__ uint32_t keep_lookup(const KeepCtx &K, uint32_t nb, bool v_is_t) {
+  uint32_t sub = hash_lookup(K.hk, K.hv, K.hmask, K.hshift, nb);
+  if (sub != NONE32 && v_is_t) { bool nb_t = false; for (int j = 0; j < K.nt; j++) nb_t |= (K.roots[j] == nb); if (nb_t) sub = NONE32; }   // PS.cpp:412-418
+  return sub;
+}
+
+// On entry: ws.row_s / ws.row_e hold the row extents, ws.row_off[0..n] the exclusive item prefix (first item of each row),
+// ws.row_kept / ws.row_less / ws.row_bug are zero / zero / NONE32.   Returns the number of staged entries of this warp.
+__device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws, int n, uint32_t num_items, const KeepCtx &K,
+                                             bool tconn, bool add_self, uint32_t *overflow) {
+  const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
+  const uint32_t rcap = (uint32_t)P.ecap / nwarp;              // staging region of this warp
+  uint2 *st = ws.st + (size_t)warp * rcap;
+  const uint32_t i_begin = (uint32_t)(((unsigned long long)num_items * warp) / nwarp);
+  const uint32_t i_end = (uint32_t)(((unsigned long long)num_items * (warp + 1)) / nwarp);
+  if (i_begin >= i_end) return 0;
+  int row;
+  { int lo = 0, hi = n; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.row_off[mid] <= i_begin) lo = mid; else hi = mid; } row = lo; }
+  uint32_t cnt = 0;
+  for (uint32_t ib = i_begin; ib < i_end; ib += SCAN_U) {
+    uint32_t nbv[SCAN_U], posv[SCAN_U];
+    int rowv[SCAN_U];
+#pragma unroll
+    for (int u = 0; u < SCAN_U; u++) {
+      const uint32_t it = ib + u;
+      nbv[u] = NONE32; posv[u] = 0; rowv[u] = row;
+      if (it < i_end) {
+        while (it >= ws.row_off[row + 1]) row++;
+        rowv[u] = row;
+        const uint32_t s = ws.row_s[row], e = ws.row_e[row];
+        const uint32_t c = (s & ~31u) + (it - ws.row_off[row]) * 32u + lane;
+        const bool bug_ok = !P.fixed_mode && e < P.num_edges;                         // slot e: PS.cpp:401
+        posv[u] = c;
+        if (c >= s && (c < e || (bug_ok && c == e))) nbv[u] = ldg_stream_u32(P.indices + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SCAN_U; u++) {
+      if (ib + u >= i_end) break;
+      const int r = rowv[u];
+      const uint32_t v = ws.nodes[r], e = ws.row_e[r];
+      uint32_t nb = nbv[u];
+      if (posv[u] == e && nb != NONE32) { ws.row_bug[r] = nb; nb = NONE32; }        // bug-slot candidate, resolved after the scan
+      bool v_is_t = false;
+      if (!tconn) for (int j = 0; j < K.nt; j++) v_is_t |= (K.roots[j] == v);
+      const uint32_t sub = (nb != NONE32) ? keep_lookup(K, nb, v_is_t) : NONE32;
+      const uint32_t mk = __ballot_sync(0xffffffffu, sub != NONE32);
+      if (add_self) {
+        const uint32_t lm = __ballot_sync(0xffffffffu, sub != NONE32 && nb < v);
+        const bool pres = __any_sync(0xffffffffu, nb == v);
+        if (lane == 0 && (lm || pres)) atomicAdd(&ws.row_less[r], (uint32_t)__popc(lm) | (pres ? 0x80000000u : 0u));
+      }
+      if (mk) {
+        if (sub != NONE32) {
+          const uint32_t at = cnt + __popc(mk & lanemask_lt());
+          if (at < rcap) st[at] = make_uint2(sub | (nb > v ? ST_GT : 0u) | ((uint32_t)r << 16), posv[u]);       // :420-422
+        }
+        if (lane == 0) atomicAdd(&ws.row_kept[r], (uint32_t)__popc(mk));
+        cnt += __popc(mk);
+      }
+    }
+  }
+  if (cnt > rcap && lane == 0) *overflow = 1;
+  return cnt;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
@@ -317,7 +399,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ uint32_t s_warp_sums[33];
   __shared__ int s_p, s_n;
-  __shared__ uint32_t s_cnt, s_cut;
+  __shared__ uint32_t s_cnt, s_cut, s_tmp[2], s_scan[32];
   __shared__ long long s_base[2];
   __shared__ uint32_t s_roots[SHADOW_MAX_ROOTS], s_tl[SHADOW_MAX_ROOTS];
 
@@ -373,8 +455,14 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
       uint32_t h = hash_slot(v, P.hshift);
       while (atomicCAS(&ws.hkeys[h], NONE32, v) != NONE32) h = (h + 1) & hmask;
       ws.hvals[h] = (uint32_t)i;
-      const uint32_t s = P.indptr[v];
-      ws.row_s[i] = s; ws.row_e[i] = P.indptr[v + 1];
+      const uint32_t s = P.indptr[v], e = P.indptr[v + 1];
+      ws.row_s[i] = s; ws.row_e[i] = e;
+      if (!GWS && P.ecap > 0) {
+        // items = 128-byte lines of `indices` covered by [s, e_last]; slot e is included when the PS.cpp:401 bug slot applies
+        const bool bug_ok = !P.fixed_mode && e < P.num_edges;
+        const uint32_t items = bug_ok ? (e >> 5) - (s >> 5) + 1u : (e > s ? ((e - 1u) >> 5) - (s >> 5) + 1u : 0u);
+        ws.row_off[i] = items; ws.row_kept[i] = 0; ws.row_less[i] = 0; ws.row_bug[i] = NONE32;
+      }
     }
     __syncthreads();
     if (threadIdx.x < nt) {
@@ -384,7 +472,36 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
     const bool tconn = P.tconn || nt == 1;                 // PS.cpp:356-358
     const bool add_self = P.add_self != 0;
 
-    // ---------------- C1: count pass (warp per row) ----------------
+    // ---------------- C: row scan ----------------
+    bool staged = false;
+    if (!GWS && P.ecap > 0) {                              // single pass, kept edges staged in shared memory
+      const uint32_t num_items = block_exclusive_scan(ws.row_off, n, s_warp_sums);
+      if (threadIdx.x == 0) { ws.row_off[n] = num_items; s_tmp[0] = 0; }
+      __syncthreads();
+      KeepCtx KC;
+      KC.hk = ws.hkeys; KC.hv = ws.hvals; KC.hmask = hmask; KC.hshift = P.hshift; KC.roots = s_roots; KC.nt = nt;
+      const uint32_t wcnt = scan_items_staged(P, ws, n, num_items, KC, tconn, add_self, &s_tmp[0]);
+      if (lane == 0) s_scan[warp] = wcnt;
+      __syncthreads();
+      staged = (s_tmp[0] == 0);
+      // per row: resolve the self-edge insertion and the bug slot now that the whole row has been seen
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t lr = ws.row_less[i], v = ws.nodes[i];
+        const bool inserting = add_self && !(lr >> 31);                                            // PS.cpp:386-400
+        uint32_t bsub = NONE32;
+        if (!inserting && ws.row_bug[i] != NONE32) {
+          bool v_is_t = false;
+          if (!tconn) for (int j = 0; j < nt; j++) v_is_t |= (s_roots[j] == v);
+          bsub = keep_lookup(KC, ws.row_bug[i], v_is_t);
+        }
+        ws.row_bug[i] = bsub;
+        ws.row_ins[i] = inserting ? (lr & 0x7fffffffu) : NONE32;
+        ws.row_cnt[i] = ws.row_kept[i] + (inserting ? 1u : 0u) + (bsub != NONE32 ? 1u : 0u);
+      }
+      __syncthreads();
+      block_exclusive_scan(ws.row_kept, n, s_warp_sums);                                           // real kept edges before each row
+    } else {
+    // count pass of the generic two-pass path (warp per row)
     for (int r = warp; r < n; r += nwarp) {
       const uint32_t v = ws.nodes[r], s = ws.row_s[r], e = ws.row_e[r];
       bool v_is_t = false;
@@ -413,6 +530,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
       }
       if (lane == 0) { ws.row_cnt[r] = kept + (inserting ? 1u : 0u); ws.row_ins[r] = inserting ? kept_less : NONE32; }
     }
+        }
     __syncthreads();
     const uint32_t m = block_exclusive_scan(ws.row_cnt, n, s_warp_sums);      // local indptr (:428-431)
     if (threadIdx.x == 0) ws.row_cnt[n] = m;
@@ -442,7 +560,32 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
         P.ppr_out[node_base + i] = ws.pprv[i];
         P.rowptr[node_base + i] = (int)(edge_base + ws.row_cnt[i]);
       }
-      // ---------------- C2: fill pass (rows come back from L2) ----------------
+      // ---------------- emit the CSR ----------------
+      if (staged) {                                        // staged rows -> CSR order already; no second read of the graph
+        const uint32_t rcap = (uint32_t)P.ecap / nwarp;
+        uint32_t ktot = 0;
+        for (int w = 0; w < nwarp; w++) ktot += s_scan[w];
+        for (uint32_t g = threadIdx.x; g < ktot; g += blockDim.x) {
+          uint32_t wb = 0; int w = 0;
+          while (g >= wb + s_scan[w]) { wb += s_scan[w]; w++; }
+          const uint2 ent = ws.st[(size_t)w * rcap + (g - wb)];
+          const uint32_t row = ent.x >> 16;
+          const long long pos = edge_base + ws.row_cnt[row] + (g - ws.row_kept[row]) + ((ws.row_ins[row] != NONE32 && (ent.x & ST_GT)) ? 1 : 0);
+          P.indices_out[pos] = (int)(node_base + (ent.x & 0x7fffu));
+          P.orig_edge[pos] = ent.y;
+        }
+        for (int r = threadIdx.x; r < n; r += blockDim.x) {
+          if (ws.row_ins[r] != NONE32) {                                                           // PS.cpp:406-411
+            const long long pos = edge_base + ws.row_cnt[r] + ws.row_ins[r];
+            P.indices_out[pos] = (int)(node_base + r); P.orig_edge[pos] = NONE32;
+          }
+          if (ws.row_bug[r] != NONE32) {
+            const long long pos = edge_base + ws.row_cnt[r + 1] - 1;
+            P.indices_out[pos] = (int)(node_base + ws.row_bug[r]); P.orig_edge[pos] = ws.row_e[r];
+          }
+        }
+      } else
+      // fill pass of the generic path (rows come back from L2)
       for (int r = warp; r < n; r += nwarp) {
         const uint32_t v = ws.nodes[r], s = ws.row_s[r], e = ws.row_e[r];
         bool v_is_t = false;
