@@ -110,16 +110,25 @@ int shadow_sampler_sample(shadow_sampler *s, const shadow_sampler_cfg *cfgs, int
 /* ---------------------------------------------------------------------------------------------- */
 /* results == SubgraphStructVec (G.h:59-97) of the latest call, one per ensemble branch, kept in   */
 /* HBM as ONE block-diagonal batch (what Subgraph.cat_to_block_diagonal, frontend/graph.py:280-320, */
-/* builds on the host in the reference):                                                           */
-/*   node_ptr[P+1], edge_ptr[P+1]   exclusive prefix sums of |V_s|, |E_s|                          */
-/*   rowptr[N_tot+1]                CSR row pointer of the whole batch (== concatenated indptr)     */
-/*   indices[E_tot]                 BATCH-global column ids (local id + node_ptr[s])                */
-/*   orig_node[N_tot], orig_edge[E_tot], ppr[N_tot], hop[N_tot], drnl[N_tot]                        */
-/*   target[P*num_roots]            BATCH-global row of each root                                  */
+/* builds on the host in the reference).  Rows (nodes) are always in subgraph order:               */
+/*   node_ptr[P+1]                  exclusive prefix sum of |V_s|                                  */
+/*   orig_node[N_tot], ppr[N_tot], hop[N_tot], drnl[N_tot]                                         */
+/*   target[P*num_roots]            BATCH-global row of each root (-1 pads a short last group)     */
+/* The edges exist in two layouts.  RAW is what the sampling kernel writes: the edge block of a    */
+/* subgraph is contiguous and in CSR order, but blocks are placed in completion order so that no   */
+/* CTA waits for another one's row scan:                                                           */
+/*   row_span[N_tot]  (int32 pairs) [start,end) of every row inside indices_raw / orig_edge_raw    */
+/*   edge_span[P]     (int32 pairs) [start,end) of every subgraph's edge block                     */
+/*   indices_raw[E_tot]             BATCH-global column ids (local id + node_ptr[s])               */
+/*   orig_edge_raw[E_tot]                                                                          */
+/* CANONICAL is the standard CSR, produced on first request by one extra streaming kernel:         */
+/*   edge_ptr[P+1], rowptr[N_tot+1] (== concatenated indptr), indices[E_tot], orig_edge[E_tot]     */
 /* ---------------------------------------------------------------------------------------------- */
 enum { SHADOW_F_NODE_PTR = 0, SHADOW_F_EDGE_PTR = 1, SHADOW_F_ROWPTR = 2, SHADOW_F_INDICES = 3,
        SHADOW_F_ORIG_NODE = 4, SHADOW_F_ORIG_EDGE = 5, SHADOW_F_TARGET = 6, SHADOW_F_PPR = 7,
-       SHADOW_F_HOP = 8, SHADOW_F_DRNL = 9, SHADOW_F_NUM_TARGET = 10, SHADOW_NUM_FIELDS = 11 };
+       SHADOW_F_HOP = 8, SHADOW_F_DRNL = 9, SHADOW_F_NUM_TARGET = 10,
+       SHADOW_F_ROW_SPAN = 11, SHADOW_F_EDGE_SPAN = 12, SHADOW_F_INDICES_RAW = 13, SHADOW_F_ORIG_EDGE_RAW = 14,
+       SHADOW_NUM_FIELDS = 15 };
 
 typedef struct {
   int32_t num_subg;        /* get_num_valid_subg() (G.cpp:92-94) */
@@ -132,7 +141,7 @@ typedef struct {
 
 /* synchronises the sampler's stream, validates capacities (re-running with larger buffers if needed) */
 int shadow_sampler_batch_info(shadow_sampler *s, int branch, shadow_batch_info *info);
-/* device pointer + element count of one field of the latest batch (valid until num_ring further calls) */
+/* device pointer + count of 4-byte elements of one field of the latest batch (valid until num_ring further calls) */
 int shadow_sampler_batch_field_dev(shadow_sampler *s, int branch, int field, void **ptr_dev, int64_t *count);
 /* copy one field to the host; 4 bytes per element */
 int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, int field, void *dst_host, int64_t count);

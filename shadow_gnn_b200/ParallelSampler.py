@@ -87,29 +87,42 @@ class _DevArray:
 
 
 class DeviceBatch:
-    """One ensemble branch of the latest call, resident in HBM as a block-diagonal batch (see shadow_b200.h).
-    Tensors are zero-copy views, valid until `num_ring` further sampler calls."""
+    """One ensemble branch of the latest call, resident in HBM as a block-diagonal batch (layouts: shadow_b200.h).
+    Tensors are zero-copy views fetched on first access, valid until `num_ring` further sampler calls.
+    RAW edge layout: row_span [N,2], edge_span [P,2], indices_raw, orig_edge_raw (what the kernel wrote);
+    CANONICAL CSR: edge_ptr, rowptr, indices, orig_edge (one extra streaming kernel on first access)."""
     _FIELDS = {"node_ptr": (_lib.F_NODE_PTR, "<i4"), "edge_ptr": (_lib.F_EDGE_PTR, "<i4"), "rowptr": (_lib.F_ROWPTR, "<i4"),
                "indices": (_lib.F_INDICES, "<i4"), "orig_node": (_lib.F_ORIG_NODE, "<i4"), "orig_edge": (_lib.F_ORIG_EDGE, "<i4"),
                "target": (_lib.F_TARGET, "<i4"), "ppr": (_lib.F_PPR, "<f4"), "hop": (_lib.F_HOP, "<i4"),
-               "drnl": (_lib.F_DRNL, "<i4"), "num_target": (_lib.F_NUM_TARGET, "<i4")}
+               "drnl": (_lib.F_DRNL, "<i4"), "num_target": (_lib.F_NUM_TARGET, "<i4"),
+               "row_span": (_lib.F_ROW_SPAN, "<i4"), "edge_span": (_lib.F_EDGE_SPAN, "<i4"),
+               "indices_raw": (_lib.F_INDICES_RAW, "<i4"), "orig_edge_raw": (_lib.F_ORIG_EDGE_RAW, "<i4")}
 
     def __init__(self, sampler, branch):
-        import torch
         info = _lib.BatchInfo()
         check(lib.shadow_sampler_batch_info(sampler._h, branch, C.byref(info)))
+        self._sampler, self._branch = sampler, branch
         self.num_subg, self.num_roots = info.num_subg, info.num_roots
         self.total_nodes, self.total_edges = info.total_nodes, info.total_edges
         self.has_csr = bool(info.has_csr)
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name not in self._FIELDS:
+            raise AttributeError(name)
+        import torch
+        fid, ts = self._FIELDS[name]
+        sampler = self._sampler
         dev = torch.device("cuda", sampler.device)
-        for name, (fid, ts) in self._FIELDS.items():
-            p, n = C.c_void_p(), C.c_int64()
-            check(lib.shadow_sampler_batch_field_dev(sampler._h, branch, fid, C.byref(p), C.byref(n)))
-            if n.value == 0:
-                t = torch.empty(0, dtype=torch.float32 if ts == "<f4" else torch.int32, device=dev)
-            else:
-                t = torch.as_tensor(_DevArray(p.value, n.value, ts, sampler), device=dev)
-            setattr(self, name, t)
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib.shadow_sampler_batch_field_dev(sampler._h, self._branch, fid, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            t = torch.empty(0, dtype=torch.float32 if ts == "<f4" else torch.int32, device=dev)
+        else:
+            t = torch.as_tensor(_DevArray(p.value, n.value, ts, sampler), device=dev)
+        if name in ("row_span", "edge_span"):
+            t = t.view(-1, 2)
+        setattr(self, name, t)
+        return t
 
 
 class SubgraphStructVec:

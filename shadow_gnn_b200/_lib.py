@@ -33,7 +33,7 @@ METHOD = {"khop": 0, "ppr": 1, "ppr_st": 2, "nodeIID": 3}
 AUG = {"hops": 1, "pprs": 2, "drnls": 4}
 RNG_GLIBC, RNG_PHILOX = 0, 1
 (F_NODE_PTR, F_EDGE_PTR, F_ROWPTR, F_INDICES, F_ORIG_NODE, F_ORIG_EDGE, F_TARGET, F_PPR, F_HOP, F_DRNL,
- F_NUM_TARGET) = range(11)
+ F_NUM_TARGET, F_ROW_SPAN, F_EDGE_SPAN, F_INDICES_RAW, F_ORIG_EDGE_RAW) = range(15)
 
 # every symbol include/shadow_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

@@ -64,6 +64,8 @@ struct DevBuf {
 
 struct Result {              // one ensemble branch of one call: SubgraphStructVec (G.h:59-97) in HBM
   DevBuf node_ptr, edge_ptr, rowptr, indices, target, num_target, orig_node, orig_edge, hop, drnl, ppr, sync;
+  DevBuf row_span, edge_span, indices_raw, orig_edge_raw;
+  bool canon_valid = false;
   long long cap_nodes = 0, cap_edges = 0;
   int cap_subg = 0;
   long long *totals_host = nullptr;   // pinned mirror of totals[3]
@@ -147,10 +149,10 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
   L.row_e = take((size_t)o->ncap * 4);
   L.row_cnt = take(((size_t)o->ncap + 1) * 4);
   L.row_ins = take((size_t)o->ncap * 4);
-  L.row_off = take(((size_t)o->ncap + 1) * 4);
-  L.row_kept = take(((size_t)o->ncap + 1) * 4);
-  L.row_less = take((size_t)o->ncap * 4);
-  L.row_bug = take((size_t)o->ncap * 4);
+  L.rowd = take(((size_t)o->ncap + 1) * 16);
+  L.row_first = take((size_t)o->ncap * 4);
+  L.row_last = take((size_t)o->ncap * 4);
+  L.row_fgt = take((size_t)o->ncap * 4);
   L.level = take((size_t)o->ncap * 4);
   L.all = take((size_t)o->acap2 * 4);
   const bool bfs = (c.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) != 0;
@@ -266,7 +268,8 @@ extern "C" int shadow_sampler_create_dev(const uint32_t *indptr_dev, const uint3
 }
 
 static void result_release(Result &r) {
-  DevBuf *all[] = {&r.node_ptr, &r.edge_ptr, &r.rowptr, &r.indices, &r.target, &r.num_target, &r.orig_node, &r.orig_edge, &r.hop, &r.drnl, &r.ppr, &r.sync};
+  DevBuf *all[] = {&r.node_ptr, &r.edge_ptr, &r.rowptr, &r.indices, &r.target, &r.num_target, &r.orig_node, &r.orig_edge, &r.hop, &r.drnl, &r.ppr, &r.sync,
+                   &r.row_span, &r.edge_span, &r.indices_raw, &r.orig_edge_raw};
   for (auto b : all) b->release();
   if (r.totals_host) cudaFreeHost(r.totals_host);
   r.totals_host = nullptr;
@@ -354,17 +357,17 @@ static int ensure_result_caps(Result &r, int P, int num_roots, long long cap_nod
   if (cap_nodes >= (1ll << 31) || cap_edges >= (1ll << 31)) FAIL(SHADOW_ECAP, "batch exceeds 2^31 nodes or edges (%lld, %lld): lower num_sampler_per_batch", cap_nodes, cap_edges);
   bool bad = false;
   bad |= r.node_ptr.ensure(((size_t)P + 1) * 4) != 0;
-  bad |= r.edge_ptr.ensure(((size_t)P + 1) * 4) != 0;
+  bad |= r.edge_span.ensure((size_t)std::max(P, 1) * 8) != 0;
   bad |= r.num_target.ensure((size_t)P * 4) != 0;
   bad |= r.target.ensure((size_t)P * num_roots * 4) != 0;
-  bad |= r.sync.ensure(64 + (size_t)P * 16) != 0;
-  bad |= r.rowptr.ensure(((size_t)cap_nodes + 1) * 4) != 0;
+  bad |= r.sync.ensure(64 + (size_t)P * 8) != 0;
+  bad |= r.row_span.ensure((size_t)std::max<long long>(cap_nodes, 1) * 8) != 0;
   bad |= r.orig_node.ensure((size_t)cap_nodes * 4) != 0;
   bad |= r.ppr.ensure((size_t)cap_nodes * 4) != 0;
   bad |= r.hop.ensure((size_t)cap_nodes * 4) != 0;
   bad |= r.drnl.ensure((size_t)cap_nodes * 4) != 0;
-  bad |= r.indices.ensure((size_t)cap_edges * 4) != 0;
-  bad |= r.orig_edge.ensure((size_t)cap_edges * 4) != 0;
+  bad |= r.indices_raw.ensure((size_t)cap_edges * 4) != 0;
+  bad |= r.orig_edge_raw.ensure((size_t)cap_edges * 4) != 0;
   if (bad) FAIL(SHADOW_ECUDA, "cudaMalloc(result buffers) failed");
   r.cap_nodes = cap_nodes; r.cap_edges = cap_edges; r.cap_subg = P;
   return 0;
@@ -406,13 +409,13 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   K.ncap = caps.ncap; K.ccap = caps.ccap; K.ccap2 = caps.ccap2; K.acap = caps.acap; K.acap2 = caps.acap2; K.hcap = caps.hcap; K.hshift = caps.hshift;
   K.L = caps.L;
   K.cap_nodes = r.cap_nodes; K.cap_edges = r.cap_edges;
-  K.node_ptr = (int *)r.node_ptr.p; K.edge_ptr = (int *)r.edge_ptr.p; K.rowptr = (int *)r.rowptr.p; K.indices_out = (int *)r.indices.p;
+  K.node_ptr = (int *)r.node_ptr.p; K.row_span = (int2 *)r.row_span.p; K.edge_span = (int2 *)r.edge_span.p; K.indices_out = (int *)r.indices_raw.p;
   K.target = (int *)r.target.p; K.num_target = (int *)r.num_target.p;
-  K.orig_node = (uint32_t *)r.orig_node.p; K.orig_edge = (uint32_t *)r.orig_edge.p; K.hop = (uint32_t *)r.hop.p; K.drnl = (uint32_t *)r.drnl.p;
+  K.orig_node = (uint32_t *)r.orig_node.p; K.orig_edge = (uint32_t *)r.orig_edge_raw.p; K.hop = (uint32_t *)r.hop.p; K.drnl = (uint32_t *)r.drnl.p;
   K.ppr_out = (float *)r.ppr.p;
   unsigned char *sync = (unsigned char *)r.sync.p;
   K.ticket = (uint32_t *)sync; K.totals = (long long *)(sync + 8);
-  K.status_n = (unsigned long long *)(sync + 64); K.status_m = K.status_n + P;
+  K.status_n = (unsigned long long *)(sync + 64);
 
   const size_t smem_limit = 200 * 1024;
   const bool use_gws = caps.L.bytes > smem_limit;
@@ -439,7 +442,7 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     CUDA_TRY(cudaMemcpyAsync(s->rand_stream.p, s->rand_host.data(), (size_t)need * 4, cudaMemcpyHostToDevice, s->stream));
     K.rand_stream = (const uint32_t *)s->rand_stream.p; K.rand_off = (long long *)s->rand_off.p;
   }
-  CUDA_TRY(cudaMemsetAsync(sync, 0, 64 + (size_t)P * 16, s->stream));
+  CUDA_TRY(cudaMemsetAsync(sync, 0, 64 + (size_t)P * 8, s->stream));
   if (glibc) {
     SampleParams Kp = K;
     Kp.count_only_last = 1;
@@ -457,7 +460,7 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(cudaMemcpyAsync(r.totals_host, K.totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
-  r.pending = true; r.valid = false; r.rand_draws = 0;
+  r.pending = true; r.valid = false; r.rand_draws = 0; r.canon_valid = false;
   if (glibc) {                 // the host generator must advance by what this call consumed before the next call
     long long used = 0;
     CUDA_TRY(cudaMemcpyAsync(&used, (long long *)s->rand_off.p + P, 8, cudaMemcpyDeviceToHost, s->stream));
@@ -542,6 +545,54 @@ extern "C" int shadow_sampler_batch_info(shadow_sampler *s, int branch, shadow_b
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// RAW -> CANONICAL CSR (see shadow_b200.h): exclusive scan of the per-subgraph edge counts, then one streaming copy
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_edge_counts_kernel(const int2 *__restrict__ edge_span, int P, int *__restrict__ edge_ptr) {
+  __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t chunk[1024];
+  uint32_t carry = 0;
+  for (int base = 0; base < P; base += 1024) {
+    const int i = base + threadIdx.x;
+    chunk[threadIdx.x] = (i < P) ? (uint32_t)(edge_span[i].y - edge_span[i].x) : 0u;
+    __syncthreads();
+    const uint32_t tot = block_exclusive_scan(chunk, 1024, warp_sums);
+    if (i < P) edge_ptr[i] = (int)(carry + chunk[threadIdx.x]);
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) edge_ptr[P] = (int)carry;
+}
+__global__ void __launch_bounds__(256) canonicalize_kernel(const int *__restrict__ node_ptr, const int2 *__restrict__ edge_span,
+                                                           const int2 *__restrict__ row_span, const int *__restrict__ idx_raw,
+                                                           const uint32_t *__restrict__ eid_raw, const int *__restrict__ edge_ptr, int P,
+                                                           int *__restrict__ rowptr, int *__restrict__ idx, uint32_t *__restrict__ eid) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P; p += gridDim.x * wpb) {
+    const int2 es = edge_span[p];
+    const int dst = edge_ptr[p], n0 = node_ptr[p], n1 = node_ptr[p + 1];
+    for (int j = lane; j < es.y - es.x; j += 32) { idx[dst + j] = idx_raw[es.x + j]; eid[dst + j] = eid_raw[es.x + j]; }
+    for (int i = n0 + lane; i < n1; i += 32) rowptr[i] = dst + (row_span[i].x - es.x);
+    if (p == P - 1 && lane == 0) rowptr[n1] = edge_ptr[P];
+  }
+}
+static int ensure_canonical(shadow_sampler *s, Result &r) {
+  if (r.canon_valid || r.cfg.return_target_only) return 0;
+  const int P = r.num_subg;
+  if (r.edge_ptr.ensure(((size_t)P + 1) * 4) || r.rowptr.ensure(((size_t)r.total_nodes + 1) * 4) ||
+      r.indices.ensure((size_t)std::max<long long>(r.total_edges, 1) * 4) || r.orig_edge.ensure((size_t)std::max<long long>(r.total_edges, 1) * 4))
+    FAIL(SHADOW_ECUDA, "cudaMalloc(canonical CSR) failed");
+  if (P == 0) { CUDA_TRY(cudaMemsetAsync(r.edge_ptr.p, 0, 4, s->stream)); CUDA_TRY(cudaMemsetAsync(r.rowptr.p, 0, 4, s->stream)); r.canon_valid = true; return 0; }
+  scan_edge_counts_kernel<<<1, 1024, 0, s->stream>>>((const int2 *)r.edge_span.p, P, (int *)r.edge_ptr.p);
+  canonicalize_kernel<<<std::min((P + 7) / 8, s->num_sms * 8), 256, 0, s->stream>>>(
+      (const int *)r.node_ptr.p, (const int2 *)r.edge_span.p, (const int2 *)r.row_span.p, (const int *)r.indices_raw.p,
+      (const uint32_t *)r.orig_edge_raw.p, (const int *)r.edge_ptr.p, P, (int *)r.rowptr.p, (int *)r.indices.p, (uint32_t *)r.orig_edge.p);
+  CUDA_TRY(cudaGetLastError());
+  r.canon_valid = true;
+  return 0;
+}
+
 static int field_lookup(shadow_sampler *s, int branch, int field, void **ptr, int64_t *count) {
   if (s->cur < 0) FAIL(SHADOW_ESTATE, "no sampler call yet");
   if (branch < 0 || branch >= s->num_ens) FAIL(SHADOW_EINVAL, "branch out of range");
@@ -550,6 +601,10 @@ static int field_lookup(shadow_sampler *s, int branch, int field, void **ptr, in
   if (rc) return rc;
   const bool csr = !r.cfg.return_target_only;
   const int P = r.num_subg;
+  if (field == SHADOW_F_EDGE_PTR || field == SHADOW_F_ROWPTR || field == SHADOW_F_INDICES || field == SHADOW_F_ORIG_EDGE) {
+    rc = ensure_canonical(s, r);
+    if (rc) return rc;
+  }
   switch (field) {
     case SHADOW_F_NODE_PTR: *ptr = r.node_ptr.p; *count = csr ? P + 1 : 0; break;
     case SHADOW_F_EDGE_PTR: *ptr = r.edge_ptr.p; *count = csr ? P + 1 : 0; break;
@@ -561,6 +616,10 @@ static int field_lookup(shadow_sampler *s, int branch, int field, void **ptr, in
     case SHADOW_F_NUM_TARGET: *ptr = r.num_target.p; *count = csr ? P : 0; break;
     case SHADOW_F_PPR: *ptr = r.ppr.p; *count = csr ? r.total_nodes : 0; break;
     case SHADOW_F_HOP: *ptr = r.hop.p; *count = (csr && (r.cfg.aug & SHADOW_AUG_HOPS) && !(r.cfg.aug & SHADOW_AUG_DRNLS)) ? r.total_nodes : 0; break;
+    case SHADOW_F_ROW_SPAN: *ptr = r.row_span.p; *count = csr ? 2 * r.total_nodes : 0; break;
+    case SHADOW_F_EDGE_SPAN: *ptr = r.edge_span.p; *count = csr ? 2 * (int64_t)P : 0; break;
+    case SHADOW_F_INDICES_RAW: *ptr = r.indices_raw.p; *count = csr ? r.total_edges : 0; break;
+    case SHADOW_F_ORIG_EDGE_RAW: *ptr = r.orig_edge_raw.p; *count = csr ? r.total_edges : 0; break;
     case SHADOW_F_DRNL: *ptr = r.drnl.p; *count = (csr && (r.cfg.aug & SHADOW_AUG_DRNLS)) ? r.total_nodes : 0; break;
     default: FAIL(SHADOW_EINVAL, "unknown field %d", field);
   }
@@ -578,7 +637,7 @@ extern "C" int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, in
   int rc = field_lookup(s, branch, field, &p, &n);
   if (rc) return rc;
   if (count != n) FAIL(SHADOW_EINVAL, "field %d has %lld elements, caller asked for %lld", field, (long long)n, (long long)count);
-  if (n) CUDA_TRY(cudaMemcpy(dst, p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (n) { CUDA_TRY(cudaMemcpyAsync(dst, p, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream)); CUDA_TRY(cudaStreamSynchronize(s->stream)); }
   return 0;
 }
 

@@ -20,7 +20,7 @@
 #define SAMPLER_BLOCK 128
 
 struct WsLayout {          // byte offsets of the per-CTA workspace (shared memory, or global for huge scopes)
-  uint32_t keys, cval, nodes, pprv, hkeys, hvals, row_s, row_e, row_cnt, row_ins, row_off, row_kept, row_less, row_bug, level, all, dist, fr_a, fr_b, st;
+  uint32_t keys, cval, nodes, pprv, hkeys, hvals, row_s, row_e, row_cnt, row_ins, rowd, row_first, row_last, row_fgt, level, all, dist, fr_a, fr_b, st;
   uint32_t bytes;
 };
 
@@ -52,20 +52,22 @@ struct SampleParams {
   unsigned long long gws_stride;
   // outputs (batch-global block-diagonal CSR)
   long long cap_nodes, cap_edges;
-  int *node_ptr, *edge_ptr, *rowptr, *indices_out, *target, *num_target;
+  int *node_ptr, *indices_out, *target, *num_target;
+  int2 *row_span, *edge_span;        // raw layout: [start,end) of every row / subgraph inside indices_out (see shadow_b200.h)
   uint32_t *orig_node, *orig_edge, *hop, *drnl;
   float *ppr_out;
   // inter-CTA state
-  unsigned long long *status_n, *status_m;   // decoupled look-back words: flag<<62 | value
+  unsigned long long *status_n;      // decoupled look-back words over the node counts: flag<<62 | value
   uint32_t *ticket;
-  long long *totals;                 // [0]=nodes [1]=edges [2]=error bits
+  long long *totals;                 // [0]=nodes [1]=edge cursor (atomic) [2]=error bits
 };
 
 enum { ERR_WS_OVERFLOW = 1, ERR_OUT_OVERFLOW = 2 };
 
 struct Ws {
   unsigned long long *keys; float *cval; uint32_t *nodes; float *pprv; uint32_t *hkeys, *hvals, *row_s, *row_e, *row_cnt,
-      *row_ins, *row_off, *row_kept, *row_less, *row_bug, *level, *all, *dist, *fr_a, *fr_b;
+      *row_ins, *row_first, *row_last, *row_fgt, *level, *all, *dist, *fr_a, *fr_b;
+  uint4 *rowd;
   uint2 *st;
 };
 __device__ __forceinline__ Ws make_ws(unsigned char *b, const WsLayout &L) {
@@ -77,8 +79,8 @@ __device__ __forceinline__ Ws make_ws(unsigned char *b, const WsLayout &L) {
   w.row_cnt = (uint32_t *)(b + L.row_cnt); w.row_ins = (uint32_t *)(b + L.row_ins);
   w.level = (uint32_t *)(b + L.level); w.all = (uint32_t *)(b + L.all);
   w.dist = (uint32_t *)(b + L.dist); w.fr_a = (uint32_t *)(b + L.fr_a); w.fr_b = (uint32_t *)(b + L.fr_b);
-  w.row_off = (uint32_t *)(b + L.row_off); w.row_kept = (uint32_t *)(b + L.row_kept); w.row_less = (uint32_t *)(b + L.row_less);
-  w.row_bug = (uint32_t *)(b + L.row_bug); w.st = (uint2 *)(b + L.st);
+  w.rowd = (uint4 *)(b + L.rowd); w.row_first = (uint32_t *)(b + L.row_first); w.row_last = (uint32_t *)(b + L.row_last);
+  w.row_fgt = (uint32_t *)(b + L.row_fgt); w.st = (uint2 *)(b + L.st);
   return w;
 }
 
@@ -252,14 +254,15 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// The node count of a subgraph is known right after the node-set phase, long before its row scan ends, so it is
+// published early (lookback_publish) and resolved late (lookback_resolve): in practice nobody ever spins.
+__device__ __forceinline__ void lookback_publish(unsigned long long *status, int p, unsigned long long mine) {
+  st_volatile_u64(&status[p], (p == 0 ? LB_INCL : LB_AGG) | mine);
+}
 // called by warp 0; returns the exclusive prefix in all lanes of warp 0
-__device__ inline unsigned long long lookback_exclusive(unsigned long long *status, int p, unsigned long long mine) {
+__device__ inline unsigned long long lookback_resolve(unsigned long long *status, int p, unsigned long long mine) {
   const int lane = lane_id();
-  if (p == 0) {
-    if (lane == 0) st_volatile_u64(&status[0], LB_INCL | mine);
-    return 0;
-  }
-  if (lane == 0) st_volatile_u64(&status[p], LB_AGG | mine);
+  if (p == 0) return 0;
   unsigned long long excl = 0;
   int idx = p - 1;
   for (;;) {
@@ -316,11 +319,12 @@ __device__ __forceinline__ uint32_t drnl_single(uint32_t dx, uint32_t dy) {     
 
 // ------------------------------------------------------------------------------------------------
 // C (fast path): ONE pass over the full-graph rows, flat and chunk-granular.
-// Every row is cut into "items" = the 128-byte lines of `indices` it touches (slot e, the PS.cpp:401 bug slot,
-// included).  The item space of the subgraph is split evenly over the warps; a warp walks its range SCAN_U items
-// at a time, issuing all SCAN_U coalesced 128-byte requests before the first use, probes the shared-memory hash
-// and appends the kept edges -- in slot order, hence already in CSR order -- to its staging region.  Hub rows are
-// simply many items, shared by all warps; no row is read twice and no warp waits on a row-sized latency chain.
+// Every row is cut into "items" of 32 consecutive slots.  The item space of the subgraph is split evenly over the
+// warps; a warp walks its range SCAN_U items at a time, issuing all SCAN_U coalesced 128-byte requests before the
+// first use, probes the shared-memory hash and appends the kept edges -- in slot order, hence already in CSR order --
+// to its staging region.  Hub rows are simply many items, shared by all warps; no row is read twice and no warp
+// waits on a row-sized latency chain.  Everything that is per row (counts, self-edge position, the PS.cpp:401
+// bug slot) is derived afterwards from the staged entries, so the inner loop is load -> probe -> ballot -> store.
 // ------------------------------------------------------------------------------------------------
 #define SCAN_U 8
 #define ST_GT 0x8000u
@@ -331,10 +335,10 @@ __device__ __forceinline__ uint32_t keep_lookup(const KeepCtx &K, uint32_t nb, b
   return sub;
 }
 
-// On entry: ws.row_s / ws.row_e hold the row extents, ws.row_off[0..n] the exclusive item prefix (first item of each row),
-// ws.row_kept / ws.row_less / ws.row_bug are zero / zero / NONE32.   Returns the number of staged entries of this warp.
+// On entry ws.rowd[r] = {row start, row length, node id, first item}, ws.rowd[n].w = num_items.
+// Returns the number of entries this warp staged (entries beyond its region are counted, not stored).
 __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws, int n, uint32_t num_items, const KeepCtx &K,
-                                             bool tconn, bool add_self, uint32_t *overflow) {
+                                             bool tconn) {
   const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
   const uint32_t rcap = (uint32_t)P.ecap / nwarp;              // staging region of this warp
   uint2 *st = ws.st + (size_t)warp * rcap;
@@ -342,52 +346,49 @@ __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws
   const uint32_t i_end = (uint32_t)(((unsigned long long)num_items * (warp + 1)) / nwarp);
   if (i_begin >= i_end) return 0;
   int row;
-  { int lo = 0, hi = n; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.row_off[mid] <= i_begin) lo = mid; else hi = mid; } row = lo; }
+  { int lo = 0, hi = n; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.rowd[mid].w <= i_begin) lo = mid; else hi = mid; } row = lo; }
+  uint4 d = ws.rowd[row];
+  uint32_t next_off = ws.rowd[row + 1].w;
   uint32_t cnt = 0;
   for (uint32_t ib = i_begin; ib < i_end; ib += SCAN_U) {
-    uint32_t nbv[SCAN_U], posv[SCAN_U];
+    uint32_t nbv[SCAN_U], cv[SCAN_U];
     int rowv[SCAN_U];
 #pragma unroll
     for (int u = 0; u < SCAN_U; u++) {
       const uint32_t it = ib + u;
-      nbv[u] = NONE32; posv[u] = 0; rowv[u] = row;
+      nbv[u] = NONE32; cv[u] = 0; rowv[u] = row;
       if (it < i_end) {
-        while (it >= ws.row_off[row + 1]) row++;
+        while (it >= next_off) { row++; d = ws.rowd[row]; next_off = ws.rowd[row + 1].w; }
         rowv[u] = row;
-        const uint32_t s = ws.row_s[row], e = ws.row_e[row];
-        const uint32_t c = (s & ~31u) + (it - ws.row_off[row]) * 32u + lane;
-        const bool bug_ok = !P.fixed_mode && e < P.num_edges;                         // slot e: PS.cpp:401
-        posv[u] = c;
-        if (c >= s && (c < e || (bug_ok && c == e))) nbv[u] = ldg_stream_u32(P.indices + c);
+        const uint32_t j = (it - d.w) * 32u + lane;
+        cv[u] = d.x + j;
+        if (j < d.y) nbv[u] = ldg_stream_u32(P.indices + cv[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < SCAN_U; u++) {
-      if (ib + u >= i_end) break;
-      const int r = rowv[u];
-      const uint32_t v = ws.nodes[r], e = ws.row_e[r];
-      uint32_t nb = nbv[u];
-      if (posv[u] == e && nb != NONE32) { ws.row_bug[r] = nb; nb = NONE32; }        // bug-slot candidate, resolved after the scan
-      bool v_is_t = false;
-      if (!tconn) for (int j = 0; j < K.nt; j++) v_is_t |= (K.roots[j] == v);
-      const uint32_t sub = (nb != NONE32) ? keep_lookup(K, nb, v_is_t) : NONE32;
-      const uint32_t mk = __ballot_sync(0xffffffffu, sub != NONE32);
-      if (add_self) {
-        const uint32_t lm = __ballot_sync(0xffffffffu, sub != NONE32 && nb < v);
-        const bool pres = __any_sync(0xffffffffu, nb == v);
-        if (lane == 0 && (lm || pres)) atomicAdd(&ws.row_less[r], (uint32_t)__popc(lm) | (pres ? 0x80000000u : 0u));
+      const uint32_t nb = nbv[u];
+      uint32_t h = hash_slot(nb, K.hshift);
+      uint32_t k = K.hk[h];
+      while (k != nb && k != NONE32) { h = (h + 1) & K.hmask; k = K.hk[h]; }
+      bool hit = (k == nb) && (nb != NONE32);
+      if (!tconn && hit) {                                     // multi-root groups: no target-target edges (PS.cpp:412-418)
+        const uint32_t v = ws.nodes[rowv[u]];
+        bool v_t = false, nb_t = false;
+        for (int q = 0; q < K.nt; q++) { v_t |= (K.roots[q] == v); nb_t |= (K.roots[q] == nb); }
+        hit = !(v_t && nb_t);
       }
+      const uint32_t mk = __ballot_sync(0xffffffffu, hit);
       if (mk) {
-        if (sub != NONE32) {
+        if (hit) {
           const uint32_t at = cnt + __popc(mk & lanemask_lt());
-          if (at < rcap) st[at] = make_uint2(sub | (nb > v ? ST_GT : 0u) | ((uint32_t)r << 16), posv[u]);       // :420-422
+          const uint32_t r = (uint32_t)rowv[u];
+          if (at < rcap) st[at] = make_uint2(K.hv[h] | (nb > ws.nodes[r] ? ST_GT : 0u) | (r << 16), cv[u]);       // :420-422
         }
-        if (lane == 0) atomicAdd(&ws.row_kept[r], (uint32_t)__popc(mk));
         cnt += __popc(mk);
       }
     }
   }
-  if (cnt > rcap && lane == 0) *overflow = 1;
   return cnt;
 }
 
@@ -395,7 +396,7 @@ __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
 template <bool GWS>
-__global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const SampleParams P) {
+__global__ void __launch_bounds__(SAMPLER_BLOCK, 8) sample_induce_kernel(const SampleParams P) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ uint32_t s_warp_sums[33];
   __shared__ int s_p, s_n;
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
     }
     bool ws_overflow = (n < 0) || (n > P.ncap);
     if (ws_overflow) n = 0;
+    if (threadIdx.x == 0) lookback_publish(P.status_n, p, (unsigned long long)n);
     __syncthreads();
 
     // ---------------- B: orig -> sub hash, targets, row extents ----------------
@@ -458,10 +460,8 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
       const uint32_t s = P.indptr[v], e = P.indptr[v + 1];
       ws.row_s[i] = s; ws.row_e[i] = e;
       if (!GWS && P.ecap > 0) {
-        // items = 128-byte lines of `indices` covered by [s, e_last]; slot e is included when the PS.cpp:401 bug slot applies
-        const bool bug_ok = !P.fixed_mode && e < P.num_edges;
-        const uint32_t items = bug_ok ? (e >> 5) - (s >> 5) + 1u : (e > s ? ((e - 1u) >> 5) - (s >> 5) + 1u : 0u);
-        ws.row_off[i] = items; ws.row_kept[i] = 0; ws.row_less[i] = 0; ws.row_bug[i] = NONE32;
+        ws.row_cnt[i] = (e - s + 31u) >> 5;                  // items of 32 slots
+        ws.row_first[i] = 0; ws.row_last[i] = 0; ws.row_fgt[i] = NONE32; ws.row_ins[i] = 0;
       }
     }
     __syncthreads();
@@ -475,32 +475,61 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
     // ---------------- C: row scan ----------------
     bool staged = false;
     if (!GWS && P.ecap > 0) {                              // single pass, kept edges staged in shared memory
-      const uint32_t num_items = block_exclusive_scan(ws.row_off, n, s_warp_sums);
-      if (threadIdx.x == 0) { ws.row_off[n] = num_items; s_tmp[0] = 0; }
+      const uint32_t num_items = block_exclusive_scan(ws.row_cnt, n, s_warp_sums);
+      for (int i = threadIdx.x; i <= n; i += blockDim.x)
+        ws.rowd[i] = (i < n) ? make_uint4(ws.row_s[i], ws.row_e[i] - ws.row_s[i], ws.nodes[i], ws.row_cnt[i]) : make_uint4(0, 0, 0, num_items);
       __syncthreads();
       KeepCtx KC;
       KC.hk = ws.hkeys; KC.hv = ws.hvals; KC.hmask = hmask; KC.hshift = P.hshift; KC.roots = s_roots; KC.nt = nt;
-      const uint32_t wcnt = scan_items_staged(P, ws, n, num_items, KC, tconn, add_self, &s_tmp[0]);
+      const uint32_t wcnt = scan_items_staged(P, ws, n, num_items, KC, tconn);
+      const uint32_t rcap = (uint32_t)P.ecap / nwarp;
       if (lane == 0) s_scan[warp] = wcnt;
       __syncthreads();
-      staged = (s_tmp[0] == 0);
-      // per row: resolve the self-edge insertion and the bug slot now that the whole row has been seen
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t lr = ws.row_less[i], v = ws.nodes[i];
-        const bool inserting = add_self && !(lr >> 31);                                            // PS.cpp:386-400
-        uint32_t bsub = NONE32;
-        if (!inserting && ws.row_bug[i] != NONE32) {
+      uint32_t ktot = 0;
+      staged = true;
+      for (int w = 0; w < nwarp; w++) { ktot += s_scan[w]; staged &= (s_scan[w] <= rcap); }
+      if (staged) {
+        // row boundaries inside the staged stream (it is in CSR order): first/last entry of each row, first entry above v,
+        // and whether the row already holds its self loop (a kept entry whose sub id is the row itself)
+        for (uint32_t g = threadIdx.x; g < ktot; g += blockDim.x) {
+          uint32_t wb = 0; int w = 0;
+          while (g >= wb + s_scan[w]) { wb += s_scan[w]; w++; }
+          const uint32_t x = ws.st[(size_t)w * rcap + (g - wb)].x;
+          uint32_t xp = NONE32, xn = NONE32;
+          if (g > 0) { const uint32_t gp = g - 1; uint32_t wb2 = 0; int w2 = 0; while (gp >= wb2 + s_scan[w2]) { wb2 += s_scan[w2]; w2++; } xp = ws.st[(size_t)w2 * rcap + (gp - wb2)].x; }
+          if (g + 1 < ktot) { const uint32_t gn = g + 1; uint32_t wb2 = 0; int w2 = 0; while (gn >= wb2 + s_scan[w2]) { wb2 += s_scan[w2]; w2++; } xn = ws.st[(size_t)w2 * rcap + (gn - wb2)].x; }
+          const uint32_t row = x >> 16;
+          const bool first = (g == 0) || (xp >> 16) != row, last = (g + 1 == ktot) || (xn >> 16) != row;
+          if (first) ws.row_first[row] = g;
+          if (last) ws.row_last[row] = g + 1;
+          if ((x & ST_GT) && (first || !(xp & ST_GT))) ws.row_fgt[row] = g;
+          if ((x & 0x7fffu) == row) ws.row_ins[row] = 1;                                             // self loop present
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const uint32_t v = ws.nodes[i], e = ws.row_e[i];
+          const uint32_t kept = ws.row_last[i] - ws.row_first[i];
           bool v_is_t = false;
           if (!tconn) for (int j = 0; j < nt; j++) v_is_t |= (s_roots[j] == v);
-          bsub = keep_lookup(KC, ws.row_bug[i], v_is_t);
+          bool present = ws.row_ins[i] != 0;
+          if (add_self && v_is_t && !present) {             // a dropped target-target self loop still counts as present: binary search (:386-400)
+            uint32_t lo = ws.row_s[i], hi = e;
+            while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (P.indices[mid] < v) lo = mid + 1; else hi = mid; }
+            present = (lo < e) && (P.indices[lo] == v);
+          }
+          const bool inserting = add_self && !present;                                             // PS.cpp:386-400
+          uint32_t bsub = NONE32;                          // PS.cpp:401: without an insertion, slot e (first slot of the next row) is tested too
+          if (!inserting && !P.fixed_mode && e < P.num_edges) bsub = keep_lookup(KC, __ldg(P.indices + e), v_is_t);
+          const uint32_t fgt = ws.row_fgt[i];
+          const uint32_t less = (fgt == NONE32) ? kept : fgt - ws.row_first[i];                     // kept entries below v
+          ws.row_fgt[i] = bsub;                              // reuse: bug-slot column (or NONE)
+          ws.row_ins[i] = inserting ? less : NONE32;
+          ws.row_cnt[i] = kept + (inserting ? 1u : 0u) + (bsub != NONE32 ? 1u : 0u);
         }
-        ws.row_bug[i] = bsub;
-        ws.row_ins[i] = inserting ? (lr & 0x7fffffffu) : NONE32;
-        ws.row_cnt[i] = ws.row_kept[i] + (inserting ? 1u : 0u) + (bsub != NONE32 ? 1u : 0u);
       }
       __syncthreads();
-      block_exclusive_scan(ws.row_kept, n, s_warp_sums);                                           // real kept edges before each row
-    } else {
+    }
+    if (!staged) {
     // count pass of the generic two-pass path (warp per row)
     for (int r = warp; r < n; r += nwarp) {
       const uint32_t v = ws.nodes[r], s = ws.row_s[r], e = ws.row_e[r];
@@ -530,16 +559,17 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
       }
       if (lane == 0) { ws.row_cnt[r] = kept + (inserting ? 1u : 0u); ws.row_ins[r] = inserting ? kept_less : NONE32; }
     }
-        }
+    }
     __syncthreads();
     const uint32_t m = block_exclusive_scan(ws.row_cnt, n, s_warp_sums);      // local indptr (:428-431)
     if (threadIdx.x == 0) ws.row_cnt[n] = m;
 
     // ---------------- look-back: batch-global offsets ----------------
+    // rows stay in subgraph order (look-back over n, resolved long after it was published); the edge block of a
+    // subgraph is placed wherever the cursor stands -- no CTA ever waits for another one's row scan
     if (warp == 0) {
-      unsigned long long nb = lookback_exclusive(P.status_n, p, (unsigned long long)n);
-      unsigned long long eb = lookback_exclusive(P.status_m, p, (unsigned long long)m);
-      if (lane == 0) { s_base[0] = (long long)nb; s_base[1] = (long long)eb; }
+      unsigned long long nb = lookback_resolve(P.status_n, p, (unsigned long long)n);
+      if (lane == 0) { s_base[0] = (long long)nb; s_base[1] = (long long)atomicAdd((unsigned long long *)&P.totals[1], (unsigned long long)m); }
     }
     __syncthreads();
     const long long node_base = s_base[0], edge_base = s_base[1];
@@ -547,18 +577,18 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
     if (threadIdx.x == 0) {
       if (ws_overflow) atomicOr((unsigned long long *)&P.totals[2], (unsigned long long)ERR_WS_OVERFLOW);
       if (out_overflow) atomicOr((unsigned long long *)&P.totals[2], (unsigned long long)ERR_OUT_OVERFLOW);
-      if (p == P.num_subg - 1) { P.totals[0] = node_base + n; P.totals[1] = edge_base + (long long)m; }
+      if (p == P.num_subg - 1) P.totals[0] = node_base + n;
     }
     if (!out_overflow) {
       if (threadIdx.x == 0) {
-        P.node_ptr[p] = (int)node_base; P.edge_ptr[p] = (int)edge_base; P.num_target[p] = nt;
-        if (p == P.num_subg - 1) { P.node_ptr[p + 1] = (int)(node_base + n); P.edge_ptr[p + 1] = (int)(edge_base + m); P.rowptr[node_base + n] = (int)(edge_base + m); }
+        P.node_ptr[p] = (int)node_base; P.edge_span[p] = make_int2((int)edge_base, (int)(edge_base + m)); P.num_target[p] = nt;
+        if (p == P.num_subg - 1) P.node_ptr[p + 1] = (int)(node_base + n);
       }
       if (threadIdx.x < P.num_roots) P.target[r0 + threadIdx.x] = (threadIdx.x < nt) ? (int)(node_base + s_tl[threadIdx.x]) : -1;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         P.orig_node[node_base + i] = ws.nodes[i];
         P.ppr_out[node_base + i] = ws.pprv[i];
-        P.rowptr[node_base + i] = (int)(edge_base + ws.row_cnt[i]);
+        P.row_span[node_base + i] = make_int2((int)(edge_base + ws.row_cnt[i]), (int)(edge_base + ws.row_cnt[i + 1]));
       }
       // ---------------- emit the CSR ----------------
       if (staged) {                                        // staged rows -> CSR order already; no second read of the graph
@@ -570,7 +600,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
           while (g >= wb + s_scan[w]) { wb += s_scan[w]; w++; }
           const uint2 ent = ws.st[(size_t)w * rcap + (g - wb)];
           const uint32_t row = ent.x >> 16;
-          const long long pos = edge_base + ws.row_cnt[row] + (g - ws.row_kept[row]) + ((ws.row_ins[row] != NONE32 && (ent.x & ST_GT)) ? 1 : 0);
+          const long long pos = edge_base + ws.row_cnt[row] + (g - ws.row_first[row]) + ((ws.row_ins[row] != NONE32 && (ent.x & ST_GT)) ? 1 : 0);
           P.indices_out[pos] = (int)(node_base + (ent.x & 0x7fffu));
           P.orig_edge[pos] = ent.y;
         }
@@ -579,9 +609,9 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK) sample_induce_kernel(const Samp
             const long long pos = edge_base + ws.row_cnt[r] + ws.row_ins[r];
             P.indices_out[pos] = (int)(node_base + r); P.orig_edge[pos] = NONE32;
           }
-          if (ws.row_bug[r] != NONE32) {
+          if (ws.row_fgt[r] != NONE32) {
             const long long pos = edge_base + ws.row_cnt[r + 1] - 1;
-            P.indices_out[pos] = (int)(node_base + ws.row_bug[r]); P.orig_edge[pos] = ws.row_e[r];
+            P.indices_out[pos] = (int)(node_base + ws.row_fgt[r]); P.orig_edge[pos] = ws.row_e[r];
           }
         }
       } else
