@@ -132,15 +132,27 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
   if (ncap > (1ll << 28) || ccap > (1ll << 28) || acap > (1ll << 28)) FAIL(SHADOW_ECAP, "sampler scope too large (ncap=%lld)", ncap);
   o->ncap = (int)ncap; o->ccap = (int)ccap; o->acap = (int)acap;
   o->ccap2 = next_pow2((int)ccap); o->acap2 = next_pow2((int)acap);
-  o->hcap = std::max(32, next_pow2(2 * (int)ncap));
-  int lg = 0; while ((1 << lg) < o->hcap) lg++;
-  o->hshift = 32 - lg;
+  o->hcap = std::max(64, next_pow2(4 * (int)ncap));          // slots; buckets of 4
+  int lg = 0; while ((1 << lg) < o->hcap / 4) lg++;
+  o->hshift = 32 - lg;                                     // hash -> bucket index
   o->max_draws = max_draws;
   WsLayout &L = o->L;
   uint32_t off = 0;
   auto take = [&](size_t bytes) { uint32_t r = off; off = align16(off + (uint32_t)bytes); return r; };
+  // region 1: node-set scratch (dead once the node set is final) -- the edge staging area of the scan overlays it
   L.keys = take((size_t)o->ccap2 * 8);
   L.cval = take((size_t)o->ccap * 4);
+  L.level = take((size_t)o->ncap * 4);
+  L.all = take((size_t)o->acap2 * 4);
+  const uint32_t region1 = off;
+  // staged-edge capacity of the single-pass path (15-bit sub ids); 0 => generic two-pass path
+  {
+    const char *env = getenv("SHADOW_ECAP_MULT");
+    const int mult = env ? atoi(env) : 6;
+    o->ecap = (o->ncap <= 32767 && mult > 0) ? std::min(16384, std::max(512, mult * o->ncap)) : 0;
+    L.st = 0;
+    off = std::max(region1, align16((uint32_t)o->ecap * 8));
+  }
   L.nodes = take((size_t)o->ncap * 4);
   L.pprv = take((size_t)o->ncap * 4);
   L.hkeys = take((size_t)o->hcap * 4);
@@ -153,21 +165,11 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
   L.row_first = take((size_t)o->ncap * 4);
   L.row_last = take((size_t)o->ncap * 4);
   L.row_fgt = take((size_t)o->ncap * 4);
-  L.level = take((size_t)o->ncap * 4);
-  L.all = take((size_t)o->acap2 * 4);
   const bool bfs = (c.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) != 0;
   L.dist = take(bfs ? (size_t)o->ncap * 4 : 0);
   L.fr_a = take(bfs ? (size_t)o->ncap * 4 : 0);
   L.fr_b = take(bfs ? (size_t)o->ncap * 4 : 0);
-  // staged-edge capacity of the single-pass path (16-bit sub ids); 0 => generic two-pass path
-  {
-    const char *env = getenv("SHADOW_ECAP_MULT");
-    const int mult = env ? atoi(env) : 8;
-    o->ecap = (o->ncap <= 32767 && mult > 0) ? std::min(16384, std::max(512, mult * o->ncap)) : 0;
-    const uint32_t base_bytes = off;
-    L.st = take((size_t)o->ecap * 8);
-    if (off > 200 * 1024) { o->ecap = 0; off = base_bytes; L.st = 0; }
-  }
+  if (off > 200 * 1024) o->ecap = 0;               // too big for shared memory anyway: global-workspace variant, generic path
   L.bytes = off;
   return 0;
 }

@@ -18,6 +18,9 @@
 
 #define SHADOW_MAX_ROOTS 4
 #define SAMPLER_BLOCK 128
+#ifndef SAMPLER_MIN_BLOCKS
+#define SAMPLER_MIN_BLOCKS 12
+#endif
 
 struct WsLayout {          // byte offsets of the per-CTA workspace (shared memory, or global for huge scopes)
   uint32_t keys, cval, nodes, pprv, hkeys, hvals, row_s, row_e, row_cnt, row_ins, rowd, row_first, row_last, row_fgt, level, all, dist, fr_a, fr_b, st;
@@ -104,14 +107,28 @@ __device__ inline uint32_t block_ordered_compact(int n, Pred pred, Emit emit, ui
   return carry;
 }
 
-__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
-__device__ __forceinline__ uint32_t hash_lookup(const uint32_t *hk, const uint32_t *hv, uint32_t mask, int shift, uint32_t key) {
-  uint32_t h = hash_slot(key, shift);
+// orig -> sub map: open addressing over BUCKETS of 4 keys (one 16-byte shared-memory load tests 4 slots, so a probe
+// almost never needs a second step and the warp-wide worst case stays at one iteration).  Buckets fill in slot order.
+__device__ __forceinline__ uint32_t hash_bucket(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
+__device__ __forceinline__ uint32_t hash_lookup(const uint32_t *hk, const uint32_t *hv, uint32_t bmask, int shift, uint32_t key) {
+  uint32_t b = hash_bucket(key, shift);
   for (;;) {
-    uint32_t k = hk[h];
-    if (k == key) return hv[h];
-    if (k == NONE32) return NONE32;
-    h = (h + 1) & mask;
+    const uint4 kk = reinterpret_cast<const uint4 *>(hk)[b];
+    if (kk.x == key) return hv[4 * b];
+    if (kk.y == key) return hv[4 * b + 1];
+    if (kk.z == key) return hv[4 * b + 2];
+    if (kk.w == key) return hv[4 * b + 3];
+    if (kk.w == NONE32) return NONE32;
+    b = (b + 1) & bmask;
+  }
+}
+__device__ __forceinline__ void hash_insert(uint32_t *hk, uint32_t *hv, uint32_t bmask, int shift, uint32_t key, uint32_t val) {
+  uint32_t b = hash_bucket(key, shift);
+  for (;;) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (atomicCAS(&hk[4 * b + j], NONE32, key) == NONE32) { hv[4 * b + j] = val; return; }
+    b = (b + 1) & bmask;
   }
 }
 
@@ -337,8 +354,8 @@ __device__ __forceinline__ uint32_t keep_lookup(const KeepCtx &K, uint32_t nb, b
 
 // On entry ws.rowd[r] = {row start, row length, node id, first item}, ws.rowd[n].w = num_items.
 // Returns the number of entries this warp staged (entries beyond its region are counted, not stored).
-__device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws, int n, uint32_t num_items, const KeepCtx &K,
-                                             bool tconn) {
+template <bool TCONN>
+__device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws, int n, uint32_t num_items, const KeepCtx &K) {
   const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
   const uint32_t rcap = (uint32_t)P.ecap / nwarp;              // staging region of this warp
   uint2 *st = ws.st + (size_t)warp * rcap;
@@ -347,45 +364,55 @@ __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws
   if (i_begin >= i_end) return 0;
   int row;
   { int lo = 0, hi = n; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.rowd[mid].w <= i_begin) lo = mid; else hi = mid; } row = lo; }
-  uint4 d = ws.rowd[row];
-  uint32_t next_off = ws.rowd[row + 1].w;
+  const uint4 *hb = reinterpret_cast<const uint4 *>(K.hk);
   uint32_t cnt = 0;
   for (uint32_t ib = i_begin; ib < i_end; ib += SCAN_U) {
-    uint32_t nbv[SCAN_U], cv[SCAN_U];
-    int rowv[SCAN_U];
+    // lanes 0..SCAN_U-1 resolve one item each (row, first slot, slots left in the row), then broadcast
+    int r = row;
+    uint32_t cbase = 0, rem = 0;
+    if (lane < SCAN_U && ib + lane < i_end) {
+      const uint32_t it = ib + lane;
+      while (it >= ws.rowd[r + 1].w) r++;
+      const uint4 d = ws.rowd[r];
+      const uint32_t j0 = (it - d.w) * 32u;
+      cbase = d.x + j0; rem = d.y - j0;
+    }
+    row = __shfl_sync(0xffffffffu, r, (int)min((uint32_t)SCAN_U, i_end - ib) - 1);
+    uint32_t nbv[SCAN_U];
 #pragma unroll
     for (int u = 0; u < SCAN_U; u++) {
-      const uint32_t it = ib + u;
-      nbv[u] = NONE32; cv[u] = 0; rowv[u] = row;
-      if (it < i_end) {
-        while (it >= next_off) { row++; d = ws.rowd[row]; next_off = ws.rowd[row + 1].w; }
-        rowv[u] = row;
-        const uint32_t j = (it - d.w) * 32u + lane;
-        cv[u] = d.x + j;
-        if (j < d.y) nbv[u] = ldg_stream_u32(P.indices + cv[u]);
-      }
+      const uint32_t rm = __shfl_sync(0xffffffffu, rem, u);
+      const uint32_t c = __shfl_sync(0xffffffffu, cbase, u) + lane;
+      nbv[u] = ((uint32_t)lane < rm) ? ldg_stream_u32(P.indices + c) : NONE32;
     }
 #pragma unroll
     for (int u = 0; u < SCAN_U; u++) {
       const uint32_t nb = nbv[u];
-      uint32_t h = hash_slot(nb, K.hshift);
-      uint32_t k = K.hk[h];
-      while (k != nb && k != NONE32) { h = (h + 1) & K.hmask; k = K.hk[h]; }
-      bool hit = (k == nb) && (nb != NONE32);
-      if (!tconn && hit) {                                     // multi-root groups: no target-target edges (PS.cpp:412-418)
-        const uint32_t v = ws.nodes[rowv[u]];
-        bool v_t = false, nb_t = false;
-        for (int q = 0; q < K.nt; q++) { v_t |= (K.roots[q] == v); nb_t |= (K.roots[q] == nb); }
-        hit = !(v_t && nb_t);
+      uint32_t b = hash_bucket(nb, K.hshift);
+      uint4 kk = hb[b];
+      bool hit = (kk.x == nb) || (kk.y == nb) || (kk.z == nb) || (kk.w == nb);
+      while (!hit && kk.w != NONE32) {                         // bucket full and no match: next bucket (rare)
+        b = (b + 1) & K.hmask; kk = hb[b];
+        hit = (kk.x == nb) || (kk.y == nb) || (kk.z == nb) || (kk.w == nb);
       }
+      hit = hit && (nb != NONE32);
       const uint32_t mk = __ballot_sync(0xffffffffu, hit);
-      if (mk) {
-        if (hit) {
-          const uint32_t at = cnt + __popc(mk & lanemask_lt());
-          const uint32_t r = (uint32_t)rowv[u];
-          if (at < rcap) st[at] = make_uint2(K.hv[h] | (nb > ws.nodes[r] ? ST_GT : 0u) | (r << 16), cv[u]);       // :420-422
+      if (mk) {                                                // everything below is the rare path (~3 % of the slots are kept)
+        const uint32_t rr = (uint32_t)__shfl_sync(0xffffffffu, r, u);
+        const uint32_t c = __shfl_sync(0xffffffffu, cbase, u) + lane;
+        if (!TCONN && hit) {                                   // multi-root groups: no target-target edges (PS.cpp:412-418)
+          const uint32_t v = ws.nodes[rr];
+          bool v_t = false, nb_t = false;
+          for (int q = 0; q < K.nt; q++) { v_t |= (K.roots[q] == v); nb_t |= (K.roots[q] == nb); }
+          hit = !(v_t && nb_t);
         }
-        cnt += __popc(mk);
+        const uint32_t mk2 = TCONN ? mk : __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const uint32_t slot = 4u * b + (kk.x == nb ? 0u : kk.y == nb ? 1u : kk.z == nb ? 2u : 3u);
+          const uint32_t at = cnt + __popc(mk2 & lanemask_lt());
+          if (at < rcap) st[at] = make_uint2(K.hv[slot] | (nb > ws.nodes[rr] ? ST_GT : 0u) | (rr << 16), c);       // :420-422
+        }
+        cnt += __popc(mk2);
       }
     }
   }
@@ -396,18 +423,18 @@ __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
 template <bool GWS>
-__global__ void __launch_bounds__(SAMPLER_BLOCK, 8) sample_induce_kernel(const SampleParams P) {
+__global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_induce_kernel(const SampleParams P) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ uint32_t s_warp_sums[33];
   __shared__ int s_p, s_n;
-  __shared__ uint32_t s_cnt, s_cut, s_tmp[2], s_scan[32];
+  __shared__ uint32_t s_cnt, s_cut, s_scan[32];
   __shared__ long long s_base[2];
   __shared__ uint32_t s_roots[SHADOW_MAX_ROOTS], s_tl[SHADOW_MAX_ROOTS];
 
   unsigned char *wsb = GWS ? (P.gws + (size_t)blockIdx.x * P.gws_stride) : smem_dyn;
   const Ws ws = make_ws(wsb, P.L);
   const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
-  const uint32_t hmask = (uint32_t)P.hcap - 1u;
+  const uint32_t hmask = ((uint32_t)P.hcap >> 2) - 1u;      // bucket mask
 
   for (;;) {
     __syncthreads();
@@ -454,9 +481,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, 8) sample_induce_kernel(const S
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const uint32_t v = ws.nodes[i];
-      uint32_t h = hash_slot(v, P.hshift);
-      while (atomicCAS(&ws.hkeys[h], NONE32, v) != NONE32) h = (h + 1) & hmask;
-      ws.hvals[h] = (uint32_t)i;
+      hash_insert(ws.hkeys, ws.hvals, hmask, P.hshift, v, (uint32_t)i);
       const uint32_t s = P.indptr[v], e = P.indptr[v + 1];
       ws.row_s[i] = s; ws.row_e[i] = e;
       if (!GWS && P.ecap > 0) {
@@ -481,7 +506,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, 8) sample_induce_kernel(const S
       __syncthreads();
       KeepCtx KC;
       KC.hk = ws.hkeys; KC.hv = ws.hvals; KC.hmask = hmask; KC.hshift = P.hshift; KC.roots = s_roots; KC.nt = nt;
-      const uint32_t wcnt = scan_items_staged(P, ws, n, num_items, KC, tconn);
+      const uint32_t wcnt = tconn ? scan_items_staged<true>(P, ws, n, num_items, KC) : scan_items_staged<false>(P, ws, n, num_items, KC);
       const uint32_t rcap = (uint32_t)P.ecap / nwarp;
       if (lane == 0) s_scan[warp] = wcnt;
       __syncthreads();
