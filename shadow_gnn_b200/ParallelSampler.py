@@ -255,10 +255,10 @@ class ParallelSampler:
         self.num_ensemble = int(num_subgraphs_ensemble)
         return self
 
-    def __del__(self):
+    def __del__(self, _destroy=lib.shadow_sampler_destroy):
         h = getattr(self, "_h", None)
         if h:
-            lib.shadow_sampler_destroy(h)
+            _destroy(h)
             self._h = None
 
     # ---- PS.cpp:726-734 ----

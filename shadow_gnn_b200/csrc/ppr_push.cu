@@ -1,5 +1,6 @@
 // ppr_push.cu -- preproc_ppr_approximate (PS.cpp:237-344) and its binary cache (PS.cpp:94-231).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(128) ppr_push_kernel(const uint32_t *__restric
         if (ins) { uint32_t pos = n_act + __popc(bm & ((1u << lane) - 1u)); if (pos < act_cap) act[pos] = u; }
         n_act += __popc(bm);
         n_used += cntnew;                                                      // occupied slots
-        if (n_act > act_cap || n_used > (tab_cap >> 1) + (tab_cap >> 2)) { overflow = true; }
+        if (n_act > act_cap || n_used > (tab_cap >> 1) + (tab_cap >> 2)) { overflow = true; break; }   // before the table can fill up
       }
       __syncwarp();
       if (overflow) break;
@@ -278,6 +279,7 @@ int shadow_ppr_push_gpu(shadow_sampler *s, const uint32_t *targets_host, uint64_
     cudaFree(tabs); cudaFree(acts); cudaFree(sbuf);
     remaining = 0;
     for (uint64_t i = 0; i < T; i++) remaining += (status[i] != 1);
+    if (getenv("SHADOW_DEBUG")) fprintf(stderr, "[ppr_push] pass %d tab_cap=%u warps=%lld remaining=%llu\n", pass, tab_cap, warps, (unsigned long long)remaining);
   }
   if (remaining) FAIL(SHADOW_ECAP, "%llu PPR targets exceed the largest push table", (unsigned long long)remaining);
   CUDA_TRY(cudaMemcpy(nb.data(), d_nb, T * k * 4, cudaMemcpyDeviceToHost));

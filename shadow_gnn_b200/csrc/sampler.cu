@@ -304,12 +304,16 @@ extern "C" int shadow_sampler_shuffle_targets(shadow_sampler *s, const uint32_t 
   if (s->targets.ensure((size_t)std::max(n, 1u) * 4)) FAIL(SHADOW_ECUDA, "cudaMalloc(targets) failed");
   CUDA_TRY(cudaMemcpyAsync(s->targets.p, t, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
-  s->targets_ptr = (const uint32_t *)s->targets.p; s->T = n;
+  s->targets_ptr = (const uint32_t *)s->targets.p;
+  if (s->T != n) s->idx_root = 0;      // the reference asserts equal sizes (PS.cpp:40); a new-size list restarts the traversal
+  s->T = n;
   return 0;
 }
 extern "C" int shadow_sampler_shuffle_targets_dev(shadow_sampler *s, const uint32_t *t, uint32_t n) {
   if (!s || (!t && n)) FAIL(SHADOW_EINVAL, "NULL argument");
-  s->targets_ptr = t; s->T = n;
+  s->targets_ptr = t;
+  if (s->T != n) s->idx_root = 0;
+  s->T = n;
   return 0;
 }
 extern "C" int shadow_sampler_drop_full_graph_info(shadow_sampler *s) {      // PS.cpp:22-34
@@ -505,6 +509,7 @@ extern "C" int shadow_sampler_sample(shadow_sampler *s, const shadow_sampler_cfg
     if ((cfgs[i].method == SHADOW_PPR || cfgs[i].method == SHADOW_PPR_ST) && cfgs[i].k < 0) FAIL(SHADOW_EINVAL, "ppr k must be >= 0");
   }
   // _get_roots_p, sequential branch (PS.cpp:458-468)
+  if (s->idx_root > s->T) s->idx_root = 0;
   const uint32_t T = s->T, idx_start = s->idx_root;
   const uint64_t want = (uint64_t)idx_start + (uint64_t)num_roots * (uint64_t)s->per_batch;
   const uint32_t idx_end = (uint32_t)std::min<uint64_t>(want, T);
