@@ -152,6 +152,52 @@ int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, int field, vo
 int shadow_gather_rows_f32(const float *feat_dev, int64_t num_rows, int32_t dim, const uint32_t *ids_dev,
                            int64_t n, float *out_dev, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------- */
+/* message-passing layers (shaDow/layers.py) on the RAW batch layout.  row_span = int32 pairs      */
+/* [start,end) per row into col[] / val[]; column id = col[p] - col_off; fp32; all pointers device. */
+/* ---------------------------------------------------------------------------------------------- */
+/* adjacency values: data = 1 (PS.cpp:411,423) */
+int shadow_edge_vals_fill(const int32_t *row_span, int32_t n, float *val, float x, void *cuda_stream);
+/* dropedge: int(e*p) indices drawn with replacement are zeroed (graph_utils.py:86-88, layers.py:516-519,593-596);
+ * row_ord[n+1] = exclusive prefix sum of the row lengths (ordinal position of every row's first edge) */
+int shadow_edge_vals_dropedge(const int32_t *row_span, const int32_t *row_ord, int32_t n, int32_t num_drop, uint32_t seed,
+                              uint32_t step, float *val, void *cuda_stream);
+/* mode 0: adj_norm_rw (graph_utils.py:89-94); mode 1: GIN rescale deg_orig/deg_dropped (layers.py:520-522) */
+int shadow_edge_vals_row_normalize(const int32_t *row_span, int32_t n, int32_t mode, float *val, void *cuda_stream);
+/* adj_norm_sym (graph_utils.py:109-145): symmetric survival of `mask` (when dropedge > 0) then D^-1/2 A D^-1/2 */
+int shadow_edge_vals_sym_normalize(const int32_t *row_span, const int32_t *col, int32_t col_off, int32_t n, int32_t symmetric_survival,
+                                   const float *mask, float *val, float *deg_scratch, void *cuda_stream);
+/* torch.sparse.mm(adj, X) (layers.py:326-327,433,475,523): Y = beta*Y + A X ; backward dX += A^T dY (dX pre-zeroed by the caller) */
+int shadow_spmm_csr_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *X, float *Y,
+                            int32_t n, int32_t F, float beta, void *cuda_stream);
+int shadow_spmm_csr_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *dY, float *dX,
+                            int32_t n, int32_t F, void *cuda_stream);
+/* act + norm_feat (layers.py:329-338; F_ACT layers.py:26-39): act ids 0 relu, 1 I, 2 elu, 3 tanh, 4 leakyrelu(0.2) */
+int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float *scale, const float *offset, float *out, int32_t ldo,
+                            float *mean, float *rstd, int32_t n, int32_t D, int32_t act, int32_t do_norm, int32_t accumulate,
+                            void *cuda_stream);
+int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const float *Z, int32_t ldz, const float *scale, const float *mean,
+                            const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, int32_t n, int32_t D,
+                            int32_t act, int32_t do_norm, void *cuda_stream);
+/* GAT._aggregate_attention for all heads (layers.py:560-582): a_self/a_neigh [n,heads] already through LeakyReLU(0.2) */
+int shadow_gat_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
+                       const float *a_neigh, const float *H, float *out, float *rowmax, float *denom, int32_t n, int32_t heads,
+                       int32_t d, void *cuda_stream);
+int shadow_gat_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
+                       const float *a_neigh, const float *H, const float *out, const float *rowmax, const float *denom,
+                       const float *dOut, float *dH, float *da_self, float *da_neigh, int32_t n, int32_t heads, int32_t d,
+                       void *cuda_stream);
+/* per-subgraph pooling (F.embedding_bag in ResPool, layers.py:168-184): mode 0 sum, 1 mean, 2 max; seg = node_ptr slice */
+int shadow_segment_pool_fwd_f32(const float *X, const int32_t *seg, int32_t seg_off, int32_t S, int32_t F, int32_t mode, float *out,
+                                int32_t *argmax, void *cuda_stream);
+int shadow_segment_pool_bwd_f32(const float *dOut, const int32_t *seg, int32_t seg_off, int32_t S, int32_t F, int32_t mode,
+                                const int32_t *argmax, float *dX, void *cuda_stream);
+/* clip_grad_norm_(params, max_norm) + Adam.step (models.py:223-224) over one flat fp32 buffer; grads are pre-scaled by
+ * grad_scale (1/world_size after the NCCL sum); *step_dev is the device-side step counter (incremented here) */
+int shadow_adam_clip_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float grad_scale,
+                              float max_norm, float lr, float beta1, float beta2, float eps, int32_t *step_dev,
+                              float *sqnorm_scratch, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

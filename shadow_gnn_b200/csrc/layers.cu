@@ -1,0 +1,503 @@
+// layers.cu -- message-passing kernels of the shaDow layers (shaDow/layers.py) on the block-diagonal batch the sampler
+// leaves in HBM.  fp32 throughout (the reference is fp32; layer parity budget 1e-3 rel).  All kernels take the RAW edge
+// layout of include/shadow_b200.h: row_span[i] = [start,end) into col[] / val[], columns are batch-global ids minus col_off.
+// At training-batch sizes (n ~ 4,800 rows, e ~ 10^4 edges, D = 256) these kernels are L2-resident and launch-bound; they are
+// written to be captured in one CUDA graph per step.  Dense Linear layers stay on cuBLAS (torch.nn.functional.linear).
+#include <algorithm>
+
+#include "common.cuh"
+
+#define LAYER_BLOCK 256
+
+// ------------------------------------------------------------------------------------------------
+// adjacency values: dropedge + normalisation   (frontend/graph_utils.py:67-145, layers.py:512-522,584-600)
+// ------------------------------------------------------------------------------------------------
+// vals[p] = 1 for every edge of rows [0,n)
+__global__ void fill_edge_vals_kernel(const int2 *__restrict__ row_span, int n, float *__restrict__ val, float x) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    for (int p = sp.x + lane; p < sp.y; p += 32) val[p] = x;
+  }
+}
+// adj_norm_rw / GAT / GIN dropedge: `num_drop` indices drawn WITH replacement, idx = floor(u * e) over the batch's e edges in
+// CSR order (graph_utils.py:86-88).  The batch's edges are not contiguous in the raw layout, so the draw is over the
+// ordinal position and mapped through edge_ord (exclusive prefix of the row lengths).
+__global__ void dropedge_kernel(const int2 *__restrict__ row_span, const int *__restrict__ row_ord /*[n+1] exclusive prefix of row lengths*/,
+                                int n, int num_drop, uint32_t seed, uint32_t step, float *__restrict__ val) {
+  const int e = row_ord[n];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < num_drop; t += gridDim.x * blockDim.x) {
+    const uint32_t r = philox4x32_10_x((uint32_t)t, step, 0x5eed0001u, 0u, seed, 0x243F6A88u);
+    int k = (int)(((unsigned long long)r * (unsigned long long)e) >> 32);          // floor(u * e), u in [0,1)
+    int lo = 0, hi = n;                                                           // row whose ordinal range holds k
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row_ord[mid] <= k) lo = mid; else hi = mid; }
+    val[row_span[lo].x + (k - row_ord[lo])] = 0.f;
+  }
+}
+// mode 0: rw   vals /= clamp(rowsum(vals), 1)                         (adj_norm_rw, graph_utils.py:89-94)
+// mode 1: gin  vals *= deg_orig / clamp(rowsum(vals), 1)              (layers.py:514-522)
+__global__ void row_normalize_kernel(const int2 *__restrict__ row_span, int n, int mode, float *__restrict__ val) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    float s = 0.f;
+    for (int p = sp.x + lane; p < sp.y; p += 32) s += val[p];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    const float deg = fmaxf(s, 1.f);
+    const float f = (mode == 0) ? 1.f / deg : (float)(sp.y - sp.x) / deg;
+    for (int p = sp.x + lane; p < sp.y; p += 32) val[p] = (mode == 0) ? val[p] / deg : val[p] * f;
+  }
+}
+// adj_norm_sym (graph_utils.py:109-145): optional symmetric survival (edge kept iff both directions were kept), then
+// D^-1/2 A D^-1/2 with D = clip(rowsum, 1).  Two kernels: survive+degree, then scale.
+__global__ void sym_survive_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off, int n,
+                                   const float *__restrict__ mask /*after dropedge*/, float *__restrict__ val, float *__restrict__ deg) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    float s = 0.f;
+    for (int p = sp.x + lane; p < sp.y; p += 32) {
+      float v = mask[p];
+      if (v != 0.f) {                                 // reverse edge (j -> i): binary search in the sorted row j
+        const int j = col[p] - col_off;
+        const int2 sj = row_span[j];
+        int lo = sj.x, hi = sj.y;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] - col_off < i) lo = mid + 1; else hi = mid; }
+        v = (lo < sj.y && col[lo] - col_off == i) ? mask[lo] : 0.f;
+      }
+      val[p] = v; s += v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) deg[i] = fmaxf(s, 1.f);
+  }
+}
+__global__ void row_degree_kernel(const int2 *__restrict__ row_span, int n, const float *__restrict__ val, float *__restrict__ deg) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    float s = 0.f;
+    for (int p = sp.x + lane; p < sp.y; p += 32) s += val[p];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) deg[i] = fmaxf(s, 1.f);
+  }
+}
+__global__ void sym_scale_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off, int n,
+                                 const float *__restrict__ deg, float *__restrict__ val) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    const float di = rsqrtf(deg[i]);
+    for (int p = sp.x + lane; p < sp.y; p += 32) val[p] = di * val[p] * rsqrtf(deg[col[p] - col_off]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR SpMM (torch.sparse.mm on uncoalesced COO, layers.py:326-327,433,475,523): duplicates are summed, nothing is deduped
+//   fwd : Y[i,:]  = sum_p val[p] * X[col[p],:]          warp per row, lanes across the feature dimension (float4)
+//   bwd : dX[c,:] += val[p] * dY[i,:]                   same traversal, red.global.add (A^T without building a CSC)
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(LAYER_BLOCK) spmm_fwd_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
+                                                               const float *__restrict__ val, const float *__restrict__ X, float *__restrict__ Y,
+                                                               int n, int F, float beta /*Y = beta*Y + A X*/) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    if (VEC) {
+      const int F4 = F >> 2;
+      for (int f = lane; f < F4; f += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = sp.x; p < sp.y; p++) {
+          const float w = val ? val[p] : 1.f;
+          const float4 x = reinterpret_cast<const float4 *>(X + (size_t)(col[p] - col_off) * F)[f];
+          acc.x += w * x.x; acc.y += w * x.y; acc.z += w * x.z; acc.w += w * x.w;
+        }
+        float4 *y = reinterpret_cast<float4 *>(Y + (size_t)i * F) + f;
+        if (beta != 0.f) { const float4 o = *y; acc.x += beta * o.x; acc.y += beta * o.y; acc.z += beta * o.z; acc.w += beta * o.w; }
+        *y = acc;
+      }
+    } else {
+      for (int f = lane; f < F; f += 32) {
+        float acc = 0.f;
+        for (int p = sp.x; p < sp.y; p++) acc += (val ? val[p] : 1.f) * X[(size_t)(col[p] - col_off) * F + f];
+        Y[(size_t)i * F + f] = acc + (beta != 0.f ? beta * Y[(size_t)i * F + f] : 0.f);
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(LAYER_BLOCK) spmm_bwd_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
+                                                               const float *__restrict__ val, const float *__restrict__ dY, float *__restrict__ dX,
+                                                               int n, int F) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    for (int f = lane; f < F; f += 32) {
+      const float g = dY[(size_t)i * F + f];
+      for (int p = sp.x; p < sp.y; p++) {
+        const float w = val ? val[p] : 1.f;
+        if (w != 0.f) atomicAdd(dX + (size_t)(col[p] - col_off) * F + f, w * g);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation + norm_feat (layers.py:329-338, F_ACT layers.py:26-39), one warp per row:
+//   a = act(z);  out = (a - mean(a)) * scale * rsqrt(var_biased(a) + 1e-9) + offset   [+ out_prev if accumulate]
+// ------------------------------------------------------------------------------------------------
+enum { ACT_RELU = 0, ACT_I = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_LRELU = 4 };
+__device__ __forceinline__ float act_f(float z, int act) {
+  switch (act) {
+    case ACT_RELU: return z > 0.f ? z : 0.f;
+    case ACT_ELU: return z > 0.f ? z : expm1f(z);
+    case ACT_TANH: return tanhf(z);
+    case ACT_LRELU: return z > 0.f ? z : 0.2f * z;
+    default: return z;                       // "I" = LeakyReLU(negative_slope=1)
+  }
+}
+__device__ __forceinline__ float act_df(float z, float a, int act) {
+  switch (act) {
+    case ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case ACT_ELU: return z > 0.f ? 1.f : a + 1.f;
+    case ACT_TANH: return 1.f - a * a;
+    case ACT_LRELU: return z > 0.f ? 1.f : 0.2f;
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+#define NORM_MAX_PER_LANE 32      // D <= 1024
+
+__global__ void __launch_bounds__(LAYER_BLOCK) act_norm_fwd_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__ scale,
+                                                                   const float *__restrict__ offset, float *__restrict__ out, int ldo,
+                                                                   float *__restrict__ mean_out, float *__restrict__ rstd_out, int n, int D,
+                                                                   int act, int do_norm, int accumulate) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    float a[NORM_MAX_PER_LANE];
+    float s = 0.f;
+    int cnt = 0;
+    for (int f = lane; f < D; f += 32, cnt++) { a[cnt] = act_f(Z[(size_t)i * ldz + f], act); s += a[cnt]; }
+    float mean = 0.f, rstd = 1.f;
+    if (do_norm) {
+      mean = warp_sum(s) / (float)D;
+      float v = 0.f;
+      for (int k = 0; k < cnt; k++) { const float d = a[k] - mean; v += d * d; }
+      rstd = rsqrtf(warp_sum(v) / (float)D + 1e-9f);
+      if (lane == 0) { mean_out[i] = mean; rstd_out[i] = rstd; }
+    }
+    cnt = 0;
+    for (int f = lane; f < D; f += 32, cnt++) {
+      float o = do_norm ? (a[cnt] - mean) * scale[f] * rstd + offset[f] : a[cnt];
+      if (accumulate) o += out[(size_t)i * ldo + f];
+      out[(size_t)i * ldo + f] = o;
+    }
+  }
+}
+// dZ = d act . d norm ; dscale / doffset accumulated with one atomicAdd per column per CTA
+__global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *__restrict__ dOut, int ldo, const float *__restrict__ Z, int ldz,
+                                                                   const float *__restrict__ scale, const float *__restrict__ mean_in,
+                                                                   const float *__restrict__ rstd_in, float *__restrict__ dZ, int lddz,
+                                                                   float *__restrict__ dscale, float *__restrict__ doffset, int n, int D, int act,
+                                                                   int do_norm) {
+  extern __shared__ float sh[];               // [2*D] column partials of this CTA
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int f = threadIdx.x; f < 2 * D; f += blockDim.x) sh[f] = 0.f;
+  __syncthreads();
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    float a[NORM_MAX_PER_LANE], g[NORM_MAX_PER_LANE];
+    int cnt = 0;
+    for (int f = lane; f < D; f += 32, cnt++) { a[cnt] = act_f(Z[(size_t)i * ldz + f], act); g[cnt] = dOut[(size_t)i * ldo + f]; }
+    if (do_norm) {
+      const float mean = mean_in[i], rstd = rstd_in[i];
+      float s1 = 0.f, s2 = 0.f;
+      cnt = 0;
+      for (int f = lane; f < D; f += 32, cnt++) {
+        const float xh = (a[cnt] - mean) * rstd, dxh = g[cnt] * scale[f];
+        s1 += dxh; s2 += dxh * xh;
+        atomicAdd(&sh[f], g[cnt] * xh); atomicAdd(&sh[D + f], g[cnt]);
+      }
+      s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
+      cnt = 0;
+      for (int f = lane; f < D; f += 32, cnt++) {
+        const float xh = (a[cnt] - mean) * rstd, dxh = g[cnt] * scale[f];
+        const float da = rstd * (dxh - s1 - xh * s2);
+        dZ[(size_t)i * lddz + f] = da * act_df(Z[(size_t)i * ldz + f], a[cnt], act);
+      }
+    } else {
+      cnt = 0;
+      for (int f = lane; f < D; f += 32, cnt++) dZ[(size_t)i * lddz + f] = g[cnt] * act_df(Z[(size_t)i * ldz + f], a[cnt], act);
+    }
+  }
+  __syncthreads();
+  if (do_norm)
+    for (int f = threadIdx.x; f < D; f += blockDim.x) { atomicAdd(&dscale[f], sh[f]); atomicAdd(&doffset[f], sh[D + f]); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GAT attention aggregation (layers.py:560-582), all heads in one launch, warp per (row, head):
+//   e_ij = a_self[i,k] + a_neigh[j,k];  u_ij = exp(e_ij - max_j e_ij) * A_ij;  out[i,k,:] = sum_j u_ij h[j,k,:] / clamp(sum_j u_ij, 1e-10)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LAYER_BLOCK) gat_fwd_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
+                                                              const float *__restrict__ val, const float *__restrict__ a_self,
+                                                              const float *__restrict__ a_neigh, const float *__restrict__ H, float *__restrict__ out,
+                                                              float *__restrict__ rowmax, float *__restrict__ denom, int n, int heads, int d) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int D = heads * d;
+  for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < n * heads; w += gridDim.x * wpb) {
+    const int i = w / heads, k = w - i * heads;
+    const int2 sp = row_span[i];
+    const float as = a_self[(size_t)i * heads + k];
+    float mx = -INFINITY;
+    for (int p = sp.x + lane; p < sp.y; p += 32) mx = fmaxf(mx, as + a_neigh[(size_t)(col[p] - col_off) * heads + k]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};       // d <= 128
+    float den = 0.f;
+    for (int p = sp.x; p < sp.y; p++) {
+      const int j = col[p] - col_off;
+      const float u = expf(as + a_neigh[(size_t)j * heads + k] - mx) * (val ? val[p] : 1.f);
+      den += u;
+      int c = 0;
+      for (int f = lane; f < d; f += 32, c++) acc[c] += u * H[(size_t)j * D + k * d + f];
+    }
+    const float S = fmaxf(den, 1e-10f);
+    int c = 0;
+    for (int f = lane; f < d; f += 32, c++) out[(size_t)i * D + k * d + f] = acc[c] / S;
+    if (lane == 0) { rowmax[w] = mx; denom[w] = den; }
+  }
+}
+__global__ void __launch_bounds__(LAYER_BLOCK) gat_bwd_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
+                                                              const float *__restrict__ val, const float *__restrict__ a_self,
+                                                              const float *__restrict__ a_neigh, const float *__restrict__ H,
+                                                              const float *__restrict__ out, const float *__restrict__ rowmax,
+                                                              const float *__restrict__ denom, const float *__restrict__ dOut,
+                                                              float *__restrict__ dH, float *__restrict__ da_self, float *__restrict__ da_neigh,
+                                                              int n, int heads, int d) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int D = heads * d;
+  for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < n * heads; w += gridDim.x * wpb) {
+    const int i = w / heads, k = w - i * heads;
+    const int2 sp = row_span[i];
+    const float as = a_self[(size_t)i * heads + k], mx = rowmax[w], den = denom[w];
+    const bool clamped = den < 1e-10f;
+    const float S = fmaxf(den, 1e-10f);
+    float g[4], go = 0.f;
+    int c = 0;
+    for (int f = lane; f < d; f += 32, c++) { g[c] = dOut[(size_t)i * D + k * d + f]; go += g[c] * out[(size_t)i * D + k * d + f]; }
+    go = warp_sum(go);
+    float das = 0.f;
+    for (int p = sp.x; p < sp.y; p++) {
+      const int j = col[p] - col_off;
+      const float u = expf(as + a_neigh[(size_t)j * heads + k] - mx) * (val ? val[p] : 1.f);
+      if (u == 0.f) continue;
+      const float alpha = u / S;
+      float gh = 0.f;
+      c = 0;
+      for (int f = lane; f < d; f += 32, c++) {
+        gh += g[c] * H[(size_t)j * D + k * d + f];
+        atomicAdd(dH + (size_t)j * D + k * d + f, alpha * g[c]);
+      }
+      gh = warp_sum(gh);
+      const float de = alpha * (gh - (clamped ? 0.f : go));      // the row max is shift-invariant: no gradient through it
+      das += de;
+      if (lane == 0) atomicAdd(da_neigh + (size_t)j * heads + k, de);
+    }
+    if (lane == 0) da_self[(size_t)i * heads + k] = das;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-subgraph pooling (F.embedding_bag in ResPool, layers.py:168-184): out[s,:] = reduce over rows [seg[s], seg[s+1])
+// mode 0 sum, 1 mean, 2 max (argmax row kept for the backward)
+// ------------------------------------------------------------------------------------------------
+__global__ void segment_pool_fwd_kernel(const float *__restrict__ X, const int *__restrict__ seg, int seg_off, int S, int F, int mode,
+                                        float *__restrict__ out, int *__restrict__ argmax) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)S * F; t += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / F), f = (int)(t - (long long)s * F);
+    const int r0 = seg[s] - seg_off, r1 = seg[s + 1] - seg_off;
+    if (mode == 2) {
+      float m = -INFINITY; int am = r0;
+      for (int r = r0; r < r1; r++) { const float x = X[(size_t)r * F + f]; if (x > m) { m = x; am = r; } }
+      out[t] = (r1 > r0) ? m : 0.f; argmax[t] = am;
+    } else {
+      float a = 0.f;
+      for (int r = r0; r < r1; r++) a += X[(size_t)r * F + f];
+      out[t] = (mode == 1 && r1 > r0) ? a / (float)(r1 - r0) : a;
+    }
+  }
+}
+__global__ void segment_pool_bwd_kernel(const float *__restrict__ dOut, const int *__restrict__ seg, int seg_off, int S, int F, int mode,
+                                        const int *__restrict__ argmax, float *__restrict__ dX) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)S * F; t += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / F), f = (int)(t - (long long)s * F);
+    const int r0 = seg[s] - seg_off, r1 = seg[s + 1] - seg_off;
+    const float g = dOut[t];
+    if (mode == 2) { if (r1 > r0) dX[(size_t)argmax[t] * F + f] = g; }
+    else { const float v = (mode == 1 && r1 > r0) ? g / (float)(r1 - r0) : g; for (int r = r0; r < r1; r++) dX[(size_t)r * F + f] = v; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimizer step of DeepGNN.step (models.py:219-224): clip_grad_norm_(params, 5) + Adam, over ONE flat fp32 buffer
+// (the same buffer NCCL all-reduces in the data-parallel run).  Two launches: squared norm, then the update.
+// ------------------------------------------------------------------------------------------------
+__global__ void sqnorm_kernel(const float *__restrict__ g, long long n, float scale, float *__restrict__ out) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) { const float x = g[i] * scale; s += x * x; }
+  s = warp_sum(s);
+  __shared__ float sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+__global__ void adam_clip_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
+                                 const float *__restrict__ sqnorm, float gscale, float max_norm, float lr, float b1, float b2, float eps,
+                                 const int *__restrict__ step_dev) {
+  const float total = sqrtf(*sqnorm);
+  const float clip = fminf(max_norm / (total + 1e-6f), 1.f) * gscale;               // torch.nn.utils.clip_grad_norm_
+  const int t = *step_dev;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * clip;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr / bc1 * mi / (sqrtf(vi) / sqrtf(bc2) + eps);                          // torch.optim.Adam (no amsgrad, no weight decay)
+  }
+}
+__global__ void bump_step_kernel(int *step_dev) { *step_dev += 1; }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static inline int grid_for(long long work_items, int per_block, int cap) { return (int)std::max<long long>(1, std::min<long long>((work_items + per_block - 1) / per_block, cap)); }
+#define ST(s) ((cudaStream_t)(s))
+#define WPB (LAYER_BLOCK / 32)
+
+extern "C" int shadow_edge_vals_fill(const int32_t *row_span, int32_t n, float *val, float x, void *stream) {
+  if (n <= 0) return 0;
+  fill_edge_vals_kernel<<<grid_for(n, WPB, 4096), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, n, val, x);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_edge_vals_dropedge(const int32_t *row_span, const int32_t *row_ord, int32_t n, int32_t num_drop, uint32_t seed,
+                                         uint32_t step, float *val, void *stream) {
+  if (n <= 0 || num_drop <= 0) return 0;
+  dropedge_kernel<<<grid_for(num_drop, 256, 1024), 256, 0, ST(stream)>>>((const int2 *)row_span, row_ord, n, num_drop, seed, step, val);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_edge_vals_row_normalize(const int32_t *row_span, int32_t n, int32_t mode, float *val, void *stream) {
+  if (n <= 0) return 0;
+  row_normalize_kernel<<<grid_for(n, WPB, 4096), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, n, mode, val);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_edge_vals_sym_normalize(const int32_t *row_span, const int32_t *col, int32_t col_off, int32_t n, int32_t symmetric_survival,
+                                              const float *mask, float *val, float *deg_scratch, void *stream) {
+  if (n <= 0) return 0;
+  if (symmetric_survival) {
+    if (mask == val) FAIL(SHADOW_EINVAL, "sym_normalize with symmetric survival needs mask != val");
+    sym_survive_kernel<<<grid_for(n, WPB, 4096), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, n, mask, val, deg_scratch);
+  } else {
+    // no dropedge: `mask` (all ones) is copied through; degree = row sum clipped at 1
+    if (mask != val) FAIL(SHADOW_EINVAL, "sym_normalize without symmetric survival works in place (mask == val)");
+    row_degree_kernel<<<grid_for(n, WPB, 4096), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, n, val, deg_scratch);
+  }
+  sym_scale_kernel<<<grid_for(n, WPB, 4096), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, n, deg_scratch, val);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int shadow_spmm_csr_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *X, float *Y,
+                                       int32_t n, int32_t F, float beta, void *stream) {
+  if (n <= 0 || F <= 0) return 0;
+  const bool vec = (F % 4 == 0) && (((uintptr_t)X | (uintptr_t)Y) % 16 == 0);
+  const int grid = grid_for(n, WPB, 8192);
+  if (vec) spmm_fwd_kernel<true><<<grid, LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, X, Y, n, F, beta);
+  else spmm_fwd_kernel<false><<<grid, LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, X, Y, n, F, beta);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_spmm_csr_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *dY, float *dX,
+                                       int32_t n, int32_t F, void *stream) {
+  if (n <= 0 || F <= 0) return 0;
+  spmm_bwd_kernel<<<grid_for(n, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, dY, dX, n, F);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float *scale, const float *offset, float *out, int32_t ldo,
+                                       float *mean, float *rstd, int32_t n, int32_t D, int32_t act, int32_t do_norm, int32_t accumulate, void *stream) {
+  if (n <= 0) return 0;
+  if (D > 32 * NORM_MAX_PER_LANE) FAIL(SHADOW_EINVAL, "norm_feat: D=%d exceeds %d", D, 32 * NORM_MAX_PER_LANE);
+  act_norm_fwd_kernel<<<grid_for(n, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>(Z, ldz, scale, offset, out, ldo, mean, rstd, n, D, act, do_norm, accumulate);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const float *Z, int32_t ldz, const float *scale, const float *mean,
+                                       const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, int32_t n, int32_t D,
+                                       int32_t act, int32_t do_norm, void *stream) {
+  if (n <= 0) return 0;
+  if (D > 32 * NORM_MAX_PER_LANE) FAIL(SHADOW_EINVAL, "norm_feat: D=%d exceeds %d", D, 32 * NORM_MAX_PER_LANE);
+  act_norm_bwd_kernel<<<grid_for(n, WPB, 296), LAYER_BLOCK, 2 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale,
+                                                                                                    doffset, n, D, act, do_norm);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_gat_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
+                                  const float *a_neigh, const float *H, float *out, float *rowmax, float *denom, int32_t n, int32_t heads,
+                                  int32_t d, void *stream) {
+  if (n <= 0) return 0;
+  if (d > 128) FAIL(SHADOW_EINVAL, "gat: head dim %d exceeds 128", d);
+  gat_fwd_kernel<<<grid_for((long long)n * heads, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, a_self, a_neigh, H, out,
+                                                                                             rowmax, denom, n, heads, d);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_gat_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
+                                  const float *a_neigh, const float *H, const float *out, const float *rowmax, const float *denom,
+                                  const float *dOut, float *dH, float *da_self, float *da_neigh, int32_t n, int32_t heads, int32_t d, void *stream) {
+  if (n <= 0) return 0;
+  if (d > 128) FAIL(SHADOW_EINVAL, "gat: head dim %d exceeds 128", d);
+  gat_bwd_kernel<<<grid_for((long long)n * heads, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, a_self, a_neigh, H, out,
+                                                                                             rowmax, denom, dOut, dH, da_self, da_neigh, n, heads, d);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_segment_pool_fwd_f32(const float *X, const int32_t *seg, int32_t seg_off, int32_t S, int32_t F, int32_t mode, float *out,
+                                           int32_t *argmax, void *stream) {
+  if (S <= 0) return 0;
+  segment_pool_fwd_kernel<<<grid_for((long long)S * F, 256, 4096), 256, 0, ST(stream)>>>(X, seg, seg_off, S, F, mode, out, argmax);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_segment_pool_bwd_f32(const float *dOut, const int32_t *seg, int32_t seg_off, int32_t S, int32_t F, int32_t mode,
+                                           const int32_t *argmax, float *dX, void *stream) {
+  if (S <= 0) return 0;
+  segment_pool_bwd_kernel<<<grid_for((long long)S * F, 256, 4096), 256, 0, ST(stream)>>>(dOut, seg, seg_off, S, F, mode, argmax, dX);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_adam_clip_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float grad_scale,
+                                         float max_norm, float lr, float beta1, float beta2, float eps, int32_t *step_dev, float *sqnorm_scratch,
+                                         void *stream) {
+  if (n <= 0) return 0;
+  CUDA_TRY(cudaMemsetAsync(sqnorm_scratch, 0, 4, ST(stream)));
+  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_dev);
+  sqnorm_kernel<<<grid_for(n, 256, 592), 256, 0, ST(stream)>>>(grad, n, grad_scale, sqnorm_scratch);
+  adam_clip_kernel<<<grid_for(n, 256, 1184), 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, sqnorm_scratch, grad_scale, max_norm, lr, beta1, beta2,
+                                                                   eps, step_dev);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

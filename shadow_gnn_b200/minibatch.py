@@ -1,0 +1,271 @@
+"""Device-resident minibatch extractor -- drop-in for the reference's `shaDow.minibatch.MinibatchShallowExtractor`
+(shaDow/minibatch.py:143-495): same constructor arguments, same epoch protocol (`epoch_start_reset`, `shuffle_entity`,
+`is_end_epoch`, `one_batch`, `epoch_end_reset`, `disable_cache`, `drop_full_graph_info`, `get_aug_dim`) and the same
+`OneBatchSubgraph` fields.
+
+What moved: the sampler call, the pool, the collation (`Subgraph.cat_to_block_diagonal`, frontend/graph.py:280-320), the
+feature gather (`feat_full[node]`, minibatch.py:469) and the hop one-hot (graph.py:134-147) all happen in HBM.  One sampler
+call produces a super-batch that already IS the block-diagonal CSR; a training batch is a zero-copy slice of it (row range +
+column offset).  The reference's per-root Python cache of PPR subgraphs (minibatch.py:69-91) is not needed: re-sampling a
+super-batch costs less than looking the subgraphs up.
+"""
+from collections import deque
+from copy import deepcopy
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ParallelSampler as PS
+from .ops import DeviceCSR
+
+TRAIN, VALID, TEST = 0, 1, 2
+MODE2STR = {TRAIN: "train", VALID: "valid", TEST: "test"}
+STR2MODE = {v: k for k, v in MODE2STR.items()}
+REUSABLE_SAMPLER = {"ppr", "nodeIID"}            # CONFIG_TEMPLATE.yml:16-17
+
+
+@dataclass
+class OneBatchSubgraph:
+    """fields of the reference's dataclass (minibatch.py:94-140); adj_ens holds DeviceCSR handles, the rest CUDA tensors"""
+    adj_ens: List[Any]
+    feat_ens: List[torch.Tensor]
+    label: torch.Tensor
+    size_subg_ens: Optional[torch.Tensor]
+    target_ens: List[torch.Tensor]
+    feat_aug_ens: Optional[List[Dict[str, Any]]]
+    idx_raw: Optional[List[Any]] = None
+
+    @property
+    def num_ens(self):
+        return len(self.adj_ens)
+
+    @property
+    def batch_size(self):
+        return self.target_ens[0].numel()
+
+    def pop_idx_raw(self):
+        ret, self.idx_raw = self.idx_raw, None
+        return ret
+
+    def to_dict(self, keys=None):
+        keys = self.__dataclass_fields__ if keys is None else keys
+        return {k: getattr(self, k) for k in keys}
+
+
+class _SuperBatch:
+    """one sampler call of one ensemble branch, kept in HBM; `cursor` = next unconsumed subgraph"""
+
+    def __init__(self, dev_batch, feat, aug, num_roots):
+        self.b = dev_batch
+        self.node_ptr_host = dev_batch.node_ptr.cpu().numpy().astype(np.int64)
+        self.feat, self.aug, self.num_roots = feat, aug, num_roots
+        self.val = torch.empty(max(dev_batch.total_edges, 1), dtype=torch.float32, device=feat.device)
+        self.cursor = 0
+
+    @property
+    def remaining(self):
+        return self.b.num_subg - self.cursor
+
+    def take(self, bs):
+        a, b = self.cursor, self.cursor + bs
+        lo, hi = int(self.node_ptr_host[a]), int(self.node_ptr_host[b])
+        self.cursor = b
+        adj = DeviceCSR(self.b.row_span[lo:hi], self.b.indices_raw, lo, self.val)
+        R = self.num_roots
+        target = self.b.target[a * R:b * R].long() - lo
+        sizes = torch.as_tensor(np.diff(self.node_ptr_host[a:b + 1]), device=self.feat.device)
+        aug = {k: v[lo:hi] for k, v in self.aug.items()}
+        return adj, self.feat[lo:hi], target, sizes, aug, self.b.orig_node[lo:hi]
+
+
+def hop2onehot(hop_i32, dim):
+    """EntityEncoding.hop2onehot_vec (frontend/graph.py:134-147): column 0 = unreachable (0xFFFFFFFF, or >= 255), column h+1 = hop h
+    for h <= dim-2; larger finite hops give an all-zero row"""
+    hop = hop_i32.long() & 0xFFFFFFFF
+    out = torch.zeros((hop.numel(), dim), dtype=torch.get_default_dtype(), device=hop.device)
+    ok = hop <= dim - 2
+    out[ok.nonzero(as_tuple=True)[0], hop[ok] + 1] = 1
+    out[(hop >= 255).nonzero(as_tuple=True)[0], 0] = 1
+    return out
+
+
+class MinibatchShallowExtractor:
+    FULL, SUBG = 0, 1
+
+    def __init__(self, name_data, dir_data, adjs, entity_set, sampler_config_ensemble, aug_feats, percent_per_epoch, feat_full, label_full,
+                 dim_feat_raw: int, is_transductive: bool, parallelism: int, full_tensor_on_gpu: bool = True, bin_adj_files=None,
+                 nocache_modes: set = frozenset(), optm_level="high", seed_cpp=-1, metrics_profile=None, *, device=None,
+                 num_subg_per_batch=500, strict_reference_compat=True, rng="glibc"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("shadow_gnn_b200.minibatch needs a CUDA device (no CPU fallback)")
+        self.dev_torch = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.name_data, self.dir_data, self.aug_feats, self.optm_level = name_data, dir_data, aug_feats, optm_level
+        self.batch_num = -1
+        self.batch_size = {TRAIN: 0, VALID: 0, TEST: 0}
+        self.raw_entity_set = entity_set
+        if isinstance(entity_set[TRAIN], dict):
+            raise NotImplementedError("link-prediction entity sets (2 roots per subgraph) are not wired through the device minibatch yet")
+        self.prediction_task = "node"
+        self.entity_epoch = {m: None for m in (TRAIN, VALID, TEST)}
+        self.label_epoch = {m: None for m in (TRAIN, VALID, TEST)}
+        self.is_transductive = is_transductive
+        self.adj = adjs
+        assert isinstance(feat_full, torch.Tensor) and (label_full is None or isinstance(label_full, torch.Tensor))
+        self.feat_full = feat_full.to(self.dev_torch).float().contiguous()       # the path keeps the full tensors in HBM
+        self.label_full = label_full.to(self.dev_torch) if label_full is not None else None
+        self.dim_feat_raw = dim_feat_raw
+        self.idx_entity_evaluated = {VALID: 0, TEST: 0, TRAIN: 0}
+        self.end_epoch = {VALID: False, TEST: False, TRAIN: False}
+        self.percent_per_epoch = {TRAIN: 1.0, VALID: 1.0, TEST: 1.0}
+        for k, v in (percent_per_epoch or {}).items():
+            self.percent_per_epoch[STR2MODE[k]] = float(v)
+        self.nocache_modes = set(nocache_modes)
+        self.graph_sampler = {TRAIN: None, VALID: None, TEST: None}
+        self.sampler_cfgs = {}
+        self._cfg_ensemble = deepcopy(sampler_config_ensemble)
+        self.num_ensemble = 0
+        for sc in self._cfg_ensemble["configs"]:
+            lens = [len(v) for k, v in sc.items() if k != "method"]
+            assert len(lens) == 0 or max(lens) == min(lens)
+            self.num_ensemble += lens[0] if lens else 1
+        assert "full" not in [c["method"] for c in self._cfg_ensemble["configs"]], "FULL (no sampling) mode is a preprocessing-only path of the reference"
+        self.mode_sample = self.SUBG
+        self.seed_cpp, self.bin_adj_files = seed_cpp, bin_adj_files
+        self._per_call, self._compat, self._rng = int(num_subg_per_batch), strict_reference_compat, rng
+        self.pool = {m: [deque() for _ in range(self.num_ensemble)] for m in (TRAIN, VALID, TEST)}
+        self.record_subgraphs = {}
+        self.is_stochastic_sampler = {}
+        self.dtype = torch.get_default_dtype()
+        self.dim_1hot_hop, self.dim_1hot_ppr, self.dim_1hot_drnl = 5 + 2, 1, 25 + 1        # minibatch.py:246-248
+        self.profiler = None
+
+    # ------------------------------------------------------------------ epoch protocol (minibatch.py:252-343)
+    def _get_cur_batch_size(self, mode):
+        self.end_epoch[mode] = False
+        return min(self.entity_epoch[mode].shape[0] - self.idx_entity_evaluated[mode], self.batch_size[mode])
+
+    def _update_batch_stat(self, mode, batch_size):
+        self.batch_num += 1
+        self.idx_entity_evaluated[mode] += batch_size
+        if self.idx_entity_evaluated[mode] >= self.entity_epoch[mode].shape[0]:
+            assert self.idx_entity_evaluated[mode] == self.entity_epoch[mode].shape[0]
+            self.idx_entity_evaluated[mode] = 0
+            self.end_epoch[mode] = True
+            assert all(sum(sb.remaining for sb in q) == 0 for q in self.pool[mode])
+
+    def shuffle_entity(self, mode):
+        perm = np.random.permutation(self.raw_entity_set[mode].size)
+        if self.percent_per_epoch[mode] < 1.0:
+            perm = perm[:int(np.ceil(self.percent_per_epoch[mode] * perm.size))]
+        self.entity_epoch[mode] = np.asarray(self.raw_entity_set[mode])[perm]
+        self.label_epoch[mode] = self.label_full[torch.as_tensor(self.entity_epoch[mode].astype(np.int64), device=self.dev_torch)]
+        self.graph_sampler[mode].shuffle_targets(self.entity_epoch[mode])
+
+    def epoch_start_reset(self, epoch, mode):
+        self.batch_num = -1
+        if self.graph_sampler[mode] is None:
+            self.instantiate_sampler(mode)
+            self.record_subgraphs[mode] = ["noncache"] * self.num_ensemble
+
+    def is_end_epoch(self, mode):
+        return self.end_epoch[mode]
+
+    def epoch_end_reset(self, mode):
+        self.end_epoch[mode] = False
+
+    def disable_cache(self, mode):
+        self.nocache_modes.add(mode)
+
+    def drop_full_graph_info(self, mode):
+        pass        # nothing is cached host-side; the graph stays resident for re-sampling
+
+    def get_aug_dim(self, aug_type):
+        return getattr(self, f"dim_1hot_{aug_type[:-1]}")
+
+    # ------------------------------------------------------------------ sampler (minibatch.py:344-401)
+    def instantiate_sampler(self, mode):
+        cfgs = []
+        for cfg in deepcopy(self._cfg_ensemble["configs"]):
+            method = cfg.pop("method")
+            cnt = [len(v) for v in cfg.values()]
+            cnt = cnt[0] if cnt else 1
+            for i in range(cnt):
+                c = {k: v[i] for k, v in cfg.items()}
+                c["method"] = "ppr" if (method == "ppr_st" and mode in (VALID, TEST)) else method          # minibatch.py:367-370
+                cfgs.append(c)
+        self.batch_size[mode] = self._cfg_ensemble["batch_size"]
+        bs = self.batch_size[mode]
+        per_call = max(bs, (self._per_call // bs) * bs)           # whole batches per sampler call: a batch never straddles two calls
+        adj = self.adj[mode]
+        indptr, indices = (adj.indptr, adj.indices) if hasattr(adj, "indptr") else adj
+        if self.bin_adj_files is not None and self.bin_adj_files.get(mode):
+            f = self.bin_adj_files[mode]
+            s = PS.ParallelSampler([], [], [], per_call, 1, True, True, [], len(cfgs), f["indptr"], f["indices"], f.get("data", ""), self.seed_cpp,
+                                   device=self.dev_torch.index, strict_reference_compat=self._compat, rng=self._rng)
+        else:
+            s = PS.ParallelSampler(indptr, indices, [], per_call, 1, True, True, [], len(cfgs), "", "", "", self.seed_cpp,
+                                   device=self.dev_torch.index, strict_reference_compat=self._compat, rng=self._rng)
+        cpp_cfgs = []
+        for c in cfgs:
+            tf = lambda key: "true" if c.get(key, False) else "false"
+            d = {"method": c["method"], "num_roots": "1", "add_self_edge": tf("add_self_edge"), "include_target_conn": tf("include_target_conn")}
+            if c["method"] == "khop":
+                d.update(depth=str(c["depth"]), budget=str(c["budget"]))
+            elif c["method"] in ("ppr", "ppr_st"):
+                d.update(k=str(c["k"]), threshold=str(c.get("threshold", 0)))
+            cpp_cfgs.append(d)
+        ppr = [c for c in cfgs if c["method"] in ("ppr", "ppr_st")]
+        if ppr:         # one table for the largest k (samplers_ensemble.py:212-248)
+            top = max(ppr, key=lambda c: int(c["k"]) * (2 if c["method"] == "ppr_st" else 1))
+            k = int(top["k"]) * (2 if top["method"] == "ppr_st" else 1)
+            alpha, eps = float(top.get("alpha", 0.85)), float(top.get("epsilon", 1e-5))
+            fn = fs = ""
+            if self.dir_data is not None and not self.dir_data.get("is_adj_changed", False):
+                import os
+                d = f"{self.dir_data['local']}/{self.name_data}/ppr_float"
+                os.makedirs(d, exist_ok=True)
+                suffix = f"{'transductive' if self.is_transductive else 'inductive'}_{MODE2STR[mode]}_{alpha}_{eps}_{k}.bin"      # samplers_cpp.py:135-170
+                fn, fs = f"{d}/neighs_{suffix}", f"{d}/scores_{suffix}"
+            s.preproc_ppr_approximate(np.asarray(self.raw_entity_set[mode]), k, alpha, eps, fn, fs)
+        self.graph_sampler[mode] = s
+        self.sampler_cfgs[mode] = cpp_cfgs
+        self.is_stochastic_sampler[mode] = any(c["method"] in ("khop", "ppr_st") for c in cfgs)
+
+    def par_graph_sample(self, mode):
+        """one sampler call -> one super-batch per ensemble branch, features gathered, aug one-hots built (minibatch.py:403-426,469-477)"""
+        s = self.graph_sampler[mode]
+        augs = [set(self.aug_feats) & {"hops", "pprs", "drnls"} for _ in self.sampler_cfgs[mode]]
+        batches = s.sample_to_device(self.sampler_cfgs[mode], augs)
+        for i, b in enumerate(batches):
+            feat = PS.gather_rows(self.feat_full, b.orig_node)
+            aug = {}
+            if "hops" in self.aug_feats:
+                aug["hops"] = hop2onehot(b.hop, self.dim_1hot_hop)
+            if "pprs" in self.aug_feats or "drnls" in self.aug_feats:
+                raise NotImplementedError("'pprs' / 'drnls' feature augmentation is not wired through the device minibatch yet")
+            # the views must outlive the sampler's ring slot: keep one super-batch per branch in flight (num_ring = 2)
+            self.pool[mode][i].append(_SuperBatch(b, feat, aug, 1))
+
+    def one_batch(self, mode=TRAIN, ret_raw_idx=False):
+        """minibatch.py:428-487"""
+        bs = self._get_cur_batch_size(mode)
+        adj_ens, feat_ens, target_ens, aug_ens, idx_raw, size_ens = [], [], [], [], [], []
+        for i in range(self.num_ensemble):
+            q = self.pool[mode][i]
+            while q and q[0].remaining == 0:
+                q.popleft()
+            if not q:
+                self.par_graph_sample(mode)
+                q = self.pool[mode][i]
+            assert q[0].remaining >= bs, "sampler call size must be a multiple of the batch size"
+            adj, feat, target, sizes, aug, node = q[0].take(bs)
+            adj_ens.append(adj); feat_ens.append(feat); target_ens.append(target); aug_ens.append(aug); idx_raw.append(node); size_ens.append(sizes)
+        a = self.idx_entity_evaluated[mode]
+        label = self.label_epoch[mode][a:a + bs]
+        self._update_batch_stat(mode, bs)
+        ret = OneBatchSubgraph(adj_ens, feat_ens, label, torch.stack(size_ens, 0), target_ens, aug_ens)
+        if ret_raw_idx:
+            ret.idx_raw = idx_raw
+        return ret

@@ -1,0 +1,282 @@
+"""torch.autograd bindings of the layer kernels in libshadow_b200.so (csrc/layers.cu) + the device adjacency handle.
+
+Every op here fails loudly without the CUDA library / a CUDA tensor: there is no eager-PyTorch fallback.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import lib, check
+
+ACT_ID = {"relu": 0, "I": 1, "elu": 2, "tanh": 3, "leakyrelu": 4}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _req(t, dtype, name):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} on {t.device} (no CPU fallback)")
+    return t
+
+
+class DeviceCSR:
+    """Adjacency of one batch in the RAW layout of include/shadow_b200.h.
+
+    row_span [n,2] int32 : [start,end) of every row inside `col` / `val`
+    col      [*]   int32 : batch-global column ids of the whole sampler super-batch; local id = col - col_off
+    val      [*]   fp32  : edge values aligned with `col` (None = all ones), written by normalize_*()
+    """
+
+    def __init__(self, row_span, col, col_off, val=None):
+        self.row_span = _req(row_span, torch.int32, "row_span")
+        self.col = _req(col, torch.int32, "col")
+        self.col_off = int(col_off)
+        self.val = val
+        self.n = row_span.shape[0]
+        self._row_ord = None
+        self.normed = None          # None | "rw" | "sym" | "gin" | "gat"
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    @property
+    def row_ord(self):
+        if self._row_ord is None:
+            lens = (self.row_span[:, 1] - self.row_span[:, 0])
+            ro = torch.zeros(self.n + 1, dtype=torch.int32, device=lens.device)
+            torch.cumsum(lens, 0, out=ro[1:])
+            self._row_ord = ro
+        return self._row_ord
+
+    @property
+    def num_edges(self):
+        return int(self.row_ord[-1])
+
+    @classmethod
+    def from_scipy(cls, adj, device):
+        """compat path: a scipy CSR block-diagonal batch as the reference's one_batch produces (minibatch.py:468)"""
+        import numpy as np
+        indptr = torch.as_tensor(np.asarray(adj.indptr, dtype=np.int64))
+        span = torch.stack([indptr[:-1], indptr[1:]], 1).to(torch.int32).contiguous().to(device)
+        col = torch.as_tensor(np.asarray(adj.indices, dtype=np.int64)).to(torch.int32).to(device)
+        return cls(span, col, 0)
+
+    def _vals(self):
+        if self.val is None or self.val.numel() < self.col.numel():
+            self.val = torch.empty(self.col.numel(), dtype=torch.float32, device=self.col.device)
+        return self.val
+
+    def _fill_and_drop(self, dropedge, seed, step):
+        val = self._vals()
+        check(lib.shadow_edge_vals_fill(_p(self.row_span), self.n, _p(val), 1.0, _stream(val)))
+        if dropedge > 0:
+            num_drop = int(self.num_edges * dropedge)            # int(e * p), graph_utils.py:86
+            check(lib.shadow_edge_vals_dropedge(_p(self.row_span), _p(self.row_ord), self.n, num_drop, seed & 0xFFFFFFFF,
+                                                step & 0xFFFFFFFF, _p(val), _stream(val)))
+        return val
+
+    def normalize_rw(self, dropedge=0.0, seed=0, step=0):
+        """adj_norm_rw (graph_utils.py:81-95)"""
+        val = self._fill_and_drop(dropedge, seed, step)
+        check(lib.shadow_edge_vals_row_normalize(_p(self.row_span), self.n, 0, _p(val), _stream(val)))
+        self.normed = "rw"
+        return self
+
+    def normalize_gin(self, dropedge=0.0, seed=0, step=0):
+        """GIN dropedge + rescale (layers.py:512-522)"""
+        val = self._fill_and_drop(dropedge, seed, step)
+        check(lib.shadow_edge_vals_row_normalize(_p(self.row_span), self.n, 1, _p(val), _stream(val)))
+        self.normed = "gin"
+        return self
+
+    def mask_only(self, dropedge=0.0, seed=0, step=0):
+        """GAT / GATScatter: values stay 1, dropped edges become 0 (layers.py:584-600)"""
+        self._fill_and_drop(dropedge, seed, step)
+        self.normed = "gat"
+        return self
+
+    def normalize_sym(self, dropedge=0.0, seed=0, step=0):
+        """adj_norm_sym (graph_utils.py:109-145); the self loops were added by the sampler"""
+        val = self._fill_and_drop(dropedge, seed, step)
+        deg = torch.empty(self.n, dtype=torch.float32, device=val.device)
+        if dropedge > 0:
+            mask = val.clone()
+            check(lib.shadow_edge_vals_sym_normalize(_p(self.row_span), _p(self.col), self.col_off, self.n, 1, _p(mask), _p(val), _p(deg), _stream(val)))
+        else:
+            check(lib.shadow_edge_vals_sym_normalize(_p(self.row_span), _p(self.col), self.col_off, self.n, 0, _p(val), _p(val), _p(deg), _stream(val)))
+        self.normed = "sym"
+        return self
+
+    def to_dense(self):
+        """[n,n] dense matrix with duplicates summed (tests)"""
+        n = self.n
+        out = torch.zeros(n, n, device=self.col.device)
+        lens = (self.row_span[:, 1] - self.row_span[:, 0]).long()
+        rows = torch.repeat_interleave(torch.arange(n, device=out.device), lens)
+        pos = torch.cat([torch.arange(int(s), int(e), device=out.device) for s, e in self.row_span.tolist()]) if n else rows
+        vals = self.val[pos] if self.val is not None else torch.ones(pos.numel(), device=out.device)
+        out.index_put_((rows, (self.col[pos] - self.col_off).long()), vals, accumulate=True)
+        return out
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, adj):
+        X = _req(X.contiguous(), torch.float32, "spmm input")
+        Y = torch.empty((adj.n, X.shape[1]), dtype=torch.float32, device=X.device)
+        check(lib.shadow_spmm_csr_fwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(X), _p(Y), adj.n, X.shape[1], 0.0, _stream(X)))
+        ctx.adj, ctx.nsrc = adj, X.shape[0]
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        adj = ctx.adj
+        dY = dY.contiguous()
+        dX = torch.zeros((ctx.nsrc, dY.shape[1]), dtype=torch.float32, device=dY.device)
+        check(lib.shadow_spmm_csr_bwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(dY), _p(dX), adj.n, dY.shape[1], _stream(dY)))
+        return dX, None
+
+
+def spmm(adj, X):
+    """torch.sparse.mm(adj, X) of the reference (layers.py:326-327)"""
+    return _SpMM.apply(X, adj)
+
+
+class _ActNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Z, scale, offset, act, do_norm):
+        Z = _req(Z.contiguous(), torch.float32, "act_norm input")
+        n, D = Z.shape
+        out = torch.empty_like(Z)
+        mean = torch.empty(n, dtype=torch.float32, device=Z.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=Z.device)
+        sc = scale.contiguous() if do_norm else None
+        of = offset.contiguous() if do_norm else None
+        check(lib.shadow_act_norm_fwd_f32(_p(Z), D, _p(sc), _p(of), _p(out), D, _p(mean), _p(rstd), n, D, act, int(do_norm), 0, _stream(Z)))
+        ctx.save_for_backward(Z, sc if do_norm else Z.new_empty(0), mean, rstd)
+        ctx.act, ctx.do_norm = act, do_norm
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        Z, sc, mean, rstd = ctx.saved_tensors
+        n, D = Z.shape
+        dOut = dOut.contiguous()
+        dZ = torch.empty_like(Z)
+        dscale = torch.zeros(D, dtype=torch.float32, device=Z.device) if ctx.do_norm else None
+        doffset = torch.zeros(D, dtype=torch.float32, device=Z.device) if ctx.do_norm else None
+        check(lib.shadow_act_norm_bwd_f32(_p(dOut), D, _p(Z), D, _p(sc) if ctx.do_norm else None, _p(mean), _p(rstd), _p(dZ), D, _p(dscale), _p(doffset),
+                                          n, D, ctx.act, int(ctx.do_norm), _stream(Z)))
+        return dZ, dscale, doffset, None, None
+
+
+def act_norm(Z, scale, offset, act, do_norm=True):
+    """norm_feat(act(Z)) (layers.py:329-338); scale/offset are 1-D of length Z.shape[1]"""
+    return _ActNorm.apply(Z, scale, offset, ACT_ID[act], bool(do_norm))
+
+
+class _GATAgg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a_self, a_neigh, H, adj, heads):
+        n, D = H.shape
+        d = D // heads
+        a_self, a_neigh, H = a_self.contiguous(), a_neigh.contiguous(), _req(H.contiguous(), torch.float32, "gat input")
+        out = torch.empty_like(H)
+        rowmax = torch.empty(n * heads, dtype=torch.float32, device=H.device)
+        denom = torch.empty(n * heads, dtype=torch.float32, device=H.device)
+        check(lib.shadow_gat_fwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(a_self), _p(a_neigh), _p(H), _p(out), _p(rowmax), _p(denom),
+                                     n, heads, d, _stream(H)))
+        ctx.save_for_backward(a_self, a_neigh, H, out, rowmax, denom)
+        ctx.adj, ctx.heads = adj, heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        a_self, a_neigh, H, out, rowmax, denom = ctx.saved_tensors
+        adj, heads = ctx.adj, ctx.heads
+        n, D = H.shape
+        dOut = dOut.contiguous()
+        dH = torch.zeros_like(H)
+        da_self = torch.zeros_like(a_self)
+        da_neigh = torch.zeros_like(a_neigh)
+        check(lib.shadow_gat_bwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(a_self), _p(a_neigh), _p(H), _p(out), _p(rowmax), _p(denom),
+                                     _p(dOut), _p(dH), _p(da_self), _p(da_neigh), n, heads, D // heads, _stream(H)))
+        return da_self, da_neigh, dH, None, None
+
+
+def gat_aggregate(adj, a_self, a_neigh, H, heads):
+    """GAT._aggregate_attention for all heads at once (layers.py:560-582)"""
+    return _GATAgg.apply(a_self, a_neigh, H, adj, heads)
+
+
+class _SegPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, seg, seg_off, mode):
+        X = _req(X.contiguous(), torch.float32, "pool input")
+        S, F = seg.numel() - 1, X.shape[1]
+        out = torch.empty((S, F), dtype=torch.float32, device=X.device)
+        argmax = torch.empty((S, F), dtype=torch.int32, device=X.device) if mode == 2 else None
+        check(lib.shadow_segment_pool_fwd_f32(_p(X), _p(seg), seg_off, S, F, mode, _p(out), _p(argmax), _stream(X)))
+        ctx.seg, ctx.seg_off, ctx.mode, ctx.argmax, ctx.n = seg, seg_off, mode, argmax, X.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        dOut = dOut.contiguous()
+        S, F = dOut.shape
+        dX = torch.zeros((ctx.n, F), dtype=torch.float32, device=dOut.device)
+        check(lib.shadow_segment_pool_bwd_f32(_p(dOut), _p(ctx.seg), ctx.seg_off, S, F, ctx.mode, _p(ctx.argmax), _p(dX), _stream(dOut)))
+        return dX, None, None, None
+
+
+def segment_pool(X, sizes_subg, mode):
+    """F.embedding_bag(arange, X, offsets, mode) of ResPool (layers.py:168-184): sizes_subg [B] rows per subgraph"""
+    seg = torch.zeros(sizes_subg.numel() + 1, dtype=torch.int32, device=X.device)
+    torch.cumsum(sizes_subg.to(torch.int32), 0, out=seg[1:])
+    return _SegPool.apply(X, seg, 0, {"sum": 0, "mean": 1, "max": 2}[mode])
+
+
+class FlatAdamClip:
+    """clip_grad_norm_(params, max_norm) + torch.optim.Adam.step (models.py:223-224) as one fused pass over a flat fp32 buffer.
+    Parameters and gradients of the module are re-pointed into two flat buffers: the gradient buffer is also what the
+    data-parallel run all-reduces (one NCCL call per step)."""
+
+    def __init__(self, params, lr, max_norm=5.0, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self, grad_scale=1.0):
+        check(lib.shadow_adam_clip_step_f32(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.flat.numel(), grad_scale,
+                                            self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps, _p(self.step_dev), _p(self.sqnorm),
+                                            _stream(self.flat)))
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_dev, "lr": self.lr}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_dev.copy_(sd["step"])

@@ -1,0 +1,226 @@
+"""GPU parity tests (-m gpu) of the CUDA layers / model / optimizer / minibatch.
+Floating point: tolerance 1e-3 relative (BASELINE.json north_star) against (1) golden outputs of the unmodified reference layers
+(tests/golden/layers_golden.npz) with the reference's own state_dict loaded into our modules, (2) the fp32 torch restatement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layers_golden.npz"))
+RTOL = 1e-3
+
+
+def close(a, b, what):
+    a, b = a.detach().float().cpu(), torch.as_tensor(b).float()
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item() + 1e-6
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert err <= RTOL * scale + 1e-5, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+def device_adj(self_edge):
+    from shadow_gnn_b200.ops import DeviceCSR
+    ip, ix = Z[f"adj{int(self_edge)}_indptr"], Z[f"adj{int(self_edge)}_indices"]
+    span = torch.as_tensor(np.stack([ip[:-1], ip[1:]], 1).astype(np.int32)).cuda()
+    # place the batch behind an offset, as a slice of a sampler super-batch would be
+    off = 7
+    col = torch.as_tensor((ix + off).astype(np.int32)).cuda()
+    return DeviceCSR(span.contiguous(), col, off), torch.as_tensor(Z[f"adj{int(self_edge)}_target"]).cuda(), torch.as_tensor(Z[f"adj{int(self_edge)}_size_subg"]).cuda()
+
+
+def load_golden_state(module, name):
+    pre = f"{name}_p_"
+    sd = {k[len(pre):]: torch.tensor(Z[k]) for k in Z.files if k.startswith(pre)}
+    module.load_state_dict(sd, strict=True)          # the reference's parameter names / shapes must fit ours exactly
+    return module.cuda().eval()
+
+
+def run_case(name, module, fwd):
+    module = load_golden_state(module, name)
+    x = torch.tensor(Z[f"{name}_x"], device="cuda", requires_grad=True)
+    out = fwd(module, x)
+    close(out, Z[f"{name}_out"], f"{name} forward")
+    (out * torch.tensor(Z[f"{name}_w"], device="cuda")).sum().backward()
+    close(x.grad, Z[f"{name}_dx"], f"{name} d/dx")
+    for pn, p in module.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        close(g, Z[f"{name}_g_{pn}"], f"{name} d/d{pn}")
+
+
+@pytest.mark.parametrize("name,cls,kw,se", [
+    ("sage", "GraphSAGE", dict(act="relu"), False), ("sage_elu", "GraphSAGE", dict(act="elu"), True), ("gcn", "GCN", dict(act="elu"), True),
+    ("gin", "GIN", dict(act="relu", eps=0.1), False), ("gat", "GAT", dict(act="relu", mulhead=4), True),
+    ("gatscat", "GATScatter", dict(act="relu", mulhead=2), True)])
+def test_layer_vs_reference_golden(name, cls, kw, se):
+    from shadow_gnn_b200 import layers as L
+    adj, _, sizes = device_adj(se)
+    run_case(name, getattr(L, cls)(12, 16, **kw), lambda m, x: m((x, adj, False, 0.0), sizes)[0])
+
+
+def test_stacked_layers_reuse_normalised_adjacency():
+    from shadow_gnn_b200 import layers as L
+    for name, cls in (("sage2", L.GraphSAGE), ("gin2", L.GIN)):
+        adj, _, sizes = device_adj(False)
+        run_case(name, torch.nn.Sequential(cls(12, 16), cls(16, 16)), lambda m, x: m[1](m[0]((x, adj, False, 0.0), sizes), sizes)[0])
+
+
+@pytest.mark.parametrize("res,pool", [("none", "center"), ("cat", "center"), ("max", "max"), ("sum", "mean"), ("cat", "sum"), ("none", "sort")])
+def test_respool_vs_reference_golden(res, pool):
+    from shadow_gnn_b200 import layers as L
+    _, tgt, sizes = device_adj(False)
+    rp = L.ResPool(16, 16, 3, res, pool, dropout=0.0, act="relu", args_pool={"k": 5} if pool == "sort" else {})
+    if res == "none" and pool == "center":
+        x = torch.tensor(Z["respool_none_center_x"], device="cuda")
+        close(rp([x[:, :16], x[:, 16:32] * 0.5 + 0.1, x[:, 32:48] - 0.2], tgt, sizes), Z["respool_none_center_out"], "center/none")
+        return
+    run_case(f"respool_{res}_{pool}", rp, lambda m, x: m([x[:, :16], x[:, 16:32] * 0.5 + 0.1, x[:, 32:48] - 0.2], tgt, sizes))
+
+
+def _arch(aggr, act, heads):
+    return dict(num_layers=3, num_cls_layers=1, heads=heads, branch_sharing=False, dim=16, act=act, layer_norm="norm_feat",
+                feature_augment_ops="sum", aggr=aggr, residue="none", pooling="center", loss="softmax", ensemble_act="leakyrelu")
+
+
+@pytest.mark.parametrize("name,aggr,se,act,heads", [("model_sage", "sage", False, "relu", 1), ("model_gat", "gat", True, "elu", 2)])
+def test_deepgnn_vs_reference_golden(name, aggr, se, act, heads):
+    from shadow_gnn_b200.models import DeepGNN
+    adj, tgt, sizes = device_adj(se)
+    model = DeepGNN(12, 12, 5, 0, _arch(aggr, act, heads), [], 1, dict(dropout=0.0, dropedge=0.0, lr=0.01, ensemble_dropout="none"), "node")
+    run_case(name, model, lambda m, x: m(1, [x], [adj], [tgt], sizes.view(1, -1), [{}], 0.0)[0])
+
+
+def test_spmm_and_norms_vs_dense_restatement_random():
+    """larger random problem incl. duplicate edges, odd feature widths, dropedge: CUDA ops vs the dense fp32 restatement"""
+    from oracle import layers_ref as R
+    from shadow_gnn_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    n, e = 700, 9000
+    rows = torch.sort(torch.randint(0, n, (e,), generator=g)).values
+    cols = torch.randint(0, n, (e,), generator=g)
+    indptr = torch.zeros(n + 1, dtype=torch.int64); indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    A = R.dense_counts(indptr.numpy(), cols.numpy(), n)
+    span = torch.stack([indptr[:-1], indptr[1:]], 1).to(torch.int32).cuda().contiguous()
+    for F_ in (100, 256, 37):
+        adj = ops.DeviceCSR(span, cols.to(torch.int32).cuda(), 0)
+        x = torch.randn(n, F_, generator=g).cuda().requires_grad_(True)
+        adj.normalize_rw(0.0)
+        y = ops.spmm(adj, x)
+        close(y, R.adj_rw(A) @ x.detach().cpu(), f"spmm rw F={F_}")
+        w = torch.randn(n, F_, generator=g).cuda()
+        (y * w).sum().backward()
+        close(x.grad, R.adj_rw(A).T @ w.cpu(), f"spmm^T F={F_}")
+        close(adj.to_dense(), R.adj_rw(A), "rw values")
+    adj = ops.DeviceCSR(span, cols.to(torch.int32).cuda(), 0).normalize_gin(0.3, seed=5, step=1)
+    D = adj.to_dense().cpu()
+    dropped = (A > 0) & (D == 0)
+    assert 0 < dropped.sum() <= int(e * 0.3)                         # draws with replacement: at most int(e*p) distinct edges dropped
+    close(D.sum(1), torch.where(D.sum(1) > 0, A.sum(1), torch.zeros(n)), "gin rescale keeps the row sums")
+    for act in ("relu", "elu", "tanh", "leakyrelu", "I"):
+        z = torch.randn(n, 64, generator=g).cuda().requires_grad_(True)
+        sc, of = torch.randn(64, generator=g).cuda().requires_grad_(True), torch.randn(64, generator=g).cuda().requires_grad_(True)
+        out = ops.act_norm(z, sc, of, act)
+        zc, scc, ofc = (t.detach().cpu().requires_grad_(True) for t in (z, sc, of))
+        ref = R.norm_feat(R.ACT[act](zc), scc, ofc)
+        close(out, ref, f"act_norm {act}")
+        w = torch.randn(n, 64, generator=g)
+        (out * w.cuda()).sum().backward(); (ref * w).sum().backward()
+        close(z.grad, zc.grad, f"act_norm {act} dz"); close(sc.grad, scc.grad, f"act_norm {act} dscale"); close(of.grad, ofc.grad, f"act_norm {act} doffset")
+
+
+def test_flat_adam_clip_matches_torch():
+    from shadow_gnn_b200.ops import FlatAdamClip
+    torch.manual_seed(0)
+    m1 = torch.nn.Sequential(torch.nn.Linear(20, 30), torch.nn.Linear(30, 5)).cuda()
+    m2 = torch.nn.Sequential(torch.nn.Linear(20, 30), torch.nn.Linear(30, 5)).cuda()
+    m2.load_state_dict(m1.state_dict())
+    ours = FlatAdamClip(list(m1.parameters()), lr=0.01, max_norm=5.0)
+    ref = torch.optim.Adam(m2.parameters(), lr=0.01)
+    for it in range(6):
+        x = torch.randn(64, 20, device="cuda") * (30.0 if it % 2 else 1.0)       # some steps clip, some do not
+        ours.zero_grad(); ref.zero_grad()
+        (m1(x) ** 2).sum().backward(); (m2(x) ** 2).sum().backward()
+        torch.nn.utils.clip_grad_norm_(m2.parameters(), 5)
+        ours.step(); ref.step()
+        for a, b in zip(m1.parameters(), m2.parameters()):
+            close(a, b.detach().cpu(), f"param after step {it}")
+
+
+def test_minibatch_epoch_matches_oracle_collation():
+    """device MinibatchShallowExtractor: every batch == cat_to_block_diagonal of the oracle's subgraphs for the same targets"""
+    from oracle import oracle as O
+    from shadow_gnn_b200 import minibatch as MB
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(1500, 10, 2)
+    N = indptr.size - 1
+    feat = torch.randn(N, 20)
+    label = torch.randint(0, 5, (N,))
+    train = np.arange(0, 230, dtype=np.int64)
+    cfg = {"batch_size": 32, "configs": [{"method": "khop", "depth": [2], "budget": [5], "add_self_edge": [True]}]}
+    np.random.seed(3)
+    mb = MB.MinibatchShallowExtractor("toy", None, {0: (indptr, indices), 1: (indptr, indices), 2: (indptr, indices)},
+                                      {0: train, 1: train[:40], 2: train[:40]}, cfg, {"hops"}, None, feat, label, 20, True, 1, seed_cpp=4,
+                                      num_subg_per_batch=100)
+    mb.epoch_start_reset(0, MB.TRAIN)
+    mb.shuffle_entity(MB.TRAIN)
+    o = O.OracleSampler(indptr, indices, 96, 1, 4)            # 96 = whole batches per call
+    o.shuffle_targets(mb.entity_epoch[MB.TRAIN].astype(np.uint32))
+    want = []
+    while True:
+        want.extend(o.sample(O.make_cfg("khop", depth=2, budget=5, add_self_edge=True, aug=("hops",))).subgraphs())
+        if o.get_idx_root() == 0:
+            break
+    seen = 0
+    while not mb.is_end_epoch(MB.TRAIN):
+        b = mb.one_batch(MB.TRAIN, ret_raw_idx=True)
+        bs = b.target_ens[0].numel()
+        col = O.cat_to_block_diagonal(want[seen:seen + bs])
+        adj = b.adj_ens[0]
+        span = adj.row_span.cpu().numpy().astype(np.int64)
+        assert np.array_equal(span[:, 1] - span[:, 0], np.diff(col["indptr"]))
+        colidx = np.concatenate([adj.col.cpu().numpy()[s:e] - adj.col_off for s, e in span])
+        assert np.array_equal(colidx, col["indices"])
+        assert np.array_equal(b.target_ens[0].cpu().numpy(), col["target"])
+        assert np.array_equal(b.size_subg_ens[0].cpu().numpy(), col["size_subg"])
+        assert np.array_equal(b.idx_raw[0].cpu().numpy().view(np.uint32), col["node"])
+        assert torch.equal(b.feat_ens[0].cpu(), feat[col["node"].astype(np.int64)])
+        assert torch.equal(b.label.cpu(), label[mb.entity_epoch[MB.TRAIN][seen:seen + bs]])
+        hop = np.concatenate([w["hop"] for w in want[seen:seen + bs]]).astype(np.int64)
+        oh = b.feat_aug_ens[0]["hops"].cpu().numpy()
+        assert oh.shape == (hop.size, 7) and np.array_equal(oh.argmax(1)[hop <= 5], hop[hop <= 5] + 1)
+        seen += bs
+    assert seen == train.size
+    mb.epoch_end_reset(MB.TRAIN)
+
+
+def test_train_step_decreases_loss_and_is_deterministic_in_eval():
+    from shadow_gnn_b200 import minibatch as MB
+    from shadow_gnn_b200.models import DeepGNN
+    from shadow_gnn_b200.synth import small_parity_graph
+    torch.manual_seed(0); np.random.seed(0)
+    indptr, indices = small_parity_graph(2000, 12, 9)
+    N = indptr.size - 1
+    label = torch.randint(0, 4, (N,))
+    feat = torch.randn(N, 16) + torch.nn.functional.one_hot(label, 4).float().repeat(1, 4) * 1.5
+    train = np.arange(0, 512, dtype=np.int64)
+    cfg = {"batch_size": 32, "configs": [{"method": "ppr", "k": [20], "threshold": [0.0], "epsilon": [1e-4]}]}
+    mb = MB.MinibatchShallowExtractor("toy", None, {m: (indptr, indices) for m in range(3)}, {0: train, 1: train[:64], 2: train[:64]}, cfg, set(), None,
+                                      feat, label, 16, True, 1, seed_cpp=1, num_subg_per_batch=256)
+    arch = dict(num_layers=3, num_cls_layers=1, heads=1, branch_sharing=False, dim=32, act="relu", layer_norm="norm_feat", feature_augment_ops="sum",
+                aggr="sage", residue="none", pooling="center", loss="softmax", ensemble_act="leakyrelu")
+    model = DeepGNN(16, 16, 4, 0, arch, [], 1, dict(dropout=0.1, dropedge=0.05, lr=0.01, ensemble_dropout="none"), "node").cuda()
+    losses = []
+    for ep in range(3):
+        mb.epoch_start_reset(ep, MB.TRAIN); mb.shuffle_entity(MB.TRAIN)
+        tot = 0.0
+        while not mb.is_end_epoch(MB.TRAIN):
+            tot += float(model.step(MB.TRAIN, "running", mb.one_batch(MB.TRAIN))["loss"])
+        mb.epoch_end_reset(MB.TRAIN)
+        losses.append(tot)
+    assert losses[-1] < 0.7 * losses[0], losses
+    mb.epoch_start_reset(0, MB.VALID); mb.shuffle_entity(MB.VALID)
+    b = mb.one_batch(MB.VALID)
+    r1 = model.step(MB.VALID, "running", b)["preds"]
+    r2 = model.step(MB.VALID, "running", b)["preds"]
+    assert torch.equal(r1, r2)
