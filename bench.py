@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--task", default=None, choices=["sampler", "train"])
     ap.add_argument("--superbatch", type=int, default=16384)
+    ap.add_argument("--superbatch-train", type=int, default=4096)
     ap.add_argument("--graph", default="S-products")
     ap.add_argument("--cpu-sample", type=int, default=4000, help="roots of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -373,11 +374,187 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# train task: sample -> 5-layer GraphSAGE forward/backward -> clip + Adam, batch of 32 targets per step
+# ------------------------------------------------------------------------------------------------
+TRAIN_CFG = dict(batch=32, layers=5, dim=256, dropout=0.4, dropedge=0.05, lr=0.002)          # config_train/products/vanilla/sage_5_ppr.yml
+ARCH = dict(num_layers=5, num_cls_layers=1, heads=1, branch_sharing=False, dim=256, act="relu", layer_norm="norm_feat",
+            feature_augment_ops="sum", aggr="sage", residue="none", pooling="center", loss="softmax", ensemble_act="leakyrelu")
+
+
+def cpu_train_arm(g_host, roots, labels_all, steps, warmup, threads, C):
+    """reference sampler (oracle/_ref, 500 roots per call) + collation + feature gather + the reference model's math on the host cores"""
+    import torch
+    from oracle import oracle as O
+    from oracle.train_ref import RefModel
+    torch.set_num_threads(threads)
+    indptr, indices, feat = g_host["indptr"], g_host["indices"], torch.from_numpy(g_host["feat"])
+    ref = O.load_ref()
+    B = TRAIN_CFG["batch"]
+    if ref is not None:
+        d = tempfile.mkdtemp()
+        fi, fx = os.path.join(d, "indptr.bin"), os.path.join(d, "indices.bin")
+        indptr.tofile(fi); indices.tofile(fx)
+        devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
+        try:
+            s = ref.ParallelSampler([], [], [], 500, threads, True, True, [], 1, fi, fx, "", 1)
+            s.preproc_ppr_approximate(roots.tolist(), PPR_K, PPR_ALPHA, PPR_EPS, "", "")
+        finally:
+            os.dup2(saved, 1); os.close(devnull)
+        s.shuffle_targets(roots.tolist())
+        kind = "reference"
+        sample = lambda: O.ref_subgraphs(s.parallel_sampler_ensemble([SAMPLER_CFG], [set()])[0])
+    else:
+        s = O.OracleSampler(indptr, indices, 500, threads, 1)
+        s.preproc_ppr_approximate(roots, PPR_K, PPR_ALPHA, PPR_EPS)
+        s.shuffle_targets(roots)
+        kind = "port"
+        sample = lambda: s.sample(O.cfg_from_cpp_config(SAMPLER_CFG)).subgraphs()
+    model = RefModel(feat.shape[1], TRAIN_CFG["dim"], C, TRAIN_CFG["layers"], TRAIN_CFG["dropout"], TRAIN_CFG["dropedge"], TRAIN_CFG["lr"])
+    pool, done, t_total, n_samples = [], 0, 0.0, 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        while len(pool) < B:
+            pool.extend(sample())                               # minibatch.py:450-451
+        sub, pool = pool[:B], pool[B:]
+        col = O.cat_to_block_diagonal(sub)                      # graph.py:280-320
+        x = feat[torch.as_tensor(col["node"].astype(np.int64))]   # minibatch.py:469
+        y = torch.as_tensor(labels_all[col["node"][col["target"]].astype(np.int64)])
+        model.step(col, x, y)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            t_total += t1 - t0; n_samples += B
+    return n_samples / t_total, kind, n_samples, t_total
+
+
+def run_reference_train(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    threads = os.cpu_count() or 1
+    gh = host_graph(args)
+    from shadow_gnn_b200.synth import PRESETS
+    C = PRESETS[args.graph][4]
+    labels = np.random.default_rng(7).integers(0, C, gh["N"])
+    B = TRAIN_CFG["batch"]
+    roots = gh["train"][:min(B * (args.steps + args.warmup) + 500, gh["train"].size)]
+    v, kind, n, t = cpu_train_arm(gh, roots, labels, args.steps, args.warmup, threads, C)
+    line = {"impl": "reference", "metric": "train_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.graph} 5-layer GraphSAGE-256, PPR(k={PPR_K}) sampler, batch {B}, full train step (sample, collate, gather, fwd, bwd, clip, Adam)",
+                       "step": "one training batch; reference sampler called for 500 roots at a time (shaDow/minibatch.py:397); model = the reference's library calls on the host cores"},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": kind, "sample": f"{n} targets"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours_train(args):
+    import torch
+    import torch.distributed as dist
+    from shadow_gnn_b200 import minibatch as MB
+    from shadow_gnn_b200.models import DeepGNN
+    from shadow_gnn_b200.synth import PRESETS
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+    g = build_graph(args.graph, dev)
+    N, F, C = g["N"], g["F"], g["C"]
+    feat = torch.randn(N, F, device=dev, generator=torch.Generator(device=dev).manual_seed(g["seed"] + 100))
+    labels = torch.from_numpy(np.random.default_rng(7).integers(0, C, N)).to(dev)
+    B = TRAIN_CFG["batch"]
+    share = g["train"][rank::world].numpy()                       # this rank's targets (independent units; gradients meet in one all-reduce)
+    cfg = {"batch_size": B, "configs": [{"method": "ppr", "k": [PPR_K], "threshold": [0.0], "epsilon": [PPR_EPS]}]}
+    adjs = {m: (g["indptr"], g["indices"]) for m in range(3)}
+    mb = MB.MinibatchShallowExtractor(args.graph, None, adjs, {0: share, 1: share[:B], 2: share[:B]}, cfg, set(), None, feat, labels, F, True, 1,
+                                      seed_cpp=1, num_subg_per_batch=args.superbatch_train)
+    model = DeepGNN(F, F, C, 0, ARCH, [], 1, dict(dropout=TRAIN_CFG["dropout"], dropedge=TRAIN_CFG["dropedge"], lr=TRAIN_CFG["lr"], ensemble_dropout="none"),
+                    "node").to(dev)
+    log("model + minibatch ready; PPR push + first super-batch next")
+    mb.epoch_start_reset(0, MB.TRAIN)
+    mb.shuffle_entity(MB.TRAIN)
+    nparams = sum(p.numel() for p in model.parameters())
+
+    def next_batch():
+        if mb.is_end_epoch(MB.TRAIN):
+            mb.epoch_end_reset(MB.TRAIN); mb.epoch_start_reset(1, MB.TRAIN); mb.shuffle_entity(MB.TRAIN)
+        return mb.one_batch(MB.TRAIN)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        model.step(MB.TRAIN, "running", next_batch())
+    log("warmup done")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    nsamp = 0
+    for _ in range(args.steps):
+        b = next_batch()
+        model.step(MB.TRAIN, "running", b)
+        nsamp += b.batch_size
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    log("timed region done", ms)
+    # ---- e2e: the user-facing call with HOST inputs: the batch's target ids + labels come from pinned host memory every step,
+    #      the loss goes back to the host every step ----
+    e2e_steps = max(5, min(args.steps, 200))
+    tgt_host = torch.from_numpy(share.astype(np.int64)).pin_memory()
+    lab_host = labels.cpu()[tgt_host].pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    ne2e = 0
+    for i in range(e2e_steps):
+        lo = (i * B) % (share.size - B)
+        t_dev = tgt_host[lo:lo + B].to(dev, non_blocking=True)           # H2D: this step's targets
+        y_dev = lab_host[lo:lo + B].to(dev, non_blocking=True)           # H2D: this step's labels
+        b = next_batch()
+        b.label = y_dev if y_dev.numel() == b.label.numel() else b.label
+        out = model.step(MB.TRAIN, "running", b)
+        loss_host.copy_(out["loss"].detach().reshape(1), non_blocking=True)   # D2H: the step's loss
+        torch.cuda.synchronize()
+        ne2e += b.batch_size
+        del t_dev
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop() if clocks else None
+    stats = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+    counts = torch.tensor([nsamp, ne2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms_all, e2e_all = float(stats[0]), float(stats[1])
+        line = {"metric": "train_samples_per_sec", "value": float(counts[0]) / (ms_all * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.graph} 5-layer GraphSAGE-256 ({nparams} params), PPR(k={PPR_K},eps={PPR_EPS}) sampler, batch {B} per GPU, dropout 0.4, dropedge 0.05, Adam lr 0.002, clip 5",
+                           "global_batch": B * world, "sampler_superbatch": args.superbatch_train,
+                           "parallelism": f"dp{world}: targets partitioned, one NCCL all-reduce of the flat {nparams * 4} B gradient bucket per step",
+                           "l2": "CSR (495 MB) and features (980 MB) exceed L2; every step trains on different roots"},
+                "e2e": {"value": float(counts[1]) / e2e_all, "unit": "samples/s", "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": 4,
+                        "note": "targets + labels from pinned host memory each step, loss read back each step"},
+                "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.task is None:
         a.task = "sampler"
     if a.impl == "reference":
-        run_reference(a)
+        run_reference_train(a) if a.task == "train" else run_reference(a)
     else:
-        run_ours(a)
+        run_ours_train(a) if a.task == "train" else run_ours(a)

@@ -200,7 +200,10 @@ class MinibatchShallowExtractor:
         per_call = max(bs, (self._per_call // bs) * bs)           # whole batches per sampler call: a batch never straddles two calls
         adj = self.adj[mode]
         indptr, indices = (adj.indptr, adj.indices) if hasattr(adj, "indptr") else adj
-        if self.bin_adj_files is not None and self.bin_adj_files.get(mode):
+        if isinstance(indptr, torch.Tensor) and indptr.is_cuda:          # CSR already resident in HBM: borrow it
+            s = PS.ParallelSampler.from_device_csr(indptr, indices, per_call, len(cfgs), self.seed_cpp, strict_reference_compat=self._compat,
+                                                   rng=self._rng)
+        elif self.bin_adj_files is not None and self.bin_adj_files.get(mode):
             f = self.bin_adj_files[mode]
             s = PS.ParallelSampler([], [], [], per_call, 1, True, True, [], len(cfgs), f["indptr"], f["indices"], f.get("data", ""), self.seed_cpp,
                                    device=self.dev_torch.index, strict_reference_compat=self._compat, rng=self._rng)
