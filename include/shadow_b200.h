@@ -159,9 +159,10 @@ int shadow_gather_rows_f32(const float *feat_dev, int64_t num_rows, int32_t dim,
 /* adjacency values: data = 1 (PS.cpp:411,423) */
 int shadow_edge_vals_fill(const int32_t *row_span, int32_t n, float *val, float x, void *cuda_stream);
 /* dropedge: int(e*p) indices drawn with replacement are zeroed (graph_utils.py:86-88, layers.py:516-519,593-596);
- * row_ord[n+1] = exclusive prefix sum of the row lengths (ordinal position of every row's first edge) */
-int shadow_edge_vals_dropedge(const int32_t *row_span, const int32_t *row_ord, int32_t n, int32_t num_drop, uint32_t seed,
-                              uint32_t step, float *val, void *cuda_stream);
+ * row_ord[n+1] = exclusive prefix sum of the row lengths (ordinal position of every row's first edge); e = row_ord[n], the number
+ * of draws int(e*p) and the Philox stream position *step_dev are read on the device (CUDA-graph friendly) */
+int shadow_edge_vals_dropedge(const int32_t *row_span, const int32_t *row_ord, int32_t n, float p, uint32_t seed,
+                              const uint32_t *step_dev, float *val, void *cuda_stream);
 /* mode 0: adj_norm_rw (graph_utils.py:89-94); mode 1: GIN rescale deg_orig/deg_dropped (layers.py:520-522) */
 int shadow_edge_vals_row_normalize(const int32_t *row_span, int32_t n, int32_t mode, float *val, void *cuda_stream);
 /* adj_norm_sym (graph_utils.py:109-145): symmetric survival of `mask` (when dropedge > 0) then D^-1/2 A D^-1/2 */

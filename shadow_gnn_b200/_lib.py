@@ -82,7 +82,7 @@ lib.shadow_sampler_batch_field_host.argtypes = [_vp, _i, _i, _vp, _i64]
 lib.shadow_gather_rows_f32.argtypes = [_vp, _i64, C.c_int32, _vp, _i64, _vp, _vp]
 _i32 = C.c_int32
 lib.shadow_edge_vals_fill.argtypes = [_vp, _i32, _vp, _f, _vp]
-lib.shadow_edge_vals_dropedge.argtypes = [_vp, _vp, _i32, _i32, _u32, _u32, _vp, _vp]
+lib.shadow_edge_vals_dropedge.argtypes = [_vp, _vp, _i32, _f, _u32, _vp, _vp, _vp]
 lib.shadow_edge_vals_row_normalize.argtypes = [_vp, _i32, _i32, _vp, _vp]
 lib.shadow_edge_vals_sym_normalize.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]
 lib.shadow_spmm_csr_fwd_f32.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _f, _vp]

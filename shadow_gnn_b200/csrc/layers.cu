@@ -24,8 +24,10 @@ __global__ void fill_edge_vals_kernel(const int2 *__restrict__ row_span, int n, 
 // CSR order (graph_utils.py:86-88).  The batch's edges are not contiguous in the raw layout, so the draw is over the
 // ordinal position and mapped through edge_ord (exclusive prefix of the row lengths).
 __global__ void dropedge_kernel(const int2 *__restrict__ row_span, const int *__restrict__ row_ord /*[n+1] exclusive prefix of row lengths*/,
-                                int n, int num_drop, uint32_t seed, uint32_t step, float *__restrict__ val) {
+                                int n, float p, uint32_t seed, const uint32_t *__restrict__ step_dev, float *__restrict__ val) {
   const int e = row_ord[n];
+  const int num_drop = (int)((double)e * (double)p);                              // int(e * dropedge), graph_utils.py:86
+  const uint32_t step = *step_dev;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < num_drop; t += gridDim.x * blockDim.x) {
     const uint32_t r = philox4x32_10_x((uint32_t)t, step, 0x5eed0001u, 0u, seed, 0x243F6A88u);
     int k = (int)(((unsigned long long)r * (unsigned long long)e) >> 32);          // floor(u * e), u in [0,1)
@@ -391,10 +393,11 @@ extern "C" int shadow_edge_vals_fill(const int32_t *row_span, int32_t n, float *
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
-extern "C" int shadow_edge_vals_dropedge(const int32_t *row_span, const int32_t *row_ord, int32_t n, int32_t num_drop, uint32_t seed,
-                                         uint32_t step, float *val, void *stream) {
-  if (n <= 0 || num_drop <= 0) return 0;
-  dropedge_kernel<<<grid_for(num_drop, 256, 1024), 256, 0, ST(stream)>>>((const int2 *)row_span, row_ord, n, num_drop, seed, step, val);
+extern "C" int shadow_edge_vals_dropedge(const int32_t *row_span, const int32_t *row_ord, int32_t n, float p, uint32_t seed,
+                                         const uint32_t *step_dev, float *val, void *stream) {
+  if (n <= 0 || p <= 0.f) return 0;
+  // the number of draws, int(e*p), and the stream position live on the device so the launch can sit in a CUDA graph
+  dropedge_kernel<<<64, 256, 0, ST(stream)>>>((const int2 *)row_span, row_ord, n, p, seed, step_dev, val);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -31,13 +31,17 @@ def get_torch_act(act, args):
 
 
 class _Dropedge:
-    """counter-based dropedge stream shared by the layers of one process (seeded by torch.initial_seed())"""
-    step = 0
+    """counter-based dropedge stream: the position lives in a device tensor that is bumped on the stream (so a captured CUDA
+    graph draws fresh edges on every replay); seeded by torch.initial_seed()"""
+    _step = {}
 
     @classmethod
-    def next(cls):
-        cls.step += 1
-        return int(torch.initial_seed()) & 0xFFFFFFFF, cls.step
+    def next(cls, device):
+        key = str(device)
+        if key not in cls._step:
+            cls._step[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        cls._step[key].add_(1)
+        return int(torch.initial_seed()) & 0xFFFFFFFF, cls._step[key]
 
 
 def _as_device_csr(adj, device):
@@ -128,7 +132,7 @@ class GCN(shaDowLayer):
         feat_in = self.f_dropout(feat_in)
         adj = _as_device_csr(adj, feat_in.device)
         if not is_normed:
-            adj.normalize_sym(dropedge, *_Dropedge.next())
+            adj.normalize_sym(dropedge, *_Dropedge.next(feat_in.device))
         feat_out = self._act_norm(self.f_lin(ops.spmm(adj, feat_in)), 0)
         return feat_out, adj, True, 0.0
 
@@ -146,7 +150,7 @@ class GraphSAGE(shaDowLayer):
         feat_in, adj, is_normed, dropedge = inputs
         adj = _as_device_csr(adj, feat_in.device)
         if not is_normed:
-            adj.normalize_rw(dropedge, *_Dropedge.next())
+            adj.normalize_rw(dropedge, *_Dropedge.next(feat_in.device))
         feat_in = self.f_dropout(feat_in)
         h_self = self._act_norm(self.f_lin_self(feat_in), 0)
         h_neigh = self._act_norm(self.f_lin_neigh(ops.spmm(adj, feat_in)), 1)
@@ -169,7 +173,7 @@ class GIN(shaDowLayer):
         first = not isinstance(adj, DeviceCSR) or adj.normed is None
         adj = _as_device_csr(adj, feat_in.device)
         if first:                                  # the reference drops / rescales only while adj is still scipy (first layer)
-            adj.normalize_gin(dropedge, *_Dropedge.next())
+            adj.normalize_gin(dropedge, *_Dropedge.next(feat_in.device))
         feat_aggr = ops.spmm(adj, feat_in) + (1 + self.eps) * feat_in
         return self._act_norm(self.mlp(feat_aggr), 0), adj, False, 0.0
 
@@ -192,7 +196,7 @@ class GAT(shaDowLayer):
         feat_in, adj, is_normed, dropedge = inputs
         adj = _as_device_csr(adj, feat_in.device)
         if not is_normed:
-            adj.mask_only(dropedge, *_Dropedge.next())
+            adj.mask_only(dropedge, *_Dropedge.next(feat_in.device))
         feat_in = self.f_dropout(feat_in)
         N, H, d = feat_in.shape[0], self.mulhead, self.dim_slice
         h_self = self.act(self.f_lin[0](feat_in))
@@ -231,7 +235,7 @@ class GATScatter(shaDowLayer):
         feat_src = self.f_lin[0](h)
         adj = _as_device_csr(adj, feat_in.device)
         if not is_dropped:
-            adj.mask_only(dropedge, *_Dropedge.next())
+            adj.mask_only(dropedge, *_Dropedge.next(feat_in.device))
         el = self.att_act((feat_src.view(N, H, d) * self.attention).sum(-1))
         agg = ops.gat_aggregate(adj, torch.zeros_like(el), el, feat_src, H)
         return self._act_norm(agg + self.f_lin[1](h), 0), adj, True, 0.0

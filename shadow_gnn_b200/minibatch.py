@@ -79,6 +79,18 @@ class _SuperBatch:
         aug = {k: v[lo:hi] for k, v in self.aug.items()}
         return adj, self.feat[lo:hi], target, sizes, aug, self.b.orig_node[lo:hi]
 
+    def take_canonical(self, bs):
+        """the same batch as contiguous slices of the CANONICAL CSR of the super-batch (for the CUDA-graph trainer, which copies
+        them into static buffers): returns (rowptr slice [n+1], indices slice [e], first row, first edge, feat slice, target slice)"""
+        if not hasattr(self, "edge_ptr_host"):
+            self.edge_ptr_host = self.b.edge_ptr.cpu().numpy().astype(np.int64)        # runs the canonicalisation kernel once per super-batch
+        a, b = self.cursor, self.cursor + bs
+        lo, hi = int(self.node_ptr_host[a]), int(self.node_ptr_host[b])
+        e0, e1 = int(self.edge_ptr_host[a]), int(self.edge_ptr_host[b])
+        self.cursor = b
+        R = self.num_roots
+        return self.b.rowptr[lo:hi + 1], self.b.indices[e0:e1], lo, e0, self.feat[lo:hi], self.b.target[a * R:b * R]
+
 
 def hop2onehot(hop_i32, dim):
     """EntityEncoding.hop2onehot_vec (frontend/graph.py:134-147): column 0 = unreachable (0xFFFFFFFF, or >= 255), column h+1 = hop h
@@ -251,19 +263,23 @@ class MinibatchShallowExtractor:
             # the views must outlive the sampler's ring slot: keep one super-batch per branch in flight (num_ring = 2)
             self.pool[mode][i].append(_SuperBatch(b, feat, aug, 1))
 
+    def _front(self, mode, i, bs):
+        """super-batch of branch i that holds the next `bs` subgraphs (sampling a new one when the pool is dry)"""
+        q = self.pool[mode][i]
+        while q and q[0].remaining == 0:
+            q.popleft()
+        if not q:
+            self.par_graph_sample(mode)
+            q = self.pool[mode][i]
+        assert q[0].remaining >= bs, "sampler call size must be a multiple of the batch size"
+        return q[0]
+
     def one_batch(self, mode=TRAIN, ret_raw_idx=False):
         """minibatch.py:428-487"""
         bs = self._get_cur_batch_size(mode)
         adj_ens, feat_ens, target_ens, aug_ens, idx_raw, size_ens = [], [], [], [], [], []
         for i in range(self.num_ensemble):
-            q = self.pool[mode][i]
-            while q and q[0].remaining == 0:
-                q.popleft()
-            if not q:
-                self.par_graph_sample(mode)
-                q = self.pool[mode][i]
-            assert q[0].remaining >= bs, "sampler call size must be a multiple of the batch size"
-            adj, feat, target, sizes, aug, node = q[0].take(bs)
+            adj, feat, target, sizes, aug, node = self._front(mode, i, bs).take(bs)
             adj_ens.append(adj); feat_ens.append(feat); target_ens.append(target); aug_ens.append(aug); idx_raw.append(node); size_ens.append(sizes)
         a = self.idx_entity_evaluated[mode]
         label = self.label_epoch[mode][a:a + bs]

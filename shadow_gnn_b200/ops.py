@@ -33,13 +33,13 @@ class DeviceCSR:
     val      [*]   fp32  : edge values aligned with `col` (None = all ones), written by normalize_*()
     """
 
-    def __init__(self, row_span, col, col_off, val=None):
+    def __init__(self, row_span, col, col_off, val=None, row_ord=None):
         self.row_span = _req(row_span, torch.int32, "row_span")
         self.col = _req(col, torch.int32, "col")
         self.col_off = int(col_off)
         self.val = val
         self.n = row_span.shape[0]
-        self._row_ord = None
+        self._row_ord = row_ord
         self.normed = None          # None | "rw" | "sym" | "gin" | "gat"
 
     @property
@@ -74,35 +74,36 @@ class DeviceCSR:
         return self.val
 
     def _fill_and_drop(self, dropedge, seed, step):
+        if dropedge > 0 and step is None:
+            raise ValueError("dropedge needs a device-side step counter (layers._Dropedge.next())")
         val = self._vals()
         check(lib.shadow_edge_vals_fill(_p(self.row_span), self.n, _p(val), 1.0, _stream(val)))
         if dropedge > 0:
-            num_drop = int(self.num_edges * dropedge)            # int(e * p), graph_utils.py:86
-            check(lib.shadow_edge_vals_dropedge(_p(self.row_span), _p(self.row_ord), self.n, num_drop, seed & 0xFFFFFFFF,
-                                                step & 0xFFFFFFFF, _p(val), _stream(val)))
+            check(lib.shadow_edge_vals_dropedge(_p(self.row_span), _p(self.row_ord), self.n, float(dropedge), seed & 0xFFFFFFFF,
+                                                _p(step), _p(val), _stream(val)))
         return val
 
-    def normalize_rw(self, dropedge=0.0, seed=0, step=0):
+    def normalize_rw(self, dropedge=0.0, seed=0, step=None):
         """adj_norm_rw (graph_utils.py:81-95)"""
         val = self._fill_and_drop(dropedge, seed, step)
         check(lib.shadow_edge_vals_row_normalize(_p(self.row_span), self.n, 0, _p(val), _stream(val)))
         self.normed = "rw"
         return self
 
-    def normalize_gin(self, dropedge=0.0, seed=0, step=0):
+    def normalize_gin(self, dropedge=0.0, seed=0, step=None):
         """GIN dropedge + rescale (layers.py:512-522)"""
         val = self._fill_and_drop(dropedge, seed, step)
         check(lib.shadow_edge_vals_row_normalize(_p(self.row_span), self.n, 1, _p(val), _stream(val)))
         self.normed = "gin"
         return self
 
-    def mask_only(self, dropedge=0.0, seed=0, step=0):
+    def mask_only(self, dropedge=0.0, seed=0, step=None):
         """GAT / GATScatter: values stay 1, dropped edges become 0 (layers.py:584-600)"""
         self._fill_and_drop(dropedge, seed, step)
         self.normed = "gat"
         return self
 
-    def normalize_sym(self, dropedge=0.0, seed=0, step=0):
+    def normalize_sym(self, dropedge=0.0, seed=0, step=None):
         """adj_norm_sym (graph_utils.py:109-145); the self loops were added by the sampler"""
         val = self._fill_and_drop(dropedge, seed, step)
         deg = torch.empty(self.n, dtype=torch.float32, device=val.device)

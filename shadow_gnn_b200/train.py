@@ -1,0 +1,107 @@
+"""Whole-step CUDA graph for the training loop of the reference (`one_batch` + `DeepGNN.step`, shaDow/main.py:151-164).
+
+At batch 32 the step is ~150 small kernels over an L2-resident working set: launch-bound.  The step is therefore captured ONCE
+at a fixed capacity (rows, edges) and replayed: every batch is copied (3 small device copies) from the sampler's super-batch into
+static buffers whose padding rows have empty adjacency rows, so they never reach a real row, the loss, or any gradient.
+Dropout uses torch's graph-safe Philox state; dropedge reads its stream position and its draw count on the device
+(csrc/layers.cu: dropedge_kernel), so every replay drops different edges.  Batches that do not fit the captured capacity (the short
+batch at the end of an epoch, an unusually large scope) run through the eager `DeepGNN.step`.
+"""
+import torch
+import torch.nn.functional as F
+
+from .minibatch import TRAIN
+from .ops import DeviceCSR
+
+
+class GraphedTrainer:
+    def __init__(self, model, minibatch, row_cap, edge_cap, mode=TRAIN):
+        assert minibatch.num_ensemble == 1 and not minibatch.aug_feats, "the graphed step covers the single-branch, no-augmentation path"
+        self.model, self.mb, self.mode = model, minibatch, mode
+        self.B = minibatch._cfg_ensemble["batch_size"]
+        dev, Fd = minibatch.dev_torch, minibatch.feat_full.shape[1]
+        self.row_cap, self.edge_cap = int(row_cap), int(edge_cap)
+        self.rowptr = torch.zeros(self.row_cap + 1, dtype=torch.int32, device=dev)
+        self.span = torch.zeros((self.row_cap, 2), dtype=torch.int32, device=dev)
+        self.col = torch.zeros(self.edge_cap, dtype=torch.int32, device=dev)
+        self.val = torch.zeros(self.edge_cap, dtype=torch.float32, device=dev)
+        self.feat = torch.zeros((self.row_cap, Fd), dtype=torch.float32, device=dev)
+        self.target = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.label = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.sizes = torch.ones((1, self.B), dtype=torch.int64, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.graph = None
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+        self.graph_bwd = None
+        self.eager_steps = self.graph_steps = 0
+
+    # ------------------------------------------------------------------
+    def _fwd_bwd(self):
+        m = self.model
+        adj = DeviceCSR(self.span, self.col, 0, self.val, row_ord=self.rowptr)
+        preds, _ = m(self.mode, [self.feat], [adj], [self.target], self.sizes, [{}], m.dropedge)
+        loss = m._loss(preds, self.label)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def _capture(self):
+        m = self.model
+        opt = m._ensure_optimizer()
+        m.train()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up off the capture stream (cuBLAS workspaces, autograd buffers)
+            for _ in range(3):
+                opt.zero_grad()
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        opt.zero_grad()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            opt.grad.zero_()
+            self._fwd_bwd()
+            if self.world == 1:
+                opt.step(1.0)
+        # with several ranks the gradient all-reduce sits between the captured fwd/bwd and the (eager, 3-launch) optimizer step
+
+    def _load_static(self, sb, bs):
+        rowptr, indices, lo, e0, feat, target = sb.take_canonical(bs)
+        n, e = rowptr.numel() - 1, indices.numel()
+        if n > self.row_cap or e > self.edge_cap:
+            return False
+        torch.sub(rowptr, e0, out=self.rowptr[:n + 1])
+        self.rowptr[n + 1:] = e                              # padding rows: empty
+        self.span[:, 0] = self.rowptr[:-1]
+        self.span[:, 1] = self.rowptr[1:]
+        torch.sub(indices, lo, out=self.col[:e])
+        self.feat[:n].copy_(feat)
+        torch.sub(target, lo, out=self.target)
+        return True
+
+    def step(self):
+        """one training step on the next batch of the epoch; returns the loss (a device scalar, no sync)"""
+        mb, mode = self.mb, self.mode
+        bs = mb._get_cur_batch_size(mode)
+        a = mb.idx_entity_evaluated[mode]
+        label = mb.label_epoch[mode][a:a + bs]
+        sb = mb._front(mode, 0, bs)
+        if bs == self.B:
+            cursor = sb.cursor
+            if self._load_static(sb, bs):
+                self.label.copy_(label)
+                mb._update_batch_stat(mode, bs)
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+                if self.world > 1:
+                    opt = self.model.optimizer
+                    torch.distributed.all_reduce(opt.grad)
+                    opt.step(1.0 / self.world)
+                self.graph_steps += 1
+                return self.loss
+            sb.cursor = cursor                               # did not fit: hand the batch to the eager path
+        self.eager_steps += 1
+        return self.model.step(mode, "running", mb.one_batch(mode))["loss"].detach()

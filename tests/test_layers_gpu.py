@@ -112,7 +112,7 @@ def test_spmm_and_norms_vs_dense_restatement_random():
         (y * w).sum().backward()
         close(x.grad, R.adj_rw(A).T @ w.cpu(), f"spmm^T F={F_}")
         close(adj.to_dense(), R.adj_rw(A), "rw values")
-    adj = ops.DeviceCSR(span, cols.to(torch.int32).cuda(), 0).normalize_gin(0.3, seed=5, step=1)
+    adj = ops.DeviceCSR(span, cols.to(torch.int32).cuda(), 0).normalize_gin(0.3, seed=5, step=torch.ones(1, dtype=torch.int32, device='cuda'))
     D = adj.to_dense().cpu()
     dropped = (A > 0) & (D == 0)
     assert 0 < dropped.sum() <= int(e * 0.3)                         # draws with replacement: at most int(e*p) distinct edges dropped
@@ -224,3 +224,38 @@ def test_train_step_decreases_loss_and_is_deterministic_in_eval():
     r1 = model.step(MB.VALID, "running", b)["preds"]
     r2 = model.step(MB.VALID, "running", b)["preds"]
     assert torch.equal(r1, r2)
+
+
+def test_graphed_trainer_matches_eager_steps():
+    """the captured whole-step graph (padded static batch) gives the same parameters as the eager DeepGNN.step (dropout = dropedge = 0)"""
+    from shadow_gnn_b200 import minibatch as MB
+    from shadow_gnn_b200.models import DeepGNN
+    from shadow_gnn_b200.train import GraphedTrainer
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(2000, 12, 9)
+    N = indptr.size - 1
+    torch.manual_seed(0)
+    label = torch.randint(0, 4, (N,))
+    feat = torch.randn(N, 16)
+    train = np.arange(0, 400, dtype=np.int64)            # 12 full batches + a short one (eager fallback)
+    cfg = {"batch_size": 32, "configs": [{"method": "ppr", "k": [20], "threshold": [0.0], "epsilon": [1e-4]}]}
+    arch = dict(num_layers=2, num_cls_layers=1, heads=1, branch_sharing=False, dim=32, act="relu", layer_norm="norm_feat", feature_augment_ops="sum",
+                aggr="sage", residue="none", pooling="center", loss="softmax", ensemble_act="leakyrelu")
+    params = []
+    for graphed in (False, True):
+        torch.manual_seed(1); np.random.seed(1)
+        mb = MB.MinibatchShallowExtractor("toy", None, {m: (indptr, indices) for m in range(3)}, {0: train, 1: train[:64], 2: train[:64]}, cfg, set(), None,
+                                          feat, label, 16, True, 1, seed_cpp=1, num_subg_per_batch=128)
+        model = DeepGNN(16, 16, 4, 0, arch, [], 1, dict(dropout=0.0, dropedge=0.0, lr=0.01, ensemble_dropout="none"), "node").cuda()
+        mb.epoch_start_reset(0, MB.TRAIN); mb.shuffle_entity(MB.TRAIN)
+        tr = GraphedTrainer(model, mb, row_cap=32 * 21, edge_cap=32 * 21 * 21) if graphed else None
+        losses = []
+        while not mb.is_end_epoch(MB.TRAIN):
+            losses.append(float(tr.step()) if graphed else float(model.step(MB.TRAIN, "running", mb.one_batch(MB.TRAIN))["loss"].detach()))
+        if graphed:
+            assert tr.graph_steps == 12 and tr.eager_steps == 1
+        params.append((losses, [p.detach().clone() for p in model.parameters()]))
+    for a, b in zip(params[0][0], params[1][0]):
+        assert abs(a - b) <= 1e-3 * max(abs(a), 1e-3) + 1e-5, (params[0][0], params[1][0])
+    for a, b in zip(params[0][1], params[1][1]):
+        close(a, b.cpu(), "parameters after one epoch: graphed vs eager")
