@@ -280,7 +280,8 @@ class Ctx:
         self.feat = torch.randn(self.N, self.F, device=self.dev, generator=torch.Generator(device=self.dev).manual_seed(self.g["seed"] + 100))
         self.deg = torch.diff(self.g["indptr64"])
         # every rank takes its share of the epoch's target order (independent units: no data-path collective in the sampler)
-        self.share = self.g["train"][self.rank::self.world].contiguous()
+        from shadow_gnn_b200.parallel import partition_targets
+        self.share = torch.from_numpy(partition_targets(self.g["train"].numpy(), self.rank, self.world, 32)).contiguous()
         self.args = args
 
     def barrier(self):

@@ -101,46 +101,89 @@ __global__ void sym_scale_kernel(const int2 *__restrict__ row_span, const int *_
 //   fwd : Y[i,:]  = sum_p val[p] * X[col[p],:]          warp per row, lanes across the feature dimension (float4)
 //   bwd : dX[c,:] += val[p] * dY[i,:]                   same traversal, red.global.add (A^T without building a CSC)
 // ------------------------------------------------------------------------------------------------
-template <bool VEC>
-__global__ void __launch_bounds__(LAYER_BLOCK) spmm_fwd_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
-                                                               const float *__restrict__ val, const float *__restrict__ X, float *__restrict__ Y,
-                                                               int n, int F, float beta /*Y = beta*Y + A X*/) {
+// NV = float4 chunks per lane (F <= 128*NV): the whole output row lives in registers, col[]/val[] are read once, and the
+// edge loop is unrolled by 4 so that a row of the batch with ~150 in-scope neighbours is not a 150-deep latency chain.
+template <int NV>
+__global__ void __launch_bounds__(LAYER_BLOCK) spmm_fwd_vec_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
+                                                                   const float *__restrict__ val, const float *__restrict__ X, float *__restrict__ Y,
+                                                                   int n, int F, float beta /*Y = beta*Y + A X*/) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int F4 = F >> 2;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     const int2 sp = row_span[i];
-    if (VEC) {
-      const int F4 = F >> 2;
-      for (int f = lane; f < F4; f += 32) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = sp.x; p < sp.y; p++) {
-          const float w = val ? val[p] : 1.f;
-          const float4 x = reinterpret_cast<const float4 *>(X + (size_t)(col[p] - col_off) * F)[f];
-          acc.x += w * x.x; acc.y += w * x.y; acc.z += w * x.z; acc.w += w * x.w;
-        }
-        float4 *y = reinterpret_cast<float4 *>(Y + (size_t)i * F) + f;
-        if (beta != 0.f) { const float4 o = *y; acc.x += beta * o.x; acc.y += beta * o.y; acc.z += beta * o.z; acc.w += beta * o.w; }
-        *y = acc;
+    float4 acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p0 = sp.x; p0 < sp.y; p0 += 4) {
+      int c[4]; float w[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const bool ok = p0 + u < sp.y;
+        c[u] = ok ? col[p0 + u] - col_off : 0;
+        w[u] = ok ? (val ? val[p0 + u] : 1.f) : 0.f;
       }
-    } else {
-      for (int f = lane; f < F; f += 32) {
-        float acc = 0.f;
-        for (int p = sp.x; p < sp.y; p++) acc += (val ? val[p] : 1.f) * X[(size_t)(col[p] - col_off) * F + f];
-        Y[(size_t)i * F + f] = acc + (beta != 0.f ? beta * Y[(size_t)i * F + f] : 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)c[u] * F);
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+          const int f = lane + 32 * k;
+          if (f < F4 && w[u] != 0.f) {
+            const float4 x = xr[f];
+            acc[k].x += w[u] * x.x; acc[k].y += w[u] * x.y; acc[k].z += w[u] * x.z; acc[k].w += w[u] * x.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const int f = lane + 32 * k;
+      if (f < F4) {
+        float4 *y = reinterpret_cast<float4 *>(Y + (size_t)i * F) + f;
+        float4 r = acc[k];
+        if (beta != 0.f) { const float4 o = *y; r.x += beta * o.x; r.y += beta * o.y; r.z += beta * o.z; r.w += beta * o.w; }
+        *y = r;
       }
     }
   }
 }
+__global__ void __launch_bounds__(LAYER_BLOCK) spmm_fwd_scalar_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
+                                                                      const float *__restrict__ val, const float *__restrict__ X, float *__restrict__ Y,
+                                                                      int n, int F, float beta) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int2 sp = row_span[i];
+    for (int f = lane; f < F; f += 32) {
+      float acc = 0.f;
+      for (int p = sp.x; p < sp.y; p++) acc += (val ? val[p] : 1.f) * X[(size_t)(col[p] - col_off) * F + f];
+      Y[(size_t)i * F + f] = acc + (beta != 0.f ? beta * Y[(size_t)i * F + f] : 0.f);
+    }
+  }
+}
+// backward: dX[c,:] += val[p] * dY[i,:] with 128-bit vector reductions (red.global.add.v4.f32, sm_90+)
+template <bool VEC>
 __global__ void __launch_bounds__(LAYER_BLOCK) spmm_bwd_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
                                                                const float *__restrict__ val, const float *__restrict__ dY, float *__restrict__ dX,
                                                                int n, int F) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     const int2 sp = row_span[i];
-    for (int f = lane; f < F; f += 32) {
-      const float g = dY[(size_t)i * F + f];
-      for (int p = sp.x; p < sp.y; p++) {
-        const float w = val ? val[p] : 1.f;
-        if (w != 0.f) atomicAdd(dX + (size_t)(col[p] - col_off) * F + f, w * g);
+    if (VEC) {
+      const int F4 = F >> 2;
+      for (int f = lane; f < F4; f += 32) {
+        const float4 g = reinterpret_cast<const float4 *>(dY + (size_t)i * F)[f];
+        for (int p = sp.x; p < sp.y; p++) {
+          const float w = val ? val[p] : 1.f;
+          if (w != 0.f) atomicAdd(reinterpret_cast<float4 *>(dX + (size_t)(col[p] - col_off) * F) + f, make_float4(w * g.x, w * g.y, w * g.z, w * g.w));
+        }
+      }
+    } else {
+      for (int f = lane; f < F; f += 32) {
+        const float g = dY[(size_t)i * F + f];
+        for (int p = sp.x; p < sp.y; p++) {
+          const float w = val ? val[p] : 1.f;
+          if (w != 0.f) atomicAdd(dX + (size_t)(col[p] - col_off) * F + f, w * g);
+        }
       }
     }
   }
@@ -176,33 +219,41 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 #define NORM_MAX_PER_LANE 32      // D <= 1024
 
+// NPL = columns per lane (D <= 32*NPL): the row stays in registers
+template <int NPL>
 __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_fwd_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__ scale,
                                                                    const float *__restrict__ offset, float *__restrict__ out, int ldo,
                                                                    float *__restrict__ mean_out, float *__restrict__ rstd_out, int n, int D,
                                                                    int act, int do_norm, int accumulate) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
-    float a[NORM_MAX_PER_LANE];
+    float a[NPL];
     float s = 0.f;
-    int cnt = 0;
-    for (int f = lane; f < D; f += 32, cnt++) { a[cnt] = act_f(Z[(size_t)i * ldz + f], act); s += a[cnt]; }
+#pragma unroll
+    for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; a[k] = (f < D) ? act_f(Z[(size_t)i * ldz + f], act) : 0.f; s += a[k]; }
     float mean = 0.f, rstd = 1.f;
     if (do_norm) {
       mean = warp_sum(s) / (float)D;
       float v = 0.f;
-      for (int k = 0; k < cnt; k++) { const float d = a[k] - mean; v += d * d; }
+#pragma unroll
+      for (int k = 0; k < NPL; k++) { const float d = (lane + 32 * k < D) ? a[k] - mean : 0.f; v += d * d; }
       rstd = rsqrtf(warp_sum(v) / (float)D + 1e-9f);
       if (lane == 0) { mean_out[i] = mean; rstd_out[i] = rstd; }
     }
-    cnt = 0;
-    for (int f = lane; f < D; f += 32, cnt++) {
-      float o = do_norm ? (a[cnt] - mean) * scale[f] * rstd + offset[f] : a[cnt];
-      if (accumulate) o += out[(size_t)i * ldo + f];
-      out[(size_t)i * ldo + f] = o;
+#pragma unroll
+    for (int k = 0; k < NPL; k++) {
+      const int f = lane + 32 * k;
+      if (f < D) {
+        float o = do_norm ? (a[k] - mean) * scale[f] * rstd + offset[f] : a[k];
+        if (accumulate) o += out[(size_t)i * ldo + f];
+        out[(size_t)i * ldo + f] = o;
+      }
     }
   }
 }
-// dZ = d act . d norm ; dscale / doffset accumulated with one atomicAdd per column per CTA
+// dZ = d act . d norm ; dscale / doffset / dbias(=column sums of dZ) accumulated per warp in registers, then one shared-memory
+// atomic per column per warp and one global atomic per column per CTA
+template <int NPL>
 __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *__restrict__ dOut, int ldo, const float *__restrict__ Z, int ldz,
                                                                    const float *__restrict__ scale, const float *__restrict__ mean_in,
                                                                    const float *__restrict__ rstd_in, float *__restrict__ dZ, int lddz,
@@ -212,30 +263,40 @@ __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int f = threadIdx.x; f < 2 * D; f += blockDim.x) sh[f] = 0.f;
   __syncthreads();
+  float ps[NPL], po[NPL];
+#pragma unroll
+  for (int k = 0; k < NPL; k++) { ps[k] = 0.f; po[k] = 0.f; }
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
-    float a[NORM_MAX_PER_LANE], g[NORM_MAX_PER_LANE];
-    int cnt = 0;
-    for (int f = lane; f < D; f += 32, cnt++) { a[cnt] = act_f(Z[(size_t)i * ldz + f], act); g[cnt] = dOut[(size_t)i * ldo + f]; }
+    float a[NPL], g[NPL], z[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; k++) {
+      const int f = lane + 32 * k;
+      z[k] = (f < D) ? Z[(size_t)i * ldz + f] : 0.f; a[k] = act_f(z[k], act); g[k] = (f < D) ? dOut[(size_t)i * ldo + f] : 0.f;
+    }
     if (do_norm) {
       const float mean = mean_in[i], rstd = rstd_in[i];
-      float s1 = 0.f, s2 = 0.f;
-      cnt = 0;
-      for (int f = lane; f < D; f += 32, cnt++) {
-        const float xh = (a[cnt] - mean) * rstd, dxh = g[cnt] * scale[f];
-        s1 += dxh; s2 += dxh * xh;
-        atomicAdd(&sh[f], g[cnt] * xh); atomicAdd(&sh[D + f], g[cnt]);
+      float s1 = 0.f, s2 = 0.f, xh[NPL], dxh[NPL];
+#pragma unroll
+      for (int k = 0; k < NPL; k++) {
+        const int f = lane + 32 * k;
+        xh[k] = (f < D) ? (a[k] - mean) * rstd : 0.f; dxh[k] = (f < D) ? g[k] * scale[f] : 0.f;
+        s1 += dxh[k]; s2 += dxh[k] * xh[k];
+        ps[k] += g[k] * xh[k]; po[k] += g[k];
       }
       s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
-      cnt = 0;
-      for (int f = lane; f < D; f += 32, cnt++) {
-        const float xh = (a[cnt] - mean) * rstd, dxh = g[cnt] * scale[f];
-        const float da = rstd * (dxh - s1 - xh * s2);
-        dZ[(size_t)i * lddz + f] = da * act_df(Z[(size_t)i * ldz + f], a[cnt], act);
+#pragma unroll
+      for (int k = 0; k < NPL; k++) {
+        const int f = lane + 32 * k;
+        if (f < D) dZ[(size_t)i * lddz + f] = rstd * (dxh[k] - s1 - xh[k] * s2) * act_df(z[k], a[k], act);
       }
     } else {
-      cnt = 0;
-      for (int f = lane; f < D; f += 32, cnt++) dZ[(size_t)i * lddz + f] = g[cnt] * act_df(Z[(size_t)i * ldz + f], a[cnt], act);
+#pragma unroll
+      for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) dZ[(size_t)i * lddz + f] = g[k] * act_df(z[k], a[k], act); }
     }
+  }
+  if (do_norm) {
+#pragma unroll
+    for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) { atomicAdd(&sh[f], ps[k]); atomicAdd(&sh[D + f], po[k]); } }
   }
   __syncthreads();
   if (do_norm)
@@ -426,17 +487,23 @@ extern "C" int shadow_edge_vals_sym_normalize(const int32_t *row_span, const int
 extern "C" int shadow_spmm_csr_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *X, float *Y,
                                        int32_t n, int32_t F, float beta, void *stream) {
   if (n <= 0 || F <= 0) return 0;
-  const bool vec = (F % 4 == 0) && (((uintptr_t)X | (uintptr_t)Y) % 16 == 0);
+  const bool vec = (F % 4 == 0) && (F <= 1024) && (((uintptr_t)X | (uintptr_t)Y) % 16 == 0);
   const int grid = grid_for(n, WPB, 8192);
-  if (vec) spmm_fwd_kernel<true><<<grid, LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, X, Y, n, F, beta);
-  else spmm_fwd_kernel<false><<<grid, LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, X, Y, n, F, beta);
+  const int2 *rs = (const int2 *)row_span;
+  if (!vec) spmm_fwd_scalar_kernel<<<grid, LAYER_BLOCK, 0, ST(stream)>>>(rs, col, col_off, val, X, Y, n, F, beta);
+  else if (F <= 128) spmm_fwd_vec_kernel<1><<<grid, LAYER_BLOCK, 0, ST(stream)>>>(rs, col, col_off, val, X, Y, n, F, beta);
+  else if (F <= 256) spmm_fwd_vec_kernel<2><<<grid, LAYER_BLOCK, 0, ST(stream)>>>(rs, col, col_off, val, X, Y, n, F, beta);
+  else if (F <= 512) spmm_fwd_vec_kernel<4><<<grid, LAYER_BLOCK, 0, ST(stream)>>>(rs, col, col_off, val, X, Y, n, F, beta);
+  else spmm_fwd_vec_kernel<8><<<grid, LAYER_BLOCK, 0, ST(stream)>>>(rs, col, col_off, val, X, Y, n, F, beta);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int shadow_spmm_csr_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *dY, float *dX,
                                        int32_t n, int32_t F, void *stream) {
   if (n <= 0 || F <= 0) return 0;
-  spmm_bwd_kernel<<<grid_for(n, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, dY, dX, n, F);
+  const bool vec = (F % 4 == 0) && (((uintptr_t)dY | (uintptr_t)dX) % 16 == 0);
+  if (vec) spmm_bwd_kernel<true><<<grid_for(n, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, dY, dX, n, F);
+  else spmm_bwd_kernel<false><<<grid_for(n, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, dY, dX, n, F);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -444,7 +511,10 @@ extern "C" int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float 
                                        float *mean, float *rstd, int32_t n, int32_t D, int32_t act, int32_t do_norm, int32_t accumulate, void *stream) {
   if (n <= 0) return 0;
   if (D > 32 * NORM_MAX_PER_LANE) FAIL(SHADOW_EINVAL, "norm_feat: D=%d exceeds %d", D, 32 * NORM_MAX_PER_LANE);
-  act_norm_fwd_kernel<<<grid_for(n, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>(Z, ldz, scale, offset, out, ldo, mean, rstd, n, D, act, do_norm, accumulate);
+#define LAUNCH_FWD(NPL) act_norm_fwd_kernel<NPL><<<grid_for(n, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>(Z, ldz, scale, offset, out, ldo, mean, rstd, n, D, act, do_norm, accumulate)
+  if (D <= 32) LAUNCH_FWD(1); else if (D <= 64) LAUNCH_FWD(2); else if (D <= 128) LAUNCH_FWD(4); else if (D <= 256) LAUNCH_FWD(8);
+  else if (D <= 512) LAUNCH_FWD(16); else LAUNCH_FWD(32);
+#undef LAUNCH_FWD
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -453,8 +523,10 @@ extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const flo
                                        int32_t act, int32_t do_norm, void *stream) {
   if (n <= 0) return 0;
   if (D > 32 * NORM_MAX_PER_LANE) FAIL(SHADOW_EINVAL, "norm_feat: D=%d exceeds %d", D, 32 * NORM_MAX_PER_LANE);
-  act_norm_bwd_kernel<<<grid_for(n, WPB, 296), LAYER_BLOCK, 2 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale,
-                                                                                                    doffset, n, D, act, do_norm);
+#define LAUNCH_BWD(NPL) act_norm_bwd_kernel<NPL><<<grid_for(n, WPB, 296), LAYER_BLOCK, 2 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale, doffset, n, D, act, do_norm)
+  if (D <= 32) LAUNCH_BWD(1); else if (D <= 64) LAUNCH_BWD(2); else if (D <= 128) LAUNCH_BWD(4); else if (D <= 256) LAUNCH_BWD(8);
+  else if (D <= 512) LAUNCH_BWD(16); else LAUNCH_BWD(32);
+#undef LAUNCH_BWD
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -14,6 +14,7 @@ from torch import nn
 
 from . import layers
 from .ops import FlatAdamClip
+from .parallel import allreduce_flat_gradients
 
 TRAIN, VALID, TEST = 0, 1, 2
 
@@ -130,10 +131,8 @@ class DeepGNN(nn.Module):
             preds, emb_ens = self(mode, dropedge=self.dropedge, **args)
             loss = self._loss(preds, label_targets)
             loss.backward()
-            if self._world > 1:                         # one NCCL all-reduce of the flat gradient bucket; clip sees the averaged gradient
-                import torch.distributed as dist
-                dist.all_reduce(opt.grad)
-            opt.step(grad_scale=1.0 / self._world)
+            # one NCCL all-reduce of the flat gradient bucket; the clip then sees the averaged gradient
+            opt.step(grad_scale=allreduce_flat_gradients(opt.grad))
         else:
             self.eval()
             with torch.no_grad():

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from .minibatch import TRAIN
 from .ops import DeviceCSR
+from .parallel import allreduce_flat_gradients
 
 
 class GraphedTrainer:
@@ -98,8 +99,7 @@ class GraphedTrainer:
                 self.graph.replay()
                 if self.world > 1:
                     opt = self.model.optimizer
-                    torch.distributed.all_reduce(opt.grad)
-                    opt.step(1.0 / self.world)
+                    opt.step(allreduce_flat_gradients(opt.grad))
                 self.graph_steps += 1
                 return self.loss
             sb.cursor = cursor                               # did not fit: hand the batch to the eager path
