@@ -93,8 +93,8 @@ struct shadow_sampler {
   int seed = 0;
   GlibcRand rng;
   // ppr tables
-  DevBuf ppr_ptr, ppr_neighs, ppr_scores;
-  bool has_ppr = false;
+  DevBuf ppr_ptr, ppr_neighs, ppr_scores, ppr_sid, ppr_sscore, ppr_srank;
+  bool has_ppr = false, ppr_sorted = false;
   std::vector<std::vector<Result>> ring;   // [num_ring][num_ens]
   DevBuf rand_stream, rand_off, gws;
   std::vector<uint32_t> rand_host;
@@ -283,6 +283,7 @@ extern "C" int shadow_sampler_destroy(shadow_sampler *s) {
   cudaStreamSynchronize(s->stream);
   if (s->owns_graph) { cudaFree(s->indptr); if (s->indices) cudaFree(s->indices); }
   s->targets.release(); s->ppr_ptr.release(); s->ppr_neighs.release(); s->ppr_scores.release();
+  s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release();
   s->rand_stream.release(); s->rand_off.release(); s->gws.release();
   for (auto &slot : s->ring) for (auto &r : slot) result_release(r);
   delete s;
@@ -322,7 +323,32 @@ extern "C" int shadow_sampler_drop_full_graph_info(shadow_sampler *s) {      // 
   if (s->owns_graph && s->indices) { cudaFree(s->indices); }
   s->indices = nullptr; s->graph_dropped = true;
   s->ppr_neighs.release(); s->ppr_scores.release(); s->ppr_ptr.release(); s->has_ppr = false;
+  s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release(); s->ppr_sorted = false;
   return 0;
+}
+
+
+// id-sorted copy of every PPR row (+ position in score order), built once when the tables are installed
+#define PPR_SORT_CAP 1024
+__global__ void __launch_bounds__(128) ppr_sort_rows_kernel(const unsigned long long *__restrict__ ptr, const uint32_t *__restrict__ neighs,
+                                                            const float *__restrict__ scores, uint32_t num_nodes, uint32_t *__restrict__ sid,
+                                                            float *__restrict__ sscore, unsigned short *__restrict__ srank, int *too_long) {
+  __shared__ unsigned long long keys[PPR_SORT_CAP];
+  for (uint32_t v = blockIdx.x; v < num_nodes; v += gridDim.x) {
+    const unsigned long long off = ptr[v];
+    const int len = (int)(ptr[v + 1] - off);
+    if (len == 0) continue;
+    if (len > PPR_SORT_CAP) { if (threadIdx.x == 0) *too_long = 1; continue; }
+    const int np2 = next_pow2(len);
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) keys[i] = i < len ? (((unsigned long long)neighs[off + i] << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    block_bitonic_sort(keys, np2);
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const uint32_t r = (uint32_t)keys[i];
+      sid[off + i] = (uint32_t)(keys[i] >> 32); sscore[off + i] = scores[off + r]; srank[off + i] = (unsigned short)r;
+    }
+    __syncthreads();
+  }
 }
 
 extern "C" int shadow_sampler_set_ppr_tables(shadow_sampler *s, const uint64_t *ptr, const uint32_t *neighs, const float *scores) {
@@ -337,6 +363,21 @@ extern "C" int shadow_sampler_set_ppr_tables(shadow_sampler *s, const uint64_t *
   CUDA_TRY(cudaMemcpy(s->ppr_neighs.p, neighs, (size_t)tot * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(s->ppr_scores.p, scores, (size_t)tot * 4, cudaMemcpyHostToDevice));
   s->has_ppr = true;
+  s->ppr_sorted = false;
+  if (!getenv("SHADOW_NO_SORTED_PPR")) {
+    if (s->ppr_sid.ensure((size_t)std::max<uint64_t>(tot, 1) * 4) || s->ppr_sscore.ensure((size_t)std::max<uint64_t>(tot, 1) * 4) ||
+        s->ppr_srank.ensure((size_t)std::max<uint64_t>(tot, 1) * 2))
+      FAIL(SHADOW_ECUDA, "cudaMalloc(sorted ppr tables) failed");
+    int *flag; CUDA_TRY(cudaMalloc(&flag, 4)); CUDA_TRY(cudaMemsetAsync(flag, 0, 4, s->stream));
+    ppr_sort_rows_kernel<<<s->num_sms * 16, 128, 0, s->stream>>>((const unsigned long long *)s->ppr_ptr.p, (const uint32_t *)s->ppr_neighs.p,
+                                                                 (const float *)s->ppr_scores.p, s->N, (uint32_t *)s->ppr_sid.p, (float *)s->ppr_sscore.p,
+                                                                 (unsigned short *)s->ppr_srank.p, flag);
+    int too_long = 0;
+    CUDA_TRY(cudaMemcpyAsync(&too_long, flag, 4, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    cudaFree(flag);
+    s->ppr_sorted = !too_long;
+  }
   return 0;
 }
 
@@ -410,6 +451,7 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   K.tconn = (c.method == SHADOW_NODEIID) ? 0 : c.include_target_conn;
   K.aug = c.aug; K.fixed_mode = c.fixed_mode; K.rng_mode = c.rng_mode;
   K.ppr_ptr = (const unsigned long long *)s->ppr_ptr.p; K.ppr_neighs = (const uint32_t *)s->ppr_neighs.p; K.ppr_scores = (const float *)s->ppr_scores.p;
+  if (s->ppr_sorted) { K.ppr_sid = (const uint32_t *)s->ppr_sid.p; K.ppr_sscore = (const float *)s->ppr_sscore.p; K.ppr_srank = (const unsigned short *)s->ppr_srank.p; }
   K.philox_seed = (uint32_t)s->seed; K.philox_epoch = r.philox_epoch; K.root_slot_base = r.idx_start / (uint32_t)c.num_roots;
   K.ecap = caps.ecap;
   K.ncap = caps.ncap; K.ccap = caps.ccap; K.ccap2 = caps.ccap2; K.acap = caps.acap; K.acap2 = caps.acap2; K.hcap = caps.hcap; K.hshift = caps.hshift;

@@ -43,6 +43,11 @@ struct SampleParams {
   const unsigned long long *ppr_ptr;
   const uint32_t *ppr_neighs;
   const float *ppr_scores;
+  // the same rows re-ordered by node id at table-install time (+ each entry's position in score order): the single-root
+  // PPR node set then needs no sort at all.  NULL => generic path.
+  const uint32_t *ppr_sid;
+  const float *ppr_sscore;
+  const unsigned short *ppr_srank;
   // random streams
   const uint32_t *rand_stream;       // glibc replay: pre-generated rand() outputs
   long long *rand_off;               // [num_subg+1] stream offset of each subgraph (written by the prepass)
@@ -181,6 +186,51 @@ __device__ inline int build_nodes_ppr(const SampleParams &P, const Ws &ws, const
     __syncthreads();
   }
   return finish_sorted_pairs(ws, ncand, P.ncap, warp_sums);
+}
+
+// ppr, single root, id-sorted table rows (PS.cpp:565-595 with the same outcome as build_nodes_ppr):
+//   cut  = first position IN SCORE ORDER whose score fails the relative threshold (or size_neigh)
+//   set  = {entries with score rank < cut}  U  {root}      (the root keeps -1, or scores[0] when the row has <= 1 entry, unless its own entry is selected)
+__device__ inline int build_nodes_ppr_sorted(const SampleParams &P, const Ws &ws, uint32_t t, uint32_t *s_cut, uint32_t *s_aux, uint32_t *warp_sums) {
+  const unsigned long long off = P.ppr_ptr[t];
+  const int len_all = (int)(P.ppr_ptr[t + 1] - off);
+  const int size_neigh = len_all < P.k ? len_all : P.k;
+  const float max_ppr = size_neigh > 1 ? P.ppr_scores[off + 1] : 0.f;
+  if (threadIdx.x == 0) { *s_cut = (uint32_t)size_neigh; s_aux[0] = 0; s_aux[1] = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < len_all; i += blockDim.x) {
+    const uint32_t r = P.ppr_srank[off + i];
+    if (r < (uint32_t)size_neigh) {
+      const float sc = P.ppr_sscore[off + i];
+      if (max_ppr == 0.f || __fdiv_rn(sc, max_ppr) < P.threshold) atomicMin(s_cut, r);
+    }
+  }
+  __syncthreads();
+  const uint32_t cut = *s_cut;
+  // is the root's own entry selected, and how many selected ids are below the root?
+  for (int base = 0; base < len_all; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    bool sel = false; uint32_t id = 0;
+    if (i < len_all) { sel = P.ppr_srank[off + i] < cut; id = P.ppr_sid[off + i]; }
+    const uint32_t below = __ballot_sync(0xffffffffu, sel && id < t), same = __ballot_sync(0xffffffffu, sel && id == t);
+    if (lane_id() == 0 && (below | same)) { if (below) atomicAdd(&s_aux[0], (uint32_t)__popc(below)); if (same) s_aux[1] = 1; }
+  }
+  __syncthreads();
+  const uint32_t n_below = s_aux[0];
+  const bool root_in = s_aux[1] != 0;
+  const int nsel = (int)block_ordered_compact(
+      len_all, [&](int i) { return P.ppr_srank[off + i] < cut; },
+      [&](int i, uint32_t r) {
+        const uint32_t id = P.ppr_sid[off + i];
+        const uint32_t at = r + ((!root_in && id > t) ? 1u : 0u);
+        if ((int)at < P.ncap) { ws.nodes[at] = id; ws.pprv[at] = P.ppr_sscore[off + i]; }
+      }, warp_sums);
+  if (!root_in && threadIdx.x == 0 && (int)n_below < P.ncap) {
+    ws.nodes[n_below] = t;
+    ws.pprv[n_below] = (size_neigh <= 1 && len_all > 0) ? P.ppr_scores[off] : -1.f;                // PS.cpp:574,581
+  }
+  __syncthreads();
+  return nsel + (root_in ? 0 : 1);
 }
 
 // sort + unique of a[0..n) (uint32), result written to out[0..cap); returns the (uncapped) count
@@ -451,7 +501,8 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
     int n = 0;
     long long draws = 0;
     if (P.method == SHADOW_PPR) {
-      n = build_nodes_ppr(P, ws, s_roots, nt, &s_cut, s_warp_sums);
+      if (nt == 1 && P.ppr_sid) n = build_nodes_ppr_sorted(P, ws, s_roots[0], &s_cut, s_scan, s_warp_sums);
+      else n = build_nodes_ppr(P, ws, s_roots, nt, &s_cut, s_warp_sums);
     } else if (P.method == SHADOW_KHOP) {
       long long rb = (P.rng_mode == SHADOW_RNG_GLIBC && P.rand_off) ? P.rand_off[p] : 0;
       n = build_nodes_khop(P, ws, s_roots, nt, p, rb, &draws, s_warp_sums, &s_n);
