@@ -149,14 +149,14 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
   {
     const char *env = getenv("SHADOW_ECAP_MULT");
     const int mult = env ? atoi(env) : 6;
-    o->ecap = (o->ncap <= 32767 && mult > 0) ? std::min(16384, std::max(512, mult * o->ncap)) : 0;
+    o->ecap = (o->ncap <= 65535 && mult > 0) ? std::min(16384, std::max(512, mult * o->ncap)) : 0;
     L.st = 0;
     off = std::max(region1, align16((uint32_t)o->ecap * 8));
   }
   L.nodes = take((size_t)o->ncap * 4);
   L.pprv = take((size_t)o->ncap * 4);
   L.hkeys = take((size_t)o->hcap * 4);
-  L.hvals = take((size_t)o->hcap * 4);
+  L.st_row = take((size_t)o->ecap * 2);
   L.row_s = take((size_t)o->ncap * 4);
   L.row_e = take((size_t)o->ncap * 4);
   L.row_cnt = take(((size_t)o->ncap + 1) * 4);

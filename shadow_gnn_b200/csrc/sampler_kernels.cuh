@@ -23,7 +23,7 @@
 #endif
 
 struct WsLayout {          // byte offsets of the per-CTA workspace (shared memory, or global for huge scopes)
-  uint32_t keys, cval, nodes, pprv, hkeys, hvals, row_s, row_e, row_cnt, row_ins, rowd, row_first, row_last, row_fgt, level, all, dist, fr_a, fr_b, st;
+  uint32_t keys, cval, nodes, pprv, hkeys, st_row, row_s, row_e, row_cnt, row_ins, rowd, row_first, row_last, row_fgt, level, all, dist, fr_a, fr_b, st;
   uint32_t bytes;
 };
 
@@ -73,16 +73,17 @@ struct SampleParams {
 enum { ERR_WS_OVERFLOW = 1, ERR_OUT_OVERFLOW = 2 };
 
 struct Ws {
-  unsigned long long *keys; float *cval; uint32_t *nodes; float *pprv; uint32_t *hkeys, *hvals, *row_s, *row_e, *row_cnt,
+  unsigned long long *keys; float *cval; uint32_t *nodes; float *pprv; uint32_t *hkeys, *row_s, *row_e, *row_cnt,
       *row_ins, *row_first, *row_last, *row_fgt, *level, *all, *dist, *fr_a, *fr_b;
   uint4 *rowd;
   uint2 *st;
+  unsigned short *st_row;
 };
 __device__ __forceinline__ Ws make_ws(unsigned char *b, const WsLayout &L) {
   Ws w;
   w.keys = (unsigned long long *)(b + L.keys); w.cval = (float *)(b + L.cval);
   w.nodes = (uint32_t *)(b + L.nodes); w.pprv = (float *)(b + L.pprv);
-  w.hkeys = (uint32_t *)(b + L.hkeys); w.hvals = (uint32_t *)(b + L.hvals);
+  w.hkeys = (uint32_t *)(b + L.hkeys); w.st_row = (unsigned short *)(b + L.st_row);
   w.row_s = (uint32_t *)(b + L.row_s); w.row_e = (uint32_t *)(b + L.row_e);
   w.row_cnt = (uint32_t *)(b + L.row_cnt); w.row_ins = (uint32_t *)(b + L.row_ins);
   w.level = (uint32_t *)(b + L.level); w.all = (uint32_t *)(b + L.all);
@@ -115,26 +116,32 @@ __device__ inline uint32_t block_ordered_compact(int n, Pred pred, Emit emit, ui
 // orig -> sub map: open addressing over BUCKETS of 4 keys (one 16-byte shared-memory load tests 4 slots, so a probe
 // almost never needs a second step and the warp-wide worst case stays at one iteration).  Buckets fill in slot order.
 __device__ __forceinline__ uint32_t hash_bucket(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
-__device__ __forceinline__ uint32_t hash_lookup(const uint32_t *hk, const uint32_t *hv, uint32_t bmask, int shift, uint32_t key) {
+// membership only: the sub id of a member is its rank in the sorted node list (sub_of), looked up on the rare hit path
+__device__ __forceinline__ bool hash_contains(const uint32_t *hk, uint32_t bmask, int shift, uint32_t key) {
   uint32_t b = hash_bucket(key, shift);
   for (;;) {
     const uint4 kk = reinterpret_cast<const uint4 *>(hk)[b];
-    if (kk.x == key) return hv[4 * b];
-    if (kk.y == key) return hv[4 * b + 1];
-    if (kk.z == key) return hv[4 * b + 2];
-    if (kk.w == key) return hv[4 * b + 3];
-    if (kk.w == NONE32) return NONE32;
+    if (kk.x == key || kk.y == key || kk.z == key || kk.w == key) return true;
+    if (kk.w == NONE32) return false;
     b = (b + 1) & bmask;
   }
 }
-__device__ __forceinline__ void hash_insert(uint32_t *hk, uint32_t *hv, uint32_t bmask, int shift, uint32_t key, uint32_t val) {
+__device__ __forceinline__ void hash_insert(uint32_t *hk, uint32_t bmask, int shift, uint32_t key) {
   uint32_t b = hash_bucket(key, shift);
   for (;;) {
 #pragma unroll
     for (int j = 0; j < 4; j++)
-      if (atomicCAS(&hk[4 * b + j], NONE32, key) == NONE32) { hv[4 * b + j] = val; return; }
+      if (atomicCAS(&hk[4 * b + j], NONE32, key) == NONE32) return;
     b = (b + 1) & bmask;
   }
+}
+__device__ __forceinline__ uint32_t sub_of(const uint32_t *nodes, int n, uint32_t key) {      // rank of a member in the sorted node list
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (nodes[mid] < key) lo = mid + 1; else hi = mid; }
+  return (uint32_t)lo;
+}
+__device__ __forceinline__ uint32_t hash_lookup(const uint32_t *hk, const uint32_t *nodes, int n, uint32_t bmask, int shift, uint32_t key) {
+  return hash_contains(hk, bmask, shift, key) ? sub_of(nodes, n, key) : NONE32;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -394,10 +401,9 @@ __device__ __forceinline__ uint32_t drnl_single(uint32_t dx, uint32_t dy) {     
 // bug slot) is derived afterwards from the staged entries, so the inner loop is load -> probe -> ballot -> store.
 // ------------------------------------------------------------------------------------------------
 #define SCAN_U 8
-#define ST_GT 0x8000u
-struct KeepCtx { const uint32_t *hk, *hv; uint32_t hmask; int hshift; const uint32_t *roots; int nt; };
+struct KeepCtx { const uint32_t *hk, *nodes; int n; uint32_t hmask; int hshift; const uint32_t *roots; int nt; };
 __device__ __forceinline__ uint32_t keep_lookup(const KeepCtx &K, uint32_t nb, bool v_is_t) {
-  uint32_t sub = hash_lookup(K.hk, K.hv, K.hmask, K.hshift, nb);
+  uint32_t sub = hash_lookup(K.hk, K.nodes, K.n, K.hmask, K.hshift, nb);
   if (sub != NONE32 && v_is_t) { bool nb_t = false; for (int j = 0; j < K.nt; j++) nb_t |= (K.roots[j] == nb); if (nb_t) sub = NONE32; }   // PS.cpp:412-418
   return sub;
 }
@@ -409,6 +415,7 @@ __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws
   const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
   const uint32_t rcap = (uint32_t)P.ecap / nwarp;              // staging region of this warp
   uint2 *st = ws.st + (size_t)warp * rcap;
+  unsigned short *strow = ws.st_row + (size_t)warp * rcap;
   const uint32_t i_begin = (uint32_t)(((unsigned long long)num_items * warp) / nwarp);
   const uint32_t i_end = (uint32_t)(((unsigned long long)num_items * (warp + 1)) / nwarp);
   if (i_begin >= i_end) return 0;
@@ -457,10 +464,9 @@ __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws
           hit = !(v_t && nb_t);
         }
         const uint32_t mk2 = TCONN ? mk : __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-          const uint32_t slot = 4u * b + (kk.x == nb ? 0u : kk.y == nb ? 1u : kk.z == nb ? 2u : 3u);
+        if (hit) {                                             // stage (neighbour id, slot) + row; sub id and order flags are resolved at emit time
           const uint32_t at = cnt + __popc(mk2 & lanemask_lt());
-          if (at < rcap) st[at] = make_uint2(K.hv[slot] | (nb > ws.nodes[rr] ? ST_GT : 0u) | (rr << 16), c);       // :420-422
+          if (at < rcap) { st[at] = make_uint2(nb, c); strow[at] = (unsigned short)rr; }                          // :420-422
         }
         cnt += __popc(mk2);
       }
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const uint32_t v = ws.nodes[i];
-      hash_insert(ws.hkeys, ws.hvals, hmask, P.hshift, v, (uint32_t)i);
+      hash_insert(ws.hkeys, hmask, P.hshift, v);
       const uint32_t s = P.indptr[v], e = P.indptr[v + 1];
       ws.row_s[i] = s; ws.row_e[i] = e;
       if (!GWS && P.ecap > 0) {
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
     }
     __syncthreads();
     if (threadIdx.x < nt) {
-      uint32_t t = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, s_roots[threadIdx.x]);
+      uint32_t t = hash_lookup(ws.hkeys, ws.nodes, n, hmask, P.hshift, s_roots[threadIdx.x]);
       s_tl[threadIdx.x] = (t == NONE32) ? 0u : t;          // operator[] default-inserts 0 (PS.cpp:375)
     }
     const bool tconn = P.tconn || nt == 1;                 // PS.cpp:356-358
@@ -556,7 +562,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
         ws.rowd[i] = (i < n) ? make_uint4(ws.row_s[i], ws.row_e[i] - ws.row_s[i], ws.nodes[i], ws.row_cnt[i]) : make_uint4(0, 0, 0, num_items);
       __syncthreads();
       KeepCtx KC;
-      KC.hk = ws.hkeys; KC.hv = ws.hvals; KC.hmask = hmask; KC.hshift = P.hshift; KC.roots = s_roots; KC.nt = nt;
+      KC.hk = ws.hkeys; KC.nodes = ws.nodes; KC.n = n; KC.hmask = hmask; KC.hshift = P.hshift; KC.roots = s_roots; KC.nt = nt;
       const uint32_t wcnt = tconn ? scan_items_staged<true>(P, ws, n, num_items, KC) : scan_items_staged<false>(P, ws, n, num_items, KC);
       const uint32_t rcap = (uint32_t)P.ecap / nwarp;
       if (lane == 0) s_scan[warp] = wcnt;
@@ -570,16 +576,16 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
         for (uint32_t g = threadIdx.x; g < ktot; g += blockDim.x) {
           uint32_t wb = 0; int w = 0;
           while (g >= wb + s_scan[w]) { wb += s_scan[w]; w++; }
-          const uint32_t x = ws.st[(size_t)w * rcap + (g - wb)].x;
-          uint32_t xp = NONE32, xn = NONE32;
-          if (g > 0) { const uint32_t gp = g - 1; uint32_t wb2 = 0; int w2 = 0; while (gp >= wb2 + s_scan[w2]) { wb2 += s_scan[w2]; w2++; } xp = ws.st[(size_t)w2 * rcap + (gp - wb2)].x; }
-          if (g + 1 < ktot) { const uint32_t gn = g + 1; uint32_t wb2 = 0; int w2 = 0; while (gn >= wb2 + s_scan[w2]) { wb2 += s_scan[w2]; w2++; } xn = ws.st[(size_t)w2 * rcap + (gn - wb2)].x; }
-          const uint32_t row = x >> 16;
-          const bool first = (g == 0) || (xp >> 16) != row, last = (g + 1 == ktot) || (xn >> 16) != row;
+          const uint32_t nb = ws.st[(size_t)w * rcap + (g - wb)].x, row = ws.st_row[(size_t)w * rcap + (g - wb)];
+          uint32_t rowp = NONE32, rown = NONE32, nbp = 0;
+          if (g > 0) { const uint32_t gp = g - 1; uint32_t wb2 = 0; int w2 = 0; while (gp >= wb2 + s_scan[w2]) { wb2 += s_scan[w2]; w2++; } rowp = ws.st_row[(size_t)w2 * rcap + (gp - wb2)]; nbp = ws.st[(size_t)w2 * rcap + (gp - wb2)].x; }
+          if (g + 1 < ktot) { const uint32_t gn = g + 1; uint32_t wb2 = 0; int w2 = 0; while (gn >= wb2 + s_scan[w2]) { wb2 += s_scan[w2]; w2++; } rown = ws.st_row[(size_t)w2 * rcap + (gn - wb2)]; }
+          const uint32_t v = ws.nodes[row];
+          const bool first = rowp != row, last = rown != row, gt = nb > v;
           if (first) ws.row_first[row] = g;
           if (last) ws.row_last[row] = g + 1;
-          if ((x & ST_GT) && (first || !(xp & ST_GT))) ws.row_fgt[row] = g;
-          if ((x & 0x7fffu) == row) ws.row_ins[row] = 1;                                             // self loop present
+          if (gt && (first || !(nbp > v))) ws.row_fgt[row] = g;
+          if (nb == v) ws.row_ins[row] = 1;                                                           // self loop present
         }
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -618,7 +624,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
         bool keep = false, less = false, self = false;
         if (c < e) {
           const uint32_t nb = ldg_stream_u32(P.indices + c);
-          keep = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb) != NONE32;
+          keep = hash_lookup(ws.hkeys, ws.nodes, n, hmask, P.hshift, nb) != NONE32;
           if (keep && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); keep = !nb_t; }   // :412-418
           less = keep && nb < v; self = (nb == v);
         }
@@ -629,7 +635,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
       if (!inserting && !P.fixed_mode && e < P.num_edges) {
         // PS.cpp:401: the row bound is idx_end + 1 even without an insertion => slot `e` (first slot of the next row) is tested too
         const uint32_t nb = P.indices[e];
-        bool keep = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb) != NONE32;
+        bool keep = hash_lookup(ws.hkeys, ws.nodes, n, hmask, P.hshift, nb) != NONE32;
         if (keep && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); keep = !nb_t; }
         kept += keep ? 1u : 0u;
       }
@@ -675,9 +681,10 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
           uint32_t wb = 0; int w = 0;
           while (g >= wb + s_scan[w]) { wb += s_scan[w]; w++; }
           const uint2 ent = ws.st[(size_t)w * rcap + (g - wb)];
-          const uint32_t row = ent.x >> 16;
-          const long long pos = edge_base + ws.row_cnt[row] + (g - ws.row_first[row]) + ((ws.row_ins[row] != NONE32 && (ent.x & ST_GT)) ? 1 : 0);
-          P.indices_out[pos] = (int)(node_base + (ent.x & 0x7fffu));
+          const uint32_t row = ws.st_row[(size_t)w * rcap + (g - wb)];
+          const bool gt = ent.x > ws.nodes[row];
+          const long long pos = edge_base + ws.row_cnt[row] + (g - ws.row_first[row]) + ((ws.row_ins[row] != NONE32 && gt) ? 1 : 0);
+          P.indices_out[pos] = (int)(node_base + sub_of(ws.nodes, n, ent.x));
           P.orig_edge[pos] = ent.y;
         }
         for (int r = threadIdx.x; r < n; r += blockDim.x) {
@@ -705,7 +712,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
           uint32_t sub = NONE32, nb = 0;
           if (c < e) {
             nb = P.indices[c];
-            sub = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb);
+            sub = hash_lookup(ws.hkeys, ws.nodes, n, hmask, P.hshift, nb);
             if (sub != NONE32 && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); if (nb_t) sub = NONE32; }
           }
           const uint32_t mask = __ballot_sync(0xffffffffu, sub != NONE32);
@@ -720,7 +727,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
           if (lane == 0) { P.indices_out[obase + ins] = (int)(node_base + r); P.orig_edge[obase + ins] = NONE32; }   // :406-411
         } else if (!P.fixed_mode && e < P.num_edges) {
           const uint32_t nb = P.indices[e];
-          uint32_t sub = hash_lookup(ws.hkeys, ws.hvals, hmask, P.hshift, nb);
+          uint32_t sub = hash_lookup(ws.hkeys, ws.nodes, n, hmask, P.hshift, nb);
           if (sub != NONE32 && v_is_t) { bool nb_t = false; for (int j = 0; j < nt; j++) nb_t |= (s_roots[j] == nb); if (nb_t) sub = NONE32; }
           if (sub != NONE32 && lane == 0) { P.indices_out[obase + kept] = (int)(node_base + sub); P.orig_edge[obase + kept] = e; }
         }
