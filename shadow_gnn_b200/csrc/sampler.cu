@@ -95,6 +95,7 @@ struct shadow_sampler {
   // ppr tables
   DevBuf ppr_ptr, ppr_neighs, ppr_scores, ppr_sid, ppr_sscore, ppr_srank;
   bool has_ppr = false, ppr_sorted = false;
+  long long ppr_maxlen = 0;
   std::vector<std::vector<Result>> ring;   // [num_ring][num_ens]
   DevBuf rand_stream, rand_off, gws;
   std::vector<uint32_t> rand_host;
@@ -113,6 +114,7 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
     ncap = nr * ((long long)c.k + 1);
     ccap = nr * ((long long)c.k + 2);
     acap = 1;
+    if (c.method == SHADOW_PPR_ST) max_draws = nr * s->ppr_maxlen;
   } else if (c.method == SHADOW_KHOP) {
     long long fan;
     if (c.budget < 0) { long long d; int rc = graph_dmax(s, &d); if (rc) return rc; fan = d; }
@@ -356,6 +358,8 @@ extern "C" int shadow_sampler_set_ppr_tables(shadow_sampler *s, const uint64_t *
   CUDA_TRY(cudaSetDevice(s->device));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   const uint64_t tot = ptr[s->N];
+  s->ppr_maxlen = 0;
+  for (uint32_t v = 0; v < s->N; v++) s->ppr_maxlen = std::max<long long>(s->ppr_maxlen, (long long)(ptr[v + 1] - ptr[v]));
   if (s->ppr_ptr.ensure(((size_t)s->N + 1) * 8) || s->ppr_neighs.ensure((size_t)std::max<uint64_t>(tot, 1) * 4) ||
       s->ppr_scores.ensure((size_t)std::max<uint64_t>(tot, 1) * 4))
     FAIL(SHADOW_ECUDA, "cudaMalloc(ppr tables) failed");
@@ -432,7 +436,6 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   }
   if (s->graph_dropped) FAIL(SHADOW_ESTATE, "full graph was dropped (drop_full_graph_info); only return_target_only sampling is possible");
   if ((c.method == SHADOW_PPR || c.method == SHADOW_PPR_ST) && !s->has_ppr) FAIL(SHADOW_ESTATE, "ppr sampler used before preproc_ppr_approximate / set_ppr_tables");
-  if (c.method == SHADOW_PPR_ST) FAIL(SHADOW_EINVAL, "ppr_st is not implemented yet (valid/test silently use ppr in the reference, minibatch.py:367-370)");
   Caps caps;
   int rc = plan_caps(s, c, &caps);
   if (rc) return rc;
@@ -481,7 +484,9 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   }
 
   // ---- glibc replay: generate the stream, fix per-subgraph offsets with the serial prepass ----
-  const bool glibc = (c.method == SHADOW_KHOP && c.rng_mode == SHADOW_RNG_GLIBC && c.budget >= 0 && c.depth > 0);
+  const bool glibc_khop = (c.method == SHADOW_KHOP && c.rng_mode == SHADOW_RNG_GLIBC && c.budget >= 0 && c.depth > 0);
+  const bool glibc_st = (c.method == SHADOW_PPR_ST && c.rng_mode == SHADOW_RNG_GLIBC);
+  const bool glibc = glibc_khop || glibc_st;
   if (glibc) {
     const long long need = (long long)P * caps.max_draws;
     if (need > (1ll << 28)) FAIL(SHADOW_ECAP, "glibc-replay stream of %lld draws is too long; use SHADOW_RNG_PHILOX for super-batches", need);
@@ -491,7 +496,11 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     K.rand_stream = (const uint32_t *)s->rand_stream.p; K.rand_off = (long long *)s->rand_off.p;
   }
   CUDA_TRY(cudaMemsetAsync(sync, 0, 64 + (size_t)P * 8, s->stream));
-  if (glibc) {
+  if (glibc_st) {
+    ppr_st_rand_offsets_kernel<<<1, 32, 0, s->stream>>>(K);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (glibc_khop) {
     SampleParams Kp = K;
     Kp.count_only_last = 1;
     if (use_gws) { khop_rand_offsets_kernel<<<1, SAMPLER_BLOCK, 0, s->stream>>>(Kp); }
@@ -566,7 +575,8 @@ extern "C" int shadow_sampler_sample(shadow_sampler *s, const shadow_sampler_cfg
     r.cfg = cfgs[b]; r.idx_start = idx_start; r.idx_end = idx_end; r.num_subg = P; r.philox_epoch = epoch;
     int rc = launch_branch(s, r);
     if (rc) return rc;
-    const bool glibc = (r.cfg.method == SHADOW_KHOP && r.cfg.rng_mode == SHADOW_RNG_GLIBC && r.cfg.budget >= 0 && !r.cfg.return_target_only);
+    const bool glibc = !r.cfg.return_target_only && r.cfg.rng_mode == SHADOW_RNG_GLIBC &&
+                       ((r.cfg.method == SHADOW_KHOP && r.cfg.budget >= 0) || r.cfg.method == SHADOW_PPR_ST);
     if (glibc) {             // keep the stream position exact: validate now, then drop the consumed prefix
       rc = validate_branch(s, r);
       if (rc) return rc;

@@ -195,6 +195,50 @@ __device__ inline int build_nodes_ppr(const SampleParams &P, const Ws &ws, const
   return finish_sorted_pairs(ws, ncand, P.ncap, warp_sums);
 }
 
+// ppr_stochastic (PS.cpp:603-650).  `rand() / RAND_MAX` is an integer division (:635): u is 1 only when the draw equals
+// RAND_MAX and 0 otherwise, so the weight -pow(u, 1/s) is -1 or -0 and nth_element keeps the entries whose draw hit RAND_MAX
+// (by index) followed by the lowest indices.  One draw is consumed per stored entry of every target row.
+__device__ inline int build_nodes_ppr_st(const SampleParams &P, const Ws &ws, const uint32_t *roots, int nt, int p, long long rand_base,
+                                         long long *draws_out, uint32_t *s_cut, uint32_t *s_aux /*[32]*/, uint32_t *warp_sums) {
+  int ncand = 0;
+  long long rcur = rand_base;
+  const uint32_t root_slot = P.root_slot_base + (uint32_t)p;
+  for (int it = 0; it < nt; it++) {
+    const uint32_t t = roots[it];
+    const unsigned long long off = P.ppr_ptr[t];
+    const int size_all = (int)(P.ppr_ptr[t + 1] - off);
+    const int size_neigh = size_all < P.k ? size_all : P.k;
+    const float max_ppr = size_neigh <= 1 ? 0.f : P.ppr_scores[off + 1];                           // :615
+    if (threadIdx.x == 0) { *s_cut = (uint32_t)size_neigh; s_aux[0] = 0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < size_neigh; i += blockDim.x)                                    // first failing index (:617-622)
+      if (max_ppr == 0.f || __fdiv_rn(P.ppr_scores[off + i], max_ppr) < P.threshold) atomicMin(s_cut, (uint32_t)i);
+    for (int i = threadIdx.x; i < size_all; i += blockDim.x) {                                    // entries whose draw is RAND_MAX (u == 1)
+      const uint32_t d = (P.rng_mode == SHADOW_RNG_GLIBC) ? P.rand_stream[rcur + i]
+                                                          : (philox4x32_10_x(t, 0x70707273u, (uint32_t)i, root_slot, P.philox_seed, P.philox_epoch) >> 1);
+      if (d == 2147483647u) { const uint32_t q = atomicAdd(&s_aux[0], 1u); if (q < 30) s_aux[2 + q] = (uint32_t)i; }
+    }
+    __syncthreads();
+    const int first_fail = (int)*s_cut;
+    const int cnt = first_fail < size_neigh ? first_fail + 1 : size_neigh;                        // the failing entry is counted too
+    const int nflag = (int)min(s_aux[0], 30u);
+    // ordered append of the selected entries (their order inside one target does not matter: ids are distinct)
+    const int nsel = (int)block_ordered_compact(
+        size_all,
+        [&](int i) { int less_f = 0; bool flagged = false; for (int q = 0; q < nflag; q++) { const int f = (int)s_aux[2 + q]; less_f += f < i; flagged |= f == i; }
+                     return (flagged ? less_f : nflag + (i - less_f)) < cnt; },
+        [&](int i, uint32_t r) { if (ncand + (int)r < P.ccap) { ws.keys[ncand + r] = ((unsigned long long)P.ppr_neighs[off + i] << 32) | (uint32_t)(ncand + r); ws.cval[ncand + r] = P.ppr_scores[off + i]; } },
+        warp_sums);
+    ncand += nsel;
+    rcur += size_all;
+    __syncthreads();
+  }
+  *draws_out = rcur - rand_base;
+  if (ncand > P.ccap) return -1;
+  if (ncand == 0) return 0;
+  return finish_sorted_pairs(ws, ncand, P.ncap, warp_sums);
+}
+
 // ppr, single root, id-sorted table rows (PS.cpp:565-595 with the same outcome as build_nodes_ppr):
 //   cut  = first position IN SCORE ORDER whose score fails the relative threshold (or size_neigh)
 //   set  = {entries with score rank < cut}  U  {root}      (the root keeps -1, or scores[0] when the row has <= 1 entry, unless its own entry is selected)
@@ -509,6 +553,9 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
     if (P.method == SHADOW_PPR) {
       if (nt == 1 && P.ppr_sid) n = build_nodes_ppr_sorted(P, ws, s_roots[0], &s_cut, s_scan, s_warp_sums);
       else n = build_nodes_ppr(P, ws, s_roots, nt, &s_cut, s_warp_sums);
+    } else if (P.method == SHADOW_PPR_ST) {
+      long long rb = (P.rng_mode == SHADOW_RNG_GLIBC && P.rand_off) ? P.rand_off[p] : 0;
+      n = build_nodes_ppr_st(P, ws, s_roots, nt, p, rb, &draws, &s_cut, s_scan, s_warp_sums);
     } else if (P.method == SHADOW_KHOP) {
       long long rb = (P.rng_mode == SHADOW_RNG_GLIBC && P.rand_off) ? P.rand_off[p] : 0;
       n = build_nodes_khop(P, ws, s_roots, nt, p, rb, &draws, s_warp_sums, &s_n);
@@ -749,6 +796,18 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
       }
     }
   }
+}
+
+// ppr_st glibc replay: the draw count of a subgraph is the total stored length of its target rows -> offsets by a serial scan
+__global__ void ppr_st_rand_offsets_kernel(const SampleParams P) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long cursor = 0;
+  for (int p = 0; p < P.num_subg; p++) {
+    P.rand_off[p] = cursor;
+    const int r0 = p * P.num_roots, nt = min(P.num_roots, P.num_root_ids - r0);
+    for (int j = 0; j < nt; j++) { const uint32_t t = P.roots[r0 + j]; cursor += (long long)(P.ppr_ptr[t + 1] - P.ppr_ptr[t]); }
+  }
+  P.rand_off[P.num_subg] = cursor;
 }
 
 // glibc-replay prepass: ONE CTA walks the subgraphs in order and fixes the rand() offset of each

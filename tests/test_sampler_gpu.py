@@ -27,8 +27,6 @@ G = Golden()
 def test_cuda_matches_reference_golden(ci):
     PS = _product()
     cfg, aug, targets, calls, want = G.case(ci)
-    if cfg["method"] == "ppr_st":
-        pytest.skip("ppr_st not implemented yet")
     s = PS.ParallelSampler(G.indptr, G.indices, [], G.meta["P"], 1, True, True, [], 1, "", "", "", G.meta["seed"])
     s.shuffle_targets(targets)
     if cfg["method"] in ("ppr", "ppr_st"):
@@ -268,3 +266,18 @@ def test_superbatch_properties_philox():
     assert torch.equal(b.orig_node, b2.orig_node) and torch.equal(b.indices, b2.indices)
     b3 = s2.sample_to_device([cfg], [{"hops"}])[0]
     assert not torch.equal(b3.orig_node[:1000], b.orig_node[:1000])
+
+
+def test_ppr_st_grid_vs_oracle():
+    """ppr_stochastic incl. its integer-division quirk (PS.cpp:635) and rand() stream consumption, 1 and 2 roots, two calls per epoch"""
+    from oracle import oracle as O
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(3000, 12, 11, self_loops=30)
+    N = indptr.size - 1
+    alln = np.arange(N, dtype=np.uint32)
+    nb, sc, ln = O.ppr_push(indptr, indices, alln, 60, 0.85, 1e-4, 8)
+    tables = O.ppr_rows_to_csr(N, alln, nb, sc, ln)
+    rng = np.random.default_rng(6)
+    for k, thr, se, nr in itertools.product([1, 20, 30], [0, 0.01, 0.3], [False, True], [1, 2]):
+        cfg = dict(method="ppr_st", k=str(k), threshold=str(thr), num_roots=str(nr), add_self_edge="true" if se else "false", include_target_conn="false")
+        _oracle_vs_cuda(indptr, indices, rng.permutation(N - 2)[:70 * nr].astype(np.uint32), 48, 5, cfg, (), ppr_tables=tables)
