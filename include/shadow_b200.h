@@ -178,8 +178,8 @@ int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float *scale, con
                             float *mean, float *rstd, int32_t n, int32_t D, int32_t act, int32_t do_norm, int32_t accumulate,
                             void *cuda_stream);
 int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const float *Z, int32_t ldz, const float *scale, const float *mean,
-                            const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, int32_t n, int32_t D,
-                            int32_t act, int32_t do_norm, void *cuda_stream);
+                            const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, float *dbias, int32_t n,
+                            int32_t D, int32_t act, int32_t do_norm, void *cuda_stream);   /* dscale/doffset/dbias (column sums of dZ, may be NULL) are ACCUMULATED */
 /* GAT._aggregate_attention for all heads (layers.py:560-582): a_self/a_neigh [n,heads] already through LeakyReLU(0.2) */
 int shadow_gat_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
                        const float *a_neigh, const float *H, float *out, float *rowmax, float *denom, int32_t n, int32_t heads,

@@ -88,7 +88,7 @@ lib.shadow_edge_vals_sym_normalize.argtypes = [_vp, _vp, _i32, _i32, _i32, _vp, 
 lib.shadow_spmm_csr_fwd_f32.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _f, _vp]
 lib.shadow_spmm_csr_bwd_f32.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp]
 lib.shadow_act_norm_fwd_f32.argtypes = [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
-lib.shadow_act_norm_bwd_f32.argtypes = [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]
+lib.shadow_act_norm_bwd_f32.argtypes = [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]
 lib.shadow_gat_fwd_f32.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]
 lib.shadow_gat_bwd_f32.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]
 lib.shadow_segment_pool_fwd_f32.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]

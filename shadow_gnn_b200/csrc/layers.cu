@@ -257,15 +257,15 @@ template <int NPL>
 __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *__restrict__ dOut, int ldo, const float *__restrict__ Z, int ldz,
                                                                    const float *__restrict__ scale, const float *__restrict__ mean_in,
                                                                    const float *__restrict__ rstd_in, float *__restrict__ dZ, int lddz,
-                                                                   float *__restrict__ dscale, float *__restrict__ doffset, int n, int D, int act,
-                                                                   int do_norm) {
-  extern __shared__ float sh[];               // [2*D] column partials of this CTA
+                                                                   float *__restrict__ dscale, float *__restrict__ doffset, float *__restrict__ dbias,
+                                                                   int n, int D, int act, int do_norm) {
+  extern __shared__ float sh[];               // [3*D] column partials of this CTA: dscale, doffset, dbias
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int f = threadIdx.x; f < 2 * D; f += blockDim.x) sh[f] = 0.f;
+  for (int f = threadIdx.x; f < 3 * D; f += blockDim.x) sh[f] = 0.f;
   __syncthreads();
-  float ps[NPL], po[NPL];
+  float ps[NPL], po[NPL], pb[NPL];
 #pragma unroll
-  for (int k = 0; k < NPL; k++) { ps[k] = 0.f; po[k] = 0.f; }
+  for (int k = 0; k < NPL; k++) { ps[k] = 0.f; po[k] = 0.f; pb[k] = 0.f; }
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     float a[NPL], g[NPL], z[NPL];
 #pragma unroll
@@ -287,20 +287,23 @@ __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *
 #pragma unroll
       for (int k = 0; k < NPL; k++) {
         const int f = lane + 32 * k;
-        if (f < D) dZ[(size_t)i * lddz + f] = rstd * (dxh[k] - s1 - xh[k] * s2) * act_df(z[k], a[k], act);
+        if (f < D) { const float dz = rstd * (dxh[k] - s1 - xh[k] * s2) * act_df(z[k], a[k], act); dZ[(size_t)i * lddz + f] = dz; pb[k] += dz; }
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) dZ[(size_t)i * lddz + f] = g[k] * act_df(z[k], a[k], act); }
+      for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) { const float dz = g[k] * act_df(z[k], a[k], act); dZ[(size_t)i * lddz + f] = dz; pb[k] += dz; } }
     }
   }
-  if (do_norm) {
 #pragma unroll
-    for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) { atomicAdd(&sh[f], ps[k]); atomicAdd(&sh[D + f], po[k]); } }
+  for (int k = 0; k < NPL; k++) {
+    const int f = lane + 32 * k;
+    if (f < D) { if (do_norm) { atomicAdd(&sh[f], ps[k]); atomicAdd(&sh[D + f], po[k]); } if (dbias) atomicAdd(&sh[2 * D + f], pb[k]); }
   }
   __syncthreads();
-  if (do_norm)
-    for (int f = threadIdx.x; f < D; f += blockDim.x) { atomicAdd(&dscale[f], sh[f]); atomicAdd(&doffset[f], sh[D + f]); }
+  for (int f = threadIdx.x; f < D; f += blockDim.x) {
+    if (do_norm) { atomicAdd(&dscale[f], sh[f]); atomicAdd(&doffset[f], sh[D + f]); }
+    if (dbias) atomicAdd(&dbias[f], sh[2 * D + f]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -519,11 +522,11 @@ extern "C" int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float 
   return 0;
 }
 extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const float *Z, int32_t ldz, const float *scale, const float *mean,
-                                       const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, int32_t n, int32_t D,
+                                       const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, float *dbias, int32_t n, int32_t D,
                                        int32_t act, int32_t do_norm, void *stream) {
   if (n <= 0) return 0;
   if (D > 32 * NORM_MAX_PER_LANE) FAIL(SHADOW_EINVAL, "norm_feat: D=%d exceeds %d", D, 32 * NORM_MAX_PER_LANE);
-#define LAUNCH_BWD(NPL) act_norm_bwd_kernel<NPL><<<grid_for(n, WPB, 296), LAYER_BLOCK, 2 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale, doffset, n, D, act, do_norm)
+#define LAUNCH_BWD(NPL) act_norm_bwd_kernel<NPL><<<grid_for(n, WPB, 296), LAYER_BLOCK, 3 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale, doffset, dbias, n, D, act, do_norm)
   if (D <= 32) LAUNCH_BWD(1); else if (D <= 64) LAUNCH_BWD(2); else if (D <= 128) LAUNCH_BWD(4); else if (D <= 256) LAUNCH_BWD(8);
   else if (D <= 512) LAUNCH_BWD(16); else LAUNCH_BWD(32);
 #undef LAUNCH_BWD

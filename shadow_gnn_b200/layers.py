@@ -108,6 +108,9 @@ class MLP(shaDowLayer):
         self.f_lin = nn.Linear(dim_in, dim_out)
 
     def forward(self, feat_in):
+        if self.act_name in ops.ACT_ID:
+            return ops.linear_act_norm(self.f_dropout(feat_in), self.f_lin, getattr(self, "scale", None), getattr(self, "offset", None), 0, self.act_name,
+                                       self.norm == "norm_feat")
         return self._act_norm(self.f_lin(self.f_dropout(feat_in)), 0)
 
 
@@ -133,7 +136,12 @@ class GCN(shaDowLayer):
         adj = _as_device_csr(adj, feat_in.device)
         if not is_normed:
             adj.normalize_sym(dropedge, *_Dropedge.next(feat_in.device))
-        feat_out = self._act_norm(self.f_lin(ops.spmm(adj, feat_in)), 0)
+        agg = ops.spmm(adj, feat_in)
+        if self.act_name in ops.ACT_ID:
+            feat_out = ops.linear_act_norm(agg, self.f_lin, getattr(self, "scale", None), getattr(self, "offset", None), 0, self.act_name,
+                                           self.norm == "norm_feat")
+        else:
+            feat_out = self._act_norm(self.f_lin(agg), 0)
         return feat_out, adj, True, 0.0
 
 
@@ -152,6 +160,10 @@ class GraphSAGE(shaDowLayer):
         if not is_normed:
             adj.normalize_rw(dropedge, *_Dropedge.next(feat_in.device))
         feat_in = self.f_dropout(feat_in)
+        if self.act_name in ops.ACT_ID:                 # whole layer body as one autograd node (fused forward / backward launches)
+            out = ops.sage_layer(feat_in, adj, self.f_lin_self, self.f_lin_neigh, getattr(self, "scale", None), getattr(self, "offset", None),
+                                 self.act_name, self.norm == "norm_feat")
+            return out, adj, True, 0.0
         h_self = self._act_norm(self.f_lin_self(feat_in), 0)
         h_neigh = self._act_norm(self.f_lin_neigh(ops.spmm(adj, feat_in)), 1)
         return h_self + h_neigh, adj, True, 0.0

@@ -103,6 +103,22 @@ def hop2onehot(hop_i32, dim):
     return out
 
 
+def ppr2onehot(ppr, dim):
+    """EntityEncoding.ppr2onehot_vec (frontend/graph.py:149-158): column i <=> 0.25**(i+1) <= ppr <= 0.25**i (last bin down to 0)"""
+    edges = [0.25 ** i for i in range(dim)] + [0.0]
+    out = torch.zeros((ppr.numel(), dim), dtype=torch.get_default_dtype(), device=ppr.device)
+    for i in range(dim):
+        out[:, i] = ((ppr <= edges[i]) & (ppr >= edges[i + 1])).to(out.dtype)
+    return out
+
+
+def drnl2onehot(drnl_i32, dim):
+    """EntityEncoding.drnl2onehot_vec (frontend/graph.py:160-172): labels >= 255 or > dim-1 collapse to column 0"""
+    d = drnl_i32.long() & 0xFFFFFFFF
+    d = torch.where((d >= 255) | (d > dim - 1), torch.zeros_like(d), d)
+    return torch.nn.functional.one_hot(d, dim).to(torch.get_default_dtype())
+
+
 class MinibatchShallowExtractor:
     FULL, SUBG = 0, 1
 
@@ -258,8 +274,10 @@ class MinibatchShallowExtractor:
             aug = {}
             if "hops" in self.aug_feats:
                 aug["hops"] = hop2onehot(b.hop, self.dim_1hot_hop)
-            if "pprs" in self.aug_feats or "drnls" in self.aug_feats:
-                raise NotImplementedError("'pprs' / 'drnls' feature augmentation is not wired through the device minibatch yet")
+            if "pprs" in self.aug_feats:
+                aug["pprs"] = ppr2onehot(b.ppr, self.dim_1hot_ppr)
+            if "drnls" in self.aug_feats:
+                aug["drnls"] = drnl2onehot(b.drnl, self.dim_1hot_drnl)
             # the views must outlive the sampler's ring slot: keep one super-batch per branch in flight (num_ring = 2)
             self.pool[mode][i].append(_SuperBatch(b, feat, aug, 1))
 

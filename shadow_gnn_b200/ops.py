@@ -174,13 +174,109 @@ class _ActNorm(torch.autograd.Function):
         dscale = torch.zeros(D, dtype=torch.float32, device=Z.device) if ctx.do_norm else None
         doffset = torch.zeros(D, dtype=torch.float32, device=Z.device) if ctx.do_norm else None
         check(lib.shadow_act_norm_bwd_f32(_p(dOut), D, _p(Z), D, _p(sc) if ctx.do_norm else None, _p(mean), _p(rstd), _p(dZ), D, _p(dscale), _p(doffset),
-                                          n, D, ctx.act, int(ctx.do_norm), _stream(Z)))
+                                          None, n, D, ctx.act, int(ctx.do_norm), _stream(Z)))
         return dZ, dscale, doffset, None, None
 
 
 def act_norm(Z, scale, offset, act, do_norm=True):
     """norm_feat(act(Z)) (layers.py:329-338); scale/offset are 1-D of length Z.shape[1]"""
     return _ActNorm.apply(Z, scale, offset, ACT_ID[act], bool(do_norm))
+
+
+def _grad_of(p):
+    """the parameter's gradient buffer (created on demand); fused ops accumulate into it in place"""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+def _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm, out=None, accumulate=False):
+    n, D = Z.shape
+    out = torch.empty_like(Z) if out is None else out
+    mean = torch.empty(n, dtype=torch.float32, device=Z.device)
+    rstd = torch.empty(n, dtype=torch.float32, device=Z.device)
+    sc = scale.detach()[idx] if do_norm else None
+    of = offset.detach()[idx] if do_norm else None
+    check(lib.shadow_act_norm_fwd_f32(_p(Z), D, _p(sc), _p(of), _p(out), D, _p(mean), _p(rstd), n, D, act, int(do_norm), int(accumulate), _stream(Z)))
+    return out, mean, rstd
+
+
+def _act_norm_bwd_raw(dOut, Z, scale, offset, bias, idx, mean, rstd, act, do_norm):
+    """dZ; dscale[idx] / doffset[idx] / dbias are accumulated straight into the parameters' .grad"""
+    n, D = Z.shape
+    dZ = torch.empty_like(Z)
+    sc = scale.detach()[idx] if do_norm else None
+    ds = _grad_of(scale)[idx] if do_norm else None
+    do = _grad_of(offset)[idx] if do_norm else None
+    db = _grad_of(bias) if bias is not None else None
+    check(lib.shadow_act_norm_bwd_f32(_p(dOut), D, _p(Z), D, _p(sc), _p(mean), _p(rstd), _p(dZ), D, _p(ds), _p(do), _p(db), n, D, act, int(do_norm), _stream(Z)))
+    return dZ
+
+
+class _LinearActNorm(torch.autograd.Function):
+    """out = norm_feat_idx(act(x W^T + b)) with ONE fused backward kernel; parameter gradients (W, b, scale[idx], offset[idx]) are
+    accumulated in place into `.grad` (the flat bucket of FlatAdamClip), so autograd launches no bias-sum / select / accumulate kernels"""
+
+    @staticmethod
+    def forward(ctx, x, lin_w, lin_b, scale, offset, idx, act, do_norm):
+        x = _req(x.contiguous(), torch.float32, "linear input")
+        Z = torch.addmm(lin_b.detach(), x, lin_w.detach().t())
+        out, mean, rstd = _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm)
+        ctx.save_for_backward(x, Z, mean, rstd)
+        ctx.p = (lin_w, lin_b, scale, offset, idx, act, do_norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        x, Z, mean, rstd = ctx.saved_tensors
+        lin_w, lin_b, scale, offset, idx, act, do_norm = ctx.p
+        dZ = _act_norm_bwd_raw(dOut.contiguous(), Z, scale, offset, lin_b, idx, mean, rstd, act, do_norm)
+        _grad_of(lin_w).addmm_(dZ.t(), x)
+        dX = dZ @ lin_w.detach() if ctx.needs_input_grad[0] else None
+        return dX, None, None, None, None, None, None, None
+
+
+def linear_act_norm(x, lin, scale, offset, idx, act, do_norm=True):
+    return _LinearActNorm.apply(x, lin.weight, lin.bias, scale, offset, idx, ACT_ID[act], bool(do_norm))
+
+
+class _SageLayer(torch.autograd.Function):
+    """GraphSAGE layer body (layers.py:474-483 of the reference) as one autograd node:
+    fwd  spmm, 2 GEMMs, 2 fused act+norm launches (the second accumulates into the first's output)
+    bwd  2 fused act+norm backward launches, 4 GEMMs (weight grads in place), spmm^T accumulating into dX"""
+
+    @staticmethod
+    def forward(ctx, x, adj, ws, bs, wn, bn, scale, offset, act, do_norm):
+        x = _req(x.contiguous(), torch.float32, "sage input")
+        agg = torch.empty_like(x)
+        check(lib.shadow_spmm_csr_fwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(x), _p(agg), adj.n, x.shape[1], 0.0, _stream(x)))
+        Zs = torch.addmm(bs.detach(), x, ws.detach().t())
+        Zn = torch.addmm(bn.detach(), agg, wn.detach().t())
+        out, mean_s, rstd_s = _act_norm_fwd_raw(Zs, scale, offset, 0, act, do_norm)
+        _, mean_n, rstd_n = _act_norm_fwd_raw(Zn, scale, offset, 1, act, do_norm, out=out, accumulate=True)
+        ctx.save_for_backward(x, agg, Zs, Zn, mean_s, rstd_s, mean_n, rstd_n)
+        ctx.p = (adj, ws, bs, wn, bn, scale, offset, act, do_norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        x, agg, Zs, Zn, mean_s, rstd_s, mean_n, rstd_n = ctx.saved_tensors
+        adj, ws, bs, wn, bn, scale, offset, act, do_norm = ctx.p
+        dOut = dOut.contiguous()
+        dZs = _act_norm_bwd_raw(dOut, Zs, scale, offset, bs, 0, mean_s, rstd_s, act, do_norm)
+        dZn = _act_norm_bwd_raw(dOut, Zn, scale, offset, bn, 1, mean_n, rstd_n, act, do_norm)
+        _grad_of(ws).addmm_(dZs.t(), x)
+        _grad_of(wn).addmm_(dZn.t(), agg)
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 10
+        dX = dZs @ ws.detach()
+        dAgg = dZn @ wn.detach()
+        check(lib.shadow_spmm_csr_bwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(dAgg), _p(dX), adj.n, dX.shape[1], _stream(dX)))
+        return (dX,) + (None,) * 9
+
+
+def sage_layer(x, adj, lin_self, lin_neigh, scale, offset, act, do_norm=True):
+    return _SageLayer.apply(x, adj, lin_self.weight, lin_self.bias, lin_neigh.weight, lin_neigh.bias, scale, offset, ACT_ID[act], bool(do_norm))
 
 
 class _GATAgg(torch.autograd.Function):

@@ -259,3 +259,26 @@ def test_graphed_trainer_matches_eager_steps():
         assert abs(a - b) <= 1e-3 * max(abs(a), 1e-3) + 1e-5, (params[0][0], params[1][0])
     for a, b in zip(params[0][1], params[1][1]):
         close(a, b.cpu(), "parameters after one epoch: graphed vs eager")
+
+
+def test_aug_onehots_match_reference_formulas():
+    """hop / ppr / drnl one-hot encodings on device vs the numpy formulas of EntityEncoding (frontend/graph.py:134-172)"""
+    from shadow_gnn_b200 import minibatch as MB
+    hop = np.array([0, 1, 2, 5, 6, 7, 254, 255, 4294967295], dtype=np.uint32)
+    want = np.zeros((hop.size, 7))
+    for i in [-1, 0, 1, 2, 3, 4, 5]:
+        want[np.where(hop.astype(np.int64) == i)[0], i + 1] = 1
+    want[np.where(hop >= 255)[0], 0] = 1
+    got = MB.hop2onehot(torch.as_tensor(hop.view(np.int32)).cuda(), 7).cpu().numpy()
+    assert np.array_equal(got, want)
+    ppr = np.array([-1.0, 0.0, 0.1, 0.25, 0.3, 1.0, 1.5], dtype=np.float32)
+    for dim in (1, 3):
+        cf = [0.25 ** i for i in range(dim)] + [0]
+        want = np.zeros((ppr.size, dim))
+        for i in range(dim):
+            want[np.where(np.logical_and(ppr <= cf[i], ppr >= cf[i + 1])), i] = 1
+        assert np.array_equal(MB.ppr2onehot(torch.as_tensor(ppr).cuda(), dim).cpu().numpy(), want)
+    drnl = np.array([0, 1, 7, 25, 26, 200, 255, 4294967295], dtype=np.uint32)
+    d = drnl.astype(np.int64).copy(); d[d >= 255] = 0; d[d > 25] = 0
+    want = np.zeros((d.size, 26)); want[np.arange(d.size), d] = 1
+    assert np.array_equal(MB.drnl2onehot(torch.as_tensor(drnl.view(np.int32)).cuda(), 26).cpu().numpy(), want)
