@@ -25,7 +25,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(10):
         model.step(MB.TRAIN, "running", mb.one_batch(MB.TRAIN))
     torch.cuda.synchronize()
-rows = [(e.key, e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total, e.count) for e in prof.key_averages()]
+rows = [(e.key, e.self_device_time_total if hasattr(e, "self_device_time_total") else e.self_cuda_time_total, e.count) for e in prof.key_averages()]
 rows = [r for r in rows if r[1] > 0]
 rows.sort(key=lambda r: -r[1])
 tot = sum(r[1] for r in rows)

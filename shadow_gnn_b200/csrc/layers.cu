@@ -114,25 +114,32 @@ __global__ void __launch_bounds__(LAYER_BLOCK) spmm_fwd_vec_kernel(const int2 *_
     float4 acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p0 = sp.x; p0 < sp.y; p0 += 4) {
-      int c[4]; float w[4];
+    for (int p0 = sp.x; p0 < sp.y; p0 += 32) {
+      // one coalesced load brings 32 (col, val) pairs; they are broadcast by shuffle so that the X-row loads below depend on
+      // nothing in memory and up to 8 of them are in flight per lane (a root row has ~140 in-scope neighbours)
+      const int pl = p0 + lane;
+      const int c_l = pl < sp.y ? col[pl] - col_off : 0;
+      const float w_l = pl < sp.y ? (val ? val[pl] : 1.f) : 0.f;
+      const int cnt = min(32, sp.y - p0);
+      constexpr int UB = NV <= 2 ? 8 : (NV == 4 ? 4 : 2);       // X-row loads in flight per lane = UB * NV float4
+      for (int u0 = 0; u0 < cnt; u0 += UB) {
+        float4 x[UB][NV];
+        float w[UB];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const bool ok = p0 + u < sp.y;
-        c[u] = ok ? col[p0 + u] - col_off : 0;
-        w[u] = ok ? (val ? val[p0 + u] : 1.f) : 0.f;
-      }
+        for (int u = 0; u < UB; u++) {
+          const int c = __shfl_sync(0xffffffffu, c_l, (u0 + u) & 31);
+          w[u] = (u0 + u < cnt) ? __shfl_sync(0xffffffffu, w_l, (u0 + u) & 31) : 0.f;
+          const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)c * F);
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)c[u] * F);
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-          const int f = lane + 32 * k;
-          if (f < F4 && w[u] != 0.f) {
-            const float4 x = xr[f];
-            acc[k].x += w[u] * x.x; acc[k].y += w[u] * x.y; acc[k].z += w[u] * x.z; acc[k].w += w[u] * x.w;
+          for (int k = 0; k < NV; k++) {
+            const int f = lane + 32 * k;
+            x[u][k] = (f < F4 && w[u] != 0.f) ? xr[f] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+#pragma unroll
+        for (int u = 0; u < UB; u++)
+#pragma unroll
+          for (int k = 0; k < NV; k++) { acc[k].x += w[u] * x[u][k].x; acc[k].y += w[u] * x[u][k].y; acc[k].z += w[u] * x[u][k].z; acc[k].w += w[u] * x[u][k].w; }
       }
     }
 #pragma unroll
@@ -170,11 +177,19 @@ __global__ void __launch_bounds__(LAYER_BLOCK) spmm_bwd_kernel(const int2 *__res
     const int2 sp = row_span[i];
     if (VEC) {
       const int F4 = F >> 2;
-      for (int f = lane; f < F4; f += 32) {
-        const float4 g = reinterpret_cast<const float4 *>(dY + (size_t)i * F)[f];
-        for (int p = sp.x; p < sp.y; p++) {
-          const float w = val ? val[p] : 1.f;
-          if (w != 0.f) atomicAdd(reinterpret_cast<float4 *>(dX + (size_t)(col[p] - col_off) * F) + f, make_float4(w * g.x, w * g.y, w * g.z, w * g.w));
+      for (int p0 = sp.x; p0 < sp.y; p0 += 32) {
+        const int pl = p0 + lane;
+        const int c_l = pl < sp.y ? col[pl] - col_off : 0;
+        const float w_l = pl < sp.y ? (val ? val[pl] : 1.f) : 0.f;
+        const int cnt = min(32, sp.y - p0);
+        for (int u = 0; u < cnt; u++) {                        // shuffles outside the feature loop: every lane takes part
+          const int c = __shfl_sync(0xffffffffu, c_l, u);
+          const float w = __shfl_sync(0xffffffffu, w_l, u);
+          if (w == 0.f) continue;
+          for (int f = lane; f < F4; f += 32) {
+            const float4 g = reinterpret_cast<const float4 *>(dY + (size_t)i * F)[f];
+            atomicAdd(reinterpret_cast<float4 *>(dX + (size_t)c * F) + f, make_float4(w * g.x, w * g.y, w * g.z, w * g.w));
+          }
         }
       }
     } else {

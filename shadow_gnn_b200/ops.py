@@ -190,6 +190,21 @@ def _grad_of(p):
     return p.grad
 
 
+_SPLITK = 16
+
+
+def _accum_wgrad(w, dZ, x):
+    """W.grad += dZ^T x.  The product is [D_out, n] x [n, D_in] with n ~ 4,800 and a 256 x 256 result: a plain GEMM runs on 16 CTAs,
+    so it is split along n into 16 batched GEMMs whose partial results are summed (same flops, ~5x less time on 148 SMs)."""
+    g = _grad_of(w)
+    n = x.shape[0]
+    if n % _SPLITK == 0 and n >= 64 * _SPLITK:
+        part = torch.bmm(dZ.view(_SPLITK, n // _SPLITK, dZ.shape[1]).transpose(1, 2), x.view(_SPLITK, n // _SPLITK, x.shape[1]))
+        g.add_(part.sum(0))
+    else:
+        g.addmm_(dZ.t(), x)
+
+
 def _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm, out=None, accumulate=False):
     n, D = Z.shape
     out = torch.empty_like(Z) if out is None else out
@@ -231,7 +246,7 @@ class _LinearActNorm(torch.autograd.Function):
         x, Z, mean, rstd = ctx.saved_tensors
         lin_w, lin_b, scale, offset, idx, act, do_norm = ctx.p
         dZ = _act_norm_bwd_raw(dOut.contiguous(), Z, scale, offset, lin_b, idx, mean, rstd, act, do_norm)
-        _grad_of(lin_w).addmm_(dZ.t(), x)
+        _accum_wgrad(lin_w, dZ, x)
         dX = dZ @ lin_w.detach() if ctx.needs_input_grad[0] else None
         return dX, None, None, None, None, None, None, None
 
@@ -265,8 +280,8 @@ class _SageLayer(torch.autograd.Function):
         dOut = dOut.contiguous()
         dZs = _act_norm_bwd_raw(dOut, Zs, scale, offset, bs, 0, mean_s, rstd_s, act, do_norm)
         dZn = _act_norm_bwd_raw(dOut, Zn, scale, offset, bn, 1, mean_n, rstd_n, act, do_norm)
-        _grad_of(ws).addmm_(dZs.t(), x)
-        _grad_of(wn).addmm_(dZn.t(), agg)
+        _accum_wgrad(ws, dZs, x)
+        _accum_wgrad(wn, dZn, agg)
         if not ctx.needs_input_grad[0]:
             return (None,) * 10
         dX = dZs @ ws.detach()
