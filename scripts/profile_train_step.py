@@ -45,3 +45,13 @@ ev[0].record()
 for _ in range(50): tr.graph.replay()
 ev[1].record(); torch.cuda.synchronize()
 print("graph replay only ms:", ev[0].elapsed_time(ev[1]) / 50)
+with profile(activities=[ProfilerActivity.CUDA]) as prof2:
+    for _ in range(10):
+        tr.step()
+    torch.cuda.synchronize()
+rows = [(e.key, e.self_device_time_total, e.count) for e in prof2.key_averages() if e.self_device_time_total > 0]
+rows.sort(key=lambda r: -r[1])
+tot = sum(r[1] for r in rows)
+print(f"GRAPHED: total kernel time per step: {tot/10:.1f} us, kernels per step: {sum(r[2] for r in rows)/10:.0f}")
+for k, t, c in rows[:22]:
+    print(f"G {t/10:9.1f} us/step {c/10:6.1f}x avg {t/max(c,1):7.2f}  {k[:110]}")

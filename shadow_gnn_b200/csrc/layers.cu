@@ -541,7 +541,7 @@ extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const flo
                                        int32_t act, int32_t do_norm, void *stream) {
   if (n <= 0) return 0;
   if (D > 32 * NORM_MAX_PER_LANE) FAIL(SHADOW_EINVAL, "norm_feat: D=%d exceeds %d", D, 32 * NORM_MAX_PER_LANE);
-#define LAUNCH_BWD(NPL) act_norm_bwd_kernel<NPL><<<grid_for(n, WPB, 296), LAYER_BLOCK, 3 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale, doffset, dbias, n, D, act, do_norm)
+#define LAUNCH_BWD(NPL) act_norm_bwd_kernel<NPL><<<grid_for(n, WPB, 1184), LAYER_BLOCK, 3 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale, doffset, dbias, n, D, act, do_norm)
   if (D <= 32) LAUNCH_BWD(1); else if (D <= 64) LAUNCH_BWD(2); else if (D <= 128) LAUNCH_BWD(4); else if (D <= 256) LAUNCH_BWD(8);
   else if (D <= 512) LAUNCH_BWD(16); else LAUNCH_BWD(32);
 #undef LAUNCH_BWD
