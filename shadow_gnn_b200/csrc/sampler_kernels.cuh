@@ -19,7 +19,7 @@
 #define SHADOW_MAX_ROOTS 4
 #define SAMPLER_BLOCK 128
 #ifndef SAMPLER_MIN_BLOCKS
-#define SAMPLER_MIN_BLOCKS 12
+#define SAMPLER_MIN_BLOCKS 10
 #endif
 
 struct WsLayout {          // byte offsets of the per-CTA workspace (shared memory, or global for huge scopes)
