@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--task", default="full", choices=["full", "sampler", "train"])
     ap.add_argument("--sampler-steps", type=int, default=20)
     ap.add_argument("--eager", action="store_true", help="train phase without the whole-step CUDA graph")
-    ap.add_argument("--superbatch", type=int, default=16384)
+    ap.add_argument("--superbatch", type=int, default=65536)
     ap.add_argument("--superbatch-train", type=int, default=4096)
     ap.add_argument("--graph", default="S-products")
     ap.add_argument("--cpu-sample", type=int, default=4000, help="roots of the bounded CPU sample")
@@ -376,16 +376,19 @@ def sampler_phase(ctx, steps, warmup):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("sample_induce_kernel_dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        if tj.get("units_per_launch") == last.num_subg:
+            traffic = tj.get("ppr_induce_warp_kernel_dram_bytes_per_launch")
     return dict(
         value=n_all / (ms_all * 1e-3), unit="subgraphs/s", ms_per_step=ms_all / steps, steps=steps, superbatch=P, per_gpu_targets=int(roots_host.size),
-        avg_nodes_per_subgraph=avg_n, avg_edges_per_subgraph=avg_e, ppr_push_setup_s=t_ppr, gpu_launches=2 * steps,
+        avg_nodes_per_subgraph=avg_n, avg_edges_per_subgraph=avg_e, ppr_push_setup_s=t_ppr, gpu_launches=5 * steps,
+        redo_last_launch=s.last_redo_count(),
         e2e={"value": ne_all / e2e_all, "unit": "subgraphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
              "note": "roots from pinned host memory; CSR, node ids, edge ids, targets, ppr copied back to pinned host memory; features stay in HBM"},
-        roofline={"kernel": "sample_induce_kernel", "bound": "hbm", "achieved": (a1 / 1e9) / (k_ms * 1e-3), "peak": peak, "unit": "GB/s",
+        roofline={"kernel": "ppr_induce_warp_kernel", "bound": "hbm", "achieved": (a1 / 1e9) / (k_ms * 1e-3), "peak": peak, "unit": "GB/s",
                   "frac": (a1 / 1e9) / (k_ms * 1e-3) / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": a1,
                   "kernel_ms": k_ms, "units_per_launch": last.num_subg,
-                  "note": "algorithmic bytes = SURVEY.md 8(d): (B_ppr + B_induce) per subgraph x subgraphs per launch; timed with CUDA events around every launch of the timed region"},
+                  "note": "algorithmic bytes = SURVEY.md 8(d): (B_ppr + B_induce) per subgraph x subgraphs per launch; kernel_ms = CUDA events around every sampler launch of the timed region, i.e. ppr_induce_warp_kernel plus its helpers (ppr_count_kernel, scan_counts_kernel, the redo launch of sample_induce_kernel: ~6 % of the time)"},
         roofline_gather={"kernel": "gather_rows_vec4_kernel", "bound": "hbm", "algorithmic_bytes_per_launch": a2})
 
 
@@ -487,7 +490,7 @@ def run_ours(args):
                                 "parallelism": f"dp{world}: targets partitioned, graph/PPR tables/features replicated, one NCCL all-reduce of the flat {tr['nparams'] * 4} B gradient bucket per step"})
             if samp:
                 line["sampler"] = {k: samp[k] for k in ("value", "unit", "ms_per_step", "steps", "superbatch", "avg_nodes_per_subgraph", "avg_edges_per_subgraph",
-                                                        "ppr_push_setup_s", "e2e")}
+                                                        "ppr_push_setup_s", "redo_last_launch", "e2e")}
                 line["roofline"] = samp["roofline"]; line["roofline_gather"] = samp["roofline_gather"]
         else:
             line.update(metric="sampler_subgraphs_per_sec", value=samp["value"], unit="subgraphs/s", ms_per_step=samp["ms_per_step"], dtype="u32",

@@ -141,6 +141,9 @@ typedef struct {
 
 /* synchronises the sampler's stream, validates capacities (re-running with larger buffers if needed) */
 int shadow_sampler_batch_info(shadow_sampler *s, int branch, shadow_batch_info *info);
+/* diagnostics: how many subgraphs of the last validated launch did not fit the one-warp-per-subgraph PPR fast path's on-chip
+ * staging and were rebuilt by the generic kernel (no reference counterpart; results are identical either way) */
+int64_t shadow_sampler_last_redo_count(const shadow_sampler *s);
 /* device pointer + count of 4-byte elements of one field of the latest batch (valid until num_ring further calls) */
 int shadow_sampler_batch_field_dev(shadow_sampler *s, int branch, int field, void **ptr_dev, int64_t *count);
 /* copy one field to the host; 4 bytes per element */

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Kernel-variant builds of libshadow_b200.so for exploration runs (scripts/explore_variants.py): selected at run time with
+# SHADOW_B200_LIB=<path>.  The variants only differ in compile-time tuning macros of csrc/ppr_warp_kernel.cuh.
+set -e
+cd "$(dirname "$0")/../shadow_gnn_b200"
+mkdir -p variants
+build() { name=$1; shift; OUT=../variants/lib_$name.so EXTRA="$*" PTXAS_V=1 bash csrc/build.sh 2>&1 | grep -A2 "ppr_induce_warp" | grep "Used" | sed "s/^/$name: /"; }
+build u2c1m28db -DWARP_U=2 -DWARP_CH=1 -DWARP_MIN_BLOCKS=28 -DWARP_DB=1 &
+build u4c1m24db -DWARP_U=4 -DWARP_CH=1 -DWARP_MIN_BLOCKS=24 -DWARP_DB=1 &
+build u4c1m28db -DWARP_U=4 -DWARP_CH=1 -DWARP_MIN_BLOCKS=28 -DWARP_DB=1 &
+build u3c1m24db -DWARP_U=3 -DWARP_CH=1 -DWARP_MIN_BLOCKS=24 -DWARP_DB=1 &
+wait
+ls -la variants

@@ -287,6 +287,10 @@ class ParallelSampler:
         return [SubgraphStructVec(self, b) for b in range(len(configs_samplers))]
 
     # ---- device-side extras ----
+    def last_redo_count(self):
+        """subgraphs of the last validated call that the one-warp PPR fast path handed to the generic kernel (diagnostics)"""
+        return int(lib.shadow_sampler_last_redo_count(self._h))
+
     def set_stream(self, cuda_stream):
         check(lib.shadow_sampler_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "sampler_kernels.cuh"
+#include "ppr_warp_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -64,11 +65,11 @@ struct DevBuf {
 
 struct Result {              // one ensemble branch of one call: SubgraphStructVec (G.h:59-97) in HBM
   DevBuf node_ptr, edge_ptr, rowptr, indices, target, num_target, orig_node, orig_edge, hop, drnl, ppr, sync;
-  DevBuf row_span, edge_span, indices_raw, orig_edge_raw;
+  DevBuf row_span, edge_span, indices_raw, orig_edge_raw, redo;
   bool canon_valid = false;
   long long cap_nodes = 0, cap_edges = 0;
   int cap_subg = 0;
-  long long *totals_host = nullptr;   // pinned mirror of totals[3]
+  long long *totals_host = nullptr;   // pinned mirror of totals[0..3] ([3] = subgraphs the warp fast path handed to the generic kernel)
   // description of the launch (for validation / re-run)
   shadow_sampler_cfg cfg;
   uint32_t idx_start = 0, idx_end = 0;
@@ -93,9 +94,12 @@ struct shadow_sampler {
   int seed = 0;
   GlibcRand rng;
   // ppr tables
-  DevBuf ppr_ptr, ppr_neighs, ppr_scores, ppr_sid, ppr_sscore, ppr_srank;
+  DevBuf ppr_ptr, ppr_neighs, ppr_scores, ppr_sid, ppr_sscore, ppr_srank, ppr_srow;
   bool has_ppr = false, ppr_sorted = false;
   long long ppr_maxlen = 0;
+  int warp_ecap_mult = 16;                 // staged edges per node of the PPR fast path (grows when launches need many redos)
+  DevBuf wscratch;                         // its per-warp staging scratch
+  long long last_redo = 0;                 // subgraphs of the last validated launch that went through the redo kernel
   std::vector<std::vector<Result>> ring;   // [num_ring][num_ens]
   DevBuf rand_stream, rand_off, gws;
   std::vector<uint32_t> rand_host;
@@ -176,6 +180,32 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
   return 0;
 }
 
+// per-warp workspace of the single-root PPR fast path (ppr_warp_kernel.cuh)
+static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, int ecap_mult, WarpLayout *W, int *w_ecap, int *w_hbuckets, int *w_hshift) {
+  uint32_t off = 0;
+  auto take = [&](size_t bytes) { uint32_t r = off; off = align16(off + (uint32_t)bytes); return r; };
+  // staged edges per warp (global scratch, L2-resident): ecap_mult (16 to start with) per node + one full stage of head room.  A subgraph
+  // that overflows is not an error, it takes the redo launch; the multiplier grows when more than 2 % of a launch had to be redone
+  const char *env = getenv("SHADOW_WARP_ECAP_MULT");
+  *w_ecap = (env ? std::max(0, atoi(env)) : ecap_mult) * caps.ncap + 32 * WARP_U * WARP_CS * (WARP_DB ? 2 : 1);
+  // 4-key buckets: >= 1 bucket per key; 2-key buckets: >= 6 per key (same overflow rate, twice the table)
+  const char *envb = getenv("SHADOW_WARP_BUCKET_MULT");
+  *w_hbuckets = std::max(16, next_pow2((envb ? std::max(1, atoi(envb)) : (WARP_BK == 4 ? 1 : 6)) * caps.ncap));
+  int lg = 0; while ((1 << lg) < *w_hbuckets) lg++;
+  *w_hshift = 32 - lg;
+  W->hkeys = take((size_t)*w_hbuckets * 4 * WARP_BK);
+  W->rs = take((size_t)caps.ncap * 8);
+  W->nodes = take((size_t)caps.ncap * 4);
+  W->cp = take(((size_t)caps.ncap + 1) * 4);
+  W->rc = take((size_t)caps.ncap * 4);
+  W->ovf = take((1 + WARP_OVF_CAP) * 4);
+  const bool ins = c.add_self_edge != 0;
+  W->rlo = take(ins ? (size_t)caps.ncap * 4 : 0);
+  W->rins = take(ins ? (size_t)caps.ncap * 4 : 0);
+  W->rbug = take(ins ? (size_t)caps.ncap * 4 : 0);
+  W->bytes = off;
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void max_degree_kernel(const uint32_t *indptr, uint32_t n, unsigned long long *out) {
   uint32_t m = 0;
@@ -221,7 +251,7 @@ static int sampler_common_init(shadow_sampler *s, int per_batch, int num_ens, in
   s->rng.seed(seed < 0 ? (uint32_t)time(nullptr) : (uint32_t)seed);     // PS.h:49-53
   s->ring.assign(num_ring, std::vector<Result>(num_ens));
   for (auto &slot : s->ring)
-    for (auto &r : slot) CUDA_TRY(cudaMallocHost(&r.totals_host, 3 * sizeof(long long)));
+    for (auto &r : slot) CUDA_TRY(cudaMallocHost(&r.totals_host, 4 * sizeof(long long)));
   return 0;
 }
 
@@ -273,7 +303,7 @@ extern "C" int shadow_sampler_create_dev(const uint32_t *indptr_dev, const uint3
 
 static void result_release(Result &r) {
   DevBuf *all[] = {&r.node_ptr, &r.edge_ptr, &r.rowptr, &r.indices, &r.target, &r.num_target, &r.orig_node, &r.orig_edge, &r.hop, &r.drnl, &r.ppr, &r.sync,
-                   &r.row_span, &r.edge_span, &r.indices_raw, &r.orig_edge_raw};
+                   &r.row_span, &r.edge_span, &r.indices_raw, &r.orig_edge_raw, &r.redo};
   for (auto b : all) b->release();
   if (r.totals_host) cudaFreeHost(r.totals_host);
   r.totals_host = nullptr;
@@ -285,8 +315,8 @@ extern "C" int shadow_sampler_destroy(shadow_sampler *s) {
   cudaStreamSynchronize(s->stream);
   if (s->owns_graph) { cudaFree(s->indptr); if (s->indices) cudaFree(s->indices); }
   s->targets.release(); s->ppr_ptr.release(); s->ppr_neighs.release(); s->ppr_scores.release();
-  s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release();
-  s->rand_stream.release(); s->rand_off.release(); s->gws.release();
+  s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release(); s->ppr_srow.release();
+  s->rand_stream.release(); s->rand_off.release(); s->gws.release(); s->wscratch.release();
   for (auto &slot : s->ring) for (auto &r : slot) result_release(r);
   delete s;
   return 0;
@@ -325,7 +355,7 @@ extern "C" int shadow_sampler_drop_full_graph_info(shadow_sampler *s) {      // 
   if (s->owns_graph && s->indices) { cudaFree(s->indices); }
   s->indices = nullptr; s->graph_dropped = true;
   s->ppr_neighs.release(); s->ppr_scores.release(); s->ppr_ptr.release(); s->has_ppr = false;
-  s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release(); s->ppr_sorted = false;
+  s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release(); s->ppr_srow.release(); s->ppr_sorted = false;
   return 0;
 }
 
@@ -334,7 +364,8 @@ extern "C" int shadow_sampler_drop_full_graph_info(shadow_sampler *s) {      // 
 #define PPR_SORT_CAP 1024
 __global__ void __launch_bounds__(128) ppr_sort_rows_kernel(const unsigned long long *__restrict__ ptr, const uint32_t *__restrict__ neighs,
                                                             const float *__restrict__ scores, uint32_t num_nodes, uint32_t *__restrict__ sid,
-                                                            float *__restrict__ sscore, unsigned short *__restrict__ srank, int *too_long) {
+                                                            float *__restrict__ sscore, unsigned short *__restrict__ srank,
+                                                            const uint32_t *__restrict__ indptr, uint2 *__restrict__ srow, int *too_long) {
   __shared__ unsigned long long keys[PPR_SORT_CAP];
   for (uint32_t v = blockIdx.x; v < num_nodes; v += gridDim.x) {
     const unsigned long long off = ptr[v];
@@ -347,7 +378,10 @@ __global__ void __launch_bounds__(128) ppr_sort_rows_kernel(const unsigned long 
     block_bitonic_sort(keys, np2);
     for (int i = threadIdx.x; i < len; i += blockDim.x) {
       const uint32_t r = (uint32_t)keys[i];
-      sid[off + i] = (uint32_t)(keys[i] >> 32); sscore[off + i] = scores[off + r]; srank[off + i] = (unsigned short)r;
+      const uint32_t id = (uint32_t)(keys[i] >> 32);
+      sid[off + i] = id; sscore[off + i] = scores[off + r]; srank[off + i] = (unsigned short)r;
+      if (id < num_nodes) { const uint32_t rs = indptr[id]; srow[off + i] = make_uint2(rs, indptr[id + 1] - rs); }   // row extent travels with the entry
+      else srow[off + i] = make_uint2(0u, 0u);
     }
     __syncthreads();
   }
@@ -370,12 +404,12 @@ extern "C" int shadow_sampler_set_ppr_tables(shadow_sampler *s, const uint64_t *
   s->ppr_sorted = false;
   if (!getenv("SHADOW_NO_SORTED_PPR")) {
     if (s->ppr_sid.ensure((size_t)std::max<uint64_t>(tot, 1) * 4) || s->ppr_sscore.ensure((size_t)std::max<uint64_t>(tot, 1) * 4) ||
-        s->ppr_srank.ensure((size_t)std::max<uint64_t>(tot, 1) * 2))
+        s->ppr_srank.ensure((size_t)std::max<uint64_t>(tot, 1) * 2) || s->ppr_srow.ensure((size_t)std::max<uint64_t>(tot, 1) * 8))
       FAIL(SHADOW_ECUDA, "cudaMalloc(sorted ppr tables) failed");
     int *flag; CUDA_TRY(cudaMalloc(&flag, 4)); CUDA_TRY(cudaMemsetAsync(flag, 0, 4, s->stream));
     ppr_sort_rows_kernel<<<s->num_sms * 16, 128, 0, s->stream>>>((const unsigned long long *)s->ppr_ptr.p, (const uint32_t *)s->ppr_neighs.p,
                                                                  (const float *)s->ppr_scores.p, s->N, (uint32_t *)s->ppr_sid.p, (float *)s->ppr_sscore.p,
-                                                                 (unsigned short *)s->ppr_srank.p, flag);
+                                                                 (unsigned short *)s->ppr_srank.p, s->indptr, (uint2 *)s->ppr_srow.p, flag);
     int too_long = 0;
     CUDA_TRY(cudaMemcpyAsync(&too_long, flag, 4, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -419,6 +453,7 @@ static int ensure_result_caps(Result &r, int P, int num_roots, long long cap_nod
   bad |= r.drnl.ensure((size_t)cap_nodes * 4) != 0;
   bad |= r.indices_raw.ensure((size_t)cap_edges * 4) != 0;
   bad |= r.orig_edge_raw.ensure((size_t)cap_edges * 4) != 0;
+  bad |= r.redo.ensure((size_t)std::max(P, 1) * 10 + 64) != 0;      // redo list int[P4] | node counts int[P4] | score-rank cuts u16[P]   (P4 = P rounded up to 4)
   if (bad) FAIL(SHADOW_ECUDA, "cudaMalloc(result buffers) failed");
   r.cap_nodes = cap_nodes; r.cap_edges = cap_edges; r.cap_subg = P;
   return 0;
@@ -454,7 +489,7 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   K.tconn = (c.method == SHADOW_NODEIID) ? 0 : c.include_target_conn;
   K.aug = c.aug; K.fixed_mode = c.fixed_mode; K.rng_mode = c.rng_mode;
   K.ppr_ptr = (const unsigned long long *)s->ppr_ptr.p; K.ppr_neighs = (const uint32_t *)s->ppr_neighs.p; K.ppr_scores = (const float *)s->ppr_scores.p;
-  if (s->ppr_sorted) { K.ppr_sid = (const uint32_t *)s->ppr_sid.p; K.ppr_sscore = (const float *)s->ppr_sscore.p; K.ppr_srank = (const unsigned short *)s->ppr_srank.p; }
+  if (s->ppr_sorted) { K.ppr_sid = (const uint32_t *)s->ppr_sid.p; K.ppr_sscore = (const float *)s->ppr_sscore.p; K.ppr_srank = (const unsigned short *)s->ppr_srank.p; K.ppr_srow = (const uint2 *)s->ppr_srow.p; }
   K.philox_seed = (uint32_t)s->seed; K.philox_epoch = r.philox_epoch; K.root_slot_base = r.idx_start / (uint32_t)c.num_roots;
   K.ecap = caps.ecap;
   K.ncap = caps.ncap; K.ccap = caps.ccap; K.ccap2 = caps.ccap2; K.acap = caps.acap; K.acap2 = caps.acap2; K.hcap = caps.hcap; K.hshift = caps.hshift;
@@ -467,6 +502,7 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   unsigned char *sync = (unsigned char *)r.sync.p;
   K.ticket = (uint32_t *)sync; K.totals = (long long *)(sync + 8);
   K.status_n = (unsigned long long *)(sync + 64);
+  K.ticket2 = (uint32_t *)(sync + 4); K.redo_count = (uint32_t *)(sync + 32);      // redo_count == low word of totals[3]
 
   const size_t smem_limit = 200 * 1024;
   const bool use_gws = caps.L.bytes > smem_limit;
@@ -511,12 +547,39 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     }
     CUDA_TRY(cudaGetLastError());
   }
+  // single-root PPR without hop/drnl labels: one warp per subgraph (ppr_warp_kernel.cuh); whatever does not fit its on-chip
+  // staging is rebuilt by the generic kernel in redo mode, launched right behind (it exits at once when the list is empty)
+  bool fast = c.method == SHADOW_PPR && c.num_roots == 1 && s->ppr_sorted && !(c.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) && !use_gws &&
+              (((uintptr_t)s->indices & 15) == 0) && caps.ncap <= 8192 && !getenv("SHADOW_NO_WARP_PPR");
+  int w_ecap = 0;
+  if (fast) { plan_warp(caps, c, s->warp_ecap_mult, &K.WL, &w_ecap, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024; }
   if (P > 0) {
     if (use_gws) sample_induce_kernel<true><<<grid, SAMPLER_BLOCK, 0, s->stream>>>(K);
-    else sample_induce_kernel<false><<<grid, SAMPLER_BLOCK, caps.L.bytes, s->stream>>>(K);
+    else if (fast) {
+      auto kern = K.add_self ? ppr_induce_warp_kernel<true> : ppr_induce_warp_kernel<false>;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.WL.bytes));
+      int wps = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wps, kern, 32, K.WL.bytes));
+      const int gridw = std::min(P, std::max(1, wps) * s->num_sms);
+      K.w_scratch_stride = ((unsigned long long)w_ecap * 10ull + 255ull) & ~255ull;
+      if (s->wscratch.ensure((size_t)K.w_scratch_stride * gridw)) FAIL(SHADOW_ECUDA, "cudaMalloc(warp scratch) failed");
+      K.w_scratch = (unsigned char *)s->wscratch.p;
+      K.redo_list = (int *)r.redo.p;
+      const size_t P4 = ((size_t)P + 3) & ~(size_t)3;      // keeps the count array 16-byte aligned for scan_counts_kernel
+      int *cnt = (int *)r.redo.p + P4;
+      K.w_cut = (const unsigned short *)((int *)r.redo.p + 2 * P4);
+      // node_ptr[] up front: the node count of a PPR subgraph depends on its table row only (no look-back in the main kernel)
+      ppr_count_kernel<<<(P + 7) / 8, 256, 0, s->stream>>>(K, cnt, (unsigned short *)K.w_cut);
+      scan_counts_kernel<<<1, 1024, 0, s->stream>>>(cnt, P, K.node_ptr, K.totals);
+      CUDA_TRY(cudaGetLastError());
+      kern<<<gridw, 32, K.WL.bytes, s->stream>>>(K);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaFuncSetAttribute(sample_induce_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)caps.L.bytes));
+      sample_induce_kernel<false, true><<<std::min(P, 2 * s->num_sms), SAMPLER_BLOCK, caps.L.bytes, s->stream>>>(K);
+    } else sample_induce_kernel<false><<<grid, SAMPLER_BLOCK, caps.L.bytes, s->stream>>>(K);
     CUDA_TRY(cudaGetLastError());
   }
-  CUDA_TRY(cudaMemcpyAsync(r.totals_host, K.totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(r.totals_host, K.totals, 4 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
   r.pending = true; r.valid = false; r.rand_draws = 0; r.canon_valid = false;
   if (glibc) {                 // the host generator must advance by what this call consumed before the next call
     long long used = 0;
@@ -543,6 +606,8 @@ static int validate_branch(shadow_sampler *s, Result &r) {
       continue;
     }
     r.total_nodes = tn; r.total_edges = te; r.pending = false; r.valid = true;
+    s->last_redo = r.num_subg ? (long long)(r.totals_host[3] & 0xffffffffll) : 0;
+    if (s->last_redo * 50 > r.num_subg && s->warp_ecap_mult < 128) s->warp_ecap_mult *= 2;
   }
   return 0;
 }
@@ -699,6 +764,8 @@ extern "C" int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, in
   if (n) { CUDA_TRY(cudaMemcpyAsync(dst, p, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream)); CUDA_TRY(cudaStreamSynchronize(s->stream)); }
   return 0;
 }
+
+extern "C" int64_t shadow_sampler_last_redo_count(const shadow_sampler *s) { return s ? s->last_redo : -1; }
 
 // hook for ppr_push.cu
 int shadow_internal_graph(shadow_sampler *s, const uint32_t **indptr, const uint32_t **indices, uint32_t *N, uint32_t *E,

@@ -27,6 +27,11 @@ struct WsLayout {          // byte offsets of the per-CTA workspace (shared memo
   uint32_t bytes;
 };
 
+struct WarpLayout {        // byte offsets of the per-warp workspace of ppr_induce_warp_kernel (ppr_warp_kernel.cuh)
+  uint32_t nodes, rs, cp, rc, hkeys, ovf, rlo, rins, rbug;
+  uint32_t bytes;
+};
+
 struct SampleParams {
   // full graph (a1: GraphStruct, G.h:19-39)
   const uint32_t *indptr, *indices;
@@ -48,6 +53,7 @@ struct SampleParams {
   const uint32_t *ppr_sid;
   const float *ppr_sscore;
   const unsigned short *ppr_srank;
+  const uint2 *ppr_srow;             // {indptr[id], degree(id)} of every entry of the id-sorted rows (warp fast path)
   // random streams
   const uint32_t *rand_stream;       // glibc replay: pre-generated rand() outputs
   long long *rand_off;               // [num_subg+1] stream offset of each subgraph (written by the prepass)
@@ -68,6 +74,14 @@ struct SampleParams {
   unsigned long long *status_n;      // decoupled look-back words over the node counts: flag<<62 | value
   uint32_t *ticket;
   long long *totals;                 // [0]=nodes [1]=edge cursor (atomic) [2]=error bits
+  // warp fast path (ppr_warp_kernel.cuh) and its hand-over to this file's kernel
+  WarpLayout WL;
+  int w_ecap, w_hbuckets, w_hshift;
+  int *redo_list;                    // subgraphs the fast path could not hold on-chip; non-NULL in a redo launch of sample_induce_kernel
+  uint32_t *redo_count, *ticket2;
+  const unsigned short *w_cut;       // per-subgraph score-rank cut from ppr_count_kernel
+  unsigned char *w_scratch;          // staged-edge scratch of the warp fast path: one region per resident warp (global memory, lives in L2)
+  unsigned long long w_scratch_stride;
 };
 
 enum { ERR_WS_OVERFLOW = 1, ERR_OUT_OVERFLOW = 2 };
@@ -522,7 +536,7 @@ __device__ inline uint32_t scan_items_staged(const SampleParams &P, const Ws &ws
 // ------------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
-template <bool GWS>
+template <bool GWS, bool REDO = false>
 __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_induce_kernel(const SampleParams P) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __shared__ uint32_t s_warp_sums[33];
@@ -538,7 +552,12 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
 
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_p = (int)atomicAdd(P.ticket, 1u);
+    if (threadIdx.x == 0) {
+      if (REDO) {                                            // redo launch: only the subgraphs the warp fast path handed over
+        const uint32_t tk = atomicAdd(P.ticket2, 1u);
+        s_p = tk < *P.redo_count ? P.redo_list[tk] : P.num_subg;
+      } else s_p = (int)atomicAdd(P.ticket, 1u);
+    }
     __syncthreads();
     const int p = s_p;
     if (p >= P.num_subg) break;
@@ -577,7 +596,7 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
     }
     bool ws_overflow = (n < 0) || (n > P.ncap);
     if (ws_overflow) n = 0;
-    if (threadIdx.x == 0) lookback_publish(P.status_n, p, (unsigned long long)n);
+    if (!REDO && threadIdx.x == 0) lookback_publish(P.status_n, p, (unsigned long long)n);
     __syncthreads();
 
     // ---------------- B: orig -> sub hash, targets, row extents ----------------
@@ -697,7 +716,8 @@ __global__ void __launch_bounds__(SAMPLER_BLOCK, SAMPLER_MIN_BLOCKS) sample_indu
     // rows stay in subgraph order (look-back over n, resolved long after it was published); the edge block of a
     // subgraph is placed wherever the cursor stands -- no CTA ever waits for another one's row scan
     if (warp == 0) {
-      unsigned long long nb = lookback_resolve(P.status_n, p, (unsigned long long)n);
+      // redo launch: the fast path already resolved the look-back and reserved the rows (node_ptr[p])
+      unsigned long long nb = REDO ? (unsigned long long)P.node_ptr[p] : lookback_resolve(P.status_n, p, (unsigned long long)n);
       if (lane == 0) { s_base[0] = (long long)nb; s_base[1] = (long long)atomicAdd((unsigned long long *)&P.totals[1], (unsigned long long)m); }
     }
     __syncthreads();

@@ -281,3 +281,114 @@ def test_ppr_st_grid_vs_oracle():
     for k, thr, se, nr in itertools.product([1, 20, 30], [0, 0.01, 0.3], [False, True], [1, 2]):
         cfg = dict(method="ppr_st", k=str(k), threshold=str(thr), num_roots=str(nr), add_self_edge="true" if se else "false", include_target_conn="false")
         _oracle_vs_cuda(indptr, indices, rng.permutation(N - 2)[:70 * nr].astype(np.uint32), 48, 5, cfg, (), ppr_tables=tables)
+
+
+# ------------------------------------------------------------------------------------------------
+# single-root PPR fast path (one warp per subgraph, csrc/ppr_warp_kernel.cuh) and its hand-over to the generic kernel
+# ------------------------------------------------------------------------------------------------
+class _Env:
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        import os
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        for k, v in self.kw.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+
+    def __exit__(self, *a):
+        import os
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _ppr_tables(indptr, indices, k, eps=1e-5):
+    from oracle import oracle as O
+    N = indptr.size - 1
+    alln = np.arange(N, dtype=np.uint32)
+    nb, sc, ln = O.ppr_push(indptr, indices, alln, k, 0.85, eps, 8)
+    return O.ppr_rows_to_csr(N, alln, nb, sc, ln)
+
+
+@pytest.mark.parametrize("env", [dict(), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_WARP_BUCKET_MULT=2),
+                                 dict(SHADOW_WARP_ECAP_MULT=1, SHADOW_WARP_BUCKET_MULT=2), dict(SHADOW_NO_WARP_PPR=1)])
+def test_ppr_warp_path_and_redo_vs_oracle(env):
+    """the fast path, its staging-overflow and bucket-overflow hand-over (redo launch of the generic kernel) and the generic
+    kernel alone all reproduce the oracle bit for bit: bug-compatible and fixed mode, self edge on/off, thresholds, k=1"""
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(6000, 24, 13, self_loops=80)
+    N = indptr.size - 1
+    tables = _ppr_tables(indptr, indices, 160)
+    rng = np.random.default_rng(9)
+    with _Env(**env):
+        for k, thr, se, fixed in itertools.product([1, 40, 150], [0, 0.004], [False, True], [False, True]):
+            cfg = dict(method="ppr", k=str(k), threshold=str(thr), num_roots="1", add_self_edge="true" if se else "false",
+                       include_target_conn="false")
+            t = rng.permutation(N - 2)[:300].astype(np.uint32)
+            assert _oracle_vs_cuda(indptr, indices, t, 128, 2, cfg, (), ppr_tables=tables, fixed=fixed) == 300
+
+
+def test_ppr_warp_redo_is_exercised():
+    """with a staging area of just one scan stage every subgraph that needs a second stage goes through the redo launch (and still matches)"""
+    from shadow_gnn_b200.synth import small_parity_graph
+    PS = _product()
+    indptr, indices = small_parity_graph(6000, 24, 13)
+    N = indptr.size - 1
+    tables = _ppr_tables(indptr, indices, 100)
+    t = np.random.default_rng(2).permutation(N - 2)[:512].astype(np.uint32)
+    cfg = dict(method="ppr", k="100", threshold="0", num_roots="1", add_self_edge="false", include_target_conn="false")
+    out = {}
+    for name, env in (("warp", dict()), ("redo", dict(SHADOW_WARP_ECAP_MULT=0)), ("generic", dict(SHADOW_NO_WARP_PPR=1))):
+        with _Env(**env):
+            s = PS.ParallelSampler(indptr, indices, [], 512, 1, True, True, [], 1, "", "", "", 1)
+            s.set_ppr_tables(*tables)
+            s.shuffle_targets(t)
+            b = s.sample_to_device([cfg], [set()])[0]
+            out[name] = {f: getattr(b, f).cpu().numpy().copy() for f in ("node_ptr", "rowptr", "indices", "orig_node", "orig_edge", "target", "ppr")}
+            out[name]["redo"] = s.last_redo_count()
+    assert out["warp"]["redo"] < 512 and out["generic"]["redo"] == 0
+    assert out["redo"]["redo"] > 0, "a one-stage staging area should overflow for some subgraphs"
+    for name in ("warp", "redo"):
+        for f, v in out["generic"].items():
+            if f != "redo":
+                assert np.array_equal(out[name][f], v), (name, f)
+
+
+def test_ppr_warp_superbatch_equals_generic_kernel():
+    """larger scale (hub rows of a few thousand slots, 8192 subgraphs per launch): fast path == generic kernel, bit for bit,
+    on the canonical CSR; plus structural properties (every kept edge is the edge its orig_edge names)"""
+    import torch
+    from shadow_gnn_b200.synth import powerlaw_graph
+    PS = _product()
+    indptr, indices = powerlaw_graph(300_000, 9_000_000, 5, dmax=6000)
+    N = indptr.size - 1
+    P = 8192
+    t = np.random.default_rng(1).permutation(N)[:P].astype(np.uint32)
+    res = {}
+    for name, env in (("warp", dict()), ("generic", dict(SHADOW_NO_WARP_PPR=1))):
+        with _Env(**env):
+            s = PS.ParallelSampler(indptr, indices, [], P, 1, True, True, [], 1, "", "", "", 1)
+            s.preproc_ppr_approximate(t, 150, 0.85, 1e-5, "", "")
+            s.shuffle_targets(t)
+            for se in ("false", "true"):
+                cfg = dict(method="ppr", k="150", threshold="0", num_roots="1", add_self_edge=se, include_target_conn="false")
+                b = s.sample_to_device([cfg], [set()])[0]
+                res[name, se] = {f: getattr(b, f).clone() for f in ("node_ptr", "rowptr", "indices", "orig_node", "orig_edge", "target", "ppr")}
+                if name == "warp":
+                    res["redo", se] = s.last_redo_count()
+    for se in ("false", "true"):
+        for f, v in res["generic", se].items():
+            assert torch.equal(res["warp", se][f], v), (se, f)
+        assert res["redo", se] < P // 4
+    r = res["warp", "false"]
+    oe = r["orig_edge"].long() & 0xFFFFFFFF
+    on = r["orig_node"].long() & 0xFFFFFFFF
+    full_idx = torch.as_tensor(indices.astype(np.int64), device="cuda")
+    assert bool((full_idx[oe] == on[r["indices"].long()]).all())
+    assert bool((on[r["target"].long().ravel()] == torch.as_tensor(t.astype(np.int64), device="cuda")).all())
