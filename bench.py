@@ -462,7 +462,7 @@ def train_phase(ctx, steps, warmup):
     mine = 38       # fill, dropedge, row-normalise, 5 x (spmm + 2 act_norm) fwd, classifier norm, 5 spmm^T + 11 act_norm bwd, 3 optimizer launches
     return dict(value=n_all / (ms_all * 1e-3), unit="samples/s", ms_per_step=ms_all / steps, nparams=nparams,
                 graph_steps=getattr(trainer, "graph_steps", 0), eager_steps=getattr(trainer, "eager_steps", steps),
-                gpu_launches=mine * steps + 2 * (steps * B // args.superbatch_train + 1),
+                gpu_launches=mine * steps + 7 * (steps * B // args.superbatch_train + 1),      # per super-batch: count, scan, fast path, redo, gather, 2 x canonical CSR
                 e2e={"value": ne_all / e2e_all, "unit": "samples/s", "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": 4,
                      "note": "targets + labels from pinned host memory each step, loss read back each step"})
 
