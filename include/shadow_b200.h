@@ -171,6 +171,25 @@ int shadow_edge_vals_row_normalize(const int32_t *row_span, int32_t n, int32_t m
 /* adj_norm_sym (graph_utils.py:109-145): symmetric survival of `mask` (when dropedge > 0) then D^-1/2 A D^-1/2 */
 int shadow_edge_vals_sym_normalize(const int32_t *row_span, const int32_t *col, int32_t col_off, int32_t n, int32_t symmetric_survival,
                                    const float *mask, float *val, float *deg_scratch, void *cuda_stream);
+/* nn.Linear (layers.py:421,451-452,501-505,556,670; models.py:81) and its two backward products on the tensor cores, fp32 in / out:
+ *   C[M,N] (+)= op(A)[M,K] op(B)[K,N] (+ bias[N]), every product an error-compensated 3xTF32 sum accumulated in fp32 (fp32-accurate).
+ *   trans_a = 0: A[m][k] = A[m*lda + k];  1: A[m][k] = A[k*lda + m].      b_kn = 0: B[k][n] = B[n*ldb + k] (a Linear weight);  1: B[k][n] = B[k*ldb + n].
+ *   accumulate = 1: C += ... with fp32 atomics (C initialised by the caller; required for split_k > 1, which cuts K into split_k slices). */
+int shadow_gemm_tf32x3_f32(const float *A, int32_t lda, int32_t trans_a, const float *B, int32_t ldb, int32_t b_kn, float *C, int32_t ldc,
+                           const float *bias, int32_t M, int32_t N, int32_t K, int32_t accumulate, int32_t split_k, void *cuda_stream);
+/* The same three products on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA-staged operands; fp32 operands split
+ * into 3 bf16 terms in the kernel, nine-term products accumulated in fp32 => fp32-level accuracy).  csrc/gemm_umma.cu.  All leading
+ * dimensions, K and N must be multiples of 4 floats and the pointers 16-byte aligned (TMA); otherwise SHADOW_EINVAL and the caller uses
+ * shadow_gemm_tf32x3_f32.
+ *   fwd    Z[M,N]  = X[M,K] W[N,K]^T + bias[N]                 (bias may be NULL)
+ *   dgrad  dX[M,N] = dZ[M,K] W[K,N]
+ *   wgrad  part[l][N_out,K_in] = dZ[l*r:(l+1)*r, :N_out]^T X[l*r:(l+1)*r, :K_in],  l < slices, r = rows_per_slice (caller sums the slices) */
+int shadow_linear_umma_fwd_f32(const float *X, int64_t ldx, const float *W, int64_t ldw, const float *bias, float *Z, int64_t ldz, int32_t M, int32_t N,
+                               int32_t K, void *cuda_stream);
+int shadow_linear_umma_dgrad_f32(const float *dZ, int64_t lddz, const float *W, int64_t ldw, float *dX, int64_t lddx, int32_t M, int32_t N, int32_t K,
+                                 void *cuda_stream);
+int shadow_linear_umma_wgrad_f32(const float *dZ, int64_t lddz, const float *X, int64_t ldx, float *part, int32_t rows_per_slice, int32_t slices,
+                                 int32_t N_out, int32_t K_in, void *cuda_stream);
 /* torch.sparse.mm(adj, X) (layers.py:326-327,433,475,523): Y = beta*Y + A X ; backward dX += A^T dY (dX pre-zeroed by the caller) */
 int shadow_spmm_csr_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *X, float *Y,
                             int32_t n, int32_t F, float beta, void *cuda_stream);

@@ -2,11 +2,29 @@
 # Build libshadow_b200.so (C ABI declared in include/shadow_b200.h) for sm_100a, in-tree.
 #   OUT=<path>        output file (default ../libshadow_b200.so)
 #   EXTRA="-DWARP_U=4 ..."   kernel-variant macros (scripts/build_variants.sh)
+# The tcgen05 Linear (gemm_umma.cu) is assembled from the CUTLASS/CuTe templates vendored in the image; its three variants are compiled
+# as separate objects in parallel (about a minute each) and cached in csrc/_obj until gemm_umma.cu changes.
 set -e
 cd "$(dirname "$0")"
 OUT=${OUT:-../libshadow_b200.so}
 NVCC=${NVCC:-nvcc}
-SRCS="sampler.cu gather.cu $(ls ppr_push.cu layers.cu 2>/dev/null || true)"
-$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2 \
-  ${PTXAS_V:+-Xptxas -v} $EXTRA --shared -o $OUT $SRCS
+ARCH="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2"
+CUTLASS_INC=${CUTLASS_INC:-$(python -c "import flashinfer, os; print(os.path.join(os.path.dirname(flashinfer.__file__), 'data', 'cutlass', 'include'))")}
+mkdir -p _obj
+pids=""
+for v in 0 1 2; do
+  if [ ! -f _obj/gemm_umma_$v.o ] || [ gemm_umma.cu -nt _obj/gemm_umma_$v.o ]; then
+    $NVCC $ARCH --expt-relaxed-constexpr -diag-suppress 20012 -I"$CUTLASS_INC" -DUMMA_VARIANT=$v -c gemm_umma.cu -o _obj/gemm_umma_$v.o &
+    pids="$pids $!"
+  fi
+done
+SRCS="sampler.cu gather.cu ppr_push.cu layers.cu gemm.cu"
+$NVCC $ARCH ${PTXAS_V:+-Xptxas -v} $EXTRA -c sampler.cu -o _obj/sampler.o &
+pids="$pids $!"
+for f in gather ppr_push layers gemm; do
+  $NVCC $ARCH ${PTXAS_V:+-Xptxas -v} -c $f.cu -o _obj/$f.o &
+  pids="$pids $!"
+done
+for p in $pids; do wait $p; done
+$NVCC -gencode arch=compute_100a,code=sm_100a --shared -o $OUT _obj/sampler.o _obj/gather.o _obj/ppr_push.o _obj/layers.o _obj/gemm.o _obj/gemm_umma_0.o _obj/gemm_umma_1.o _obj/gemm_umma_2.o
 echo "built $(realpath $OUT)"

@@ -3,6 +3,7 @@
 Every op here fails loudly without the CUDA library / a CUDA tensor: there is no eager-PyTorch fallback.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -190,19 +191,88 @@ def _grad_of(p):
     return p.grad
 
 
+# The dense Linear runs on the tensor cores.  SHADOW_LINEAR selects the implementation (all three are parity-tested):
+#   "tf32x3" (default) the warp-level mma.sync kernel of csrc/gemm.cu: error-compensated 3xTF32, fp32-accurate; 13.6-22.9 us per
+#            4,832 x 256 x {100,256} product inside the captured step (the fp32 SIMT library GEMM: 13.8-26.5 us)
+#   "umma"   the tcgen05 / TMEM / TMA kernel assembled from CUTLASS templates (csrc/gemm_umma.cu, fp32 emulated with 9 bf16 products);
+#            shapes that miss the 16-byte TMA alignment (e.g. the 47-class classifier) take the kernel above.  Correct, but its
+#            load -> transform -> MMA -> epilogue pipeline is latency-bound at K = 256 with one tile per SM (24.8-32.7 us): not the default
+#   "cublas" the fp32 SIMT library GEMM (the former path, kept for A/B timing)
+_LINEAR = os.environ.get("SHADOW_LINEAR", "tf32x3")
+_TC_LINEAR = _LINEAR != "cublas"
 _SPLITK = 16
 
 
+def _al(*xs):
+    return all(int(x) % 4 == 0 for x in xs)
+
+
+def gemm(A, B, *, trans_a=False, b_kn=False, bias=None, out=None, accumulate=False, split_k=1):
+    """C (+)= op(A) op(B) (+ bias) on the tensor cores (include/shadow_b200.h: shadow_gemm_tf32x3_f32).
+    trans_a: A is stored [K, M];  b_kn: B is stored [K, N] (default: [N, K], a Linear weight)."""
+    A = _req(A.contiguous(), torch.float32, "gemm A")
+    B = _req(B.contiguous(), torch.float32, "gemm B")
+    K, M = (A.shape if trans_a else (A.shape[1], A.shape[0]))
+    N = B.shape[1] if b_kn else B.shape[0]
+    assert (B.shape[0] if b_kn else B.shape[1]) == K, "gemm: inner dimensions differ"
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    check(lib.shadow_gemm_tf32x3_f32(_p(A), A.stride(0), int(trans_a), _p(B), B.stride(0), int(b_kn), _p(out), out.stride(0),
+                                     _p(bias.contiguous()) if bias is not None else None, M, N, K, int(accumulate), int(split_k), _stream(A)))
+    return out
+
+
+def _linear_fwd(x, w, b):
+    """x W^T + b"""
+    if not _TC_LINEAR:
+        return torch.addmm(b.detach(), x, w.detach().t()) if b is not None else x @ w.detach().t()
+    w = w.detach()
+    b = b.detach() if b is not None else None
+    M, K = x.shape
+    N = w.shape[0]
+    if _LINEAR == "umma" and M > 0 and _al(K, N) and w.is_contiguous() and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0 and \
+            (b is None or (b.is_contiguous() and b.data_ptr() % 16 == 0)):
+        Z = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        check(lib.shadow_linear_umma_fwd_f32(_p(x), K, _p(w), K, _p(b), _p(Z), N, M, N, K, _stream(x)))
+        return Z
+    return gemm(x, w, bias=b)
+
+
+def _linear_dgrad(dZ, w):
+    """dZ W"""
+    if not _TC_LINEAR:
+        return dZ @ w.detach()
+    w = w.detach()
+    M, K = dZ.shape              # reduction over the Linear's output features
+    N = w.shape[1]
+    if _LINEAR == "umma" and M > 0 and _al(K, N) and w.is_contiguous() and dZ.is_contiguous() and dZ.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0:
+        dX = torch.empty((M, N), dtype=torch.float32, device=dZ.device)
+        check(lib.shadow_linear_umma_dgrad_f32(_p(dZ), K, _p(w), N, _p(dX), N, M, N, K, _stream(dZ)))
+        return dX
+    return gemm(dZ, w, b_kn=True)
+
+
 def _accum_wgrad(w, dZ, x):
-    """W.grad += dZ^T x.  The product is [D_out, n] x [n, D_in] with n ~ 4,800 and a 256 x 256 result: a plain GEMM runs on 16 CTAs,
-    so it is split along n into 16 batched GEMMs whose partial results are summed (same flops, ~5x less time on 148 SMs)."""
+    """W.grad += dZ^T x.  The product is [D_out, n] x [n, D_in] with n ~ 4,800 and a 256 x 256 result: a handful of output tiles, so it is
+    split along n (tcgen05 path: 16 batched slices + a sum; warp-MMA path: ~160 rows per CTA, fp32 atomics into the gradient)."""
     g = _grad_of(w)
     n = x.shape[0]
-    if n % _SPLITK == 0 and n >= 64 * _SPLITK:
-        part = torch.bmm(dZ.view(_SPLITK, n // _SPLITK, dZ.shape[1]).transpose(1, 2), x.view(_SPLITK, n // _SPLITK, x.shape[1]))
+    if not _TC_LINEAR:
+        if n % _SPLITK == 0 and n >= 64 * _SPLITK:
+            part = torch.bmm(dZ.view(_SPLITK, n // _SPLITK, dZ.shape[1]).transpose(1, 2), x.view(_SPLITK, n // _SPLITK, x.shape[1]))
+            g.add_(part.sum(0))
+        else:
+            g.addmm_(dZ.t(), x)
+        return
+    N_out, K_in = dZ.shape[1], x.shape[1]
+    if _LINEAR == "umma" and n % _SPLITK == 0 and n >= 64 * _SPLITK and _al(N_out, K_in) and dZ.is_contiguous() and x.is_contiguous() and \
+            dZ.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0:
+        part = torch.empty((_SPLITK, N_out, K_in), dtype=torch.float32, device=x.device)
+        check(lib.shadow_linear_umma_wgrad_f32(_p(dZ), N_out, _p(x), K_in, _p(part), n // _SPLITK, _SPLITK, N_out, K_in, _stream(x)))
         g.add_(part.sum(0))
     else:
-        g.addmm_(dZ.t(), x)
+        gemm(dZ, x, trans_a=True, b_kn=True, out=g, accumulate=True, split_k=max(1, n // 160))
 
 
 def _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm, out=None, accumulate=False):
@@ -235,7 +305,7 @@ class _LinearActNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, lin_w, lin_b, scale, offset, idx, act, do_norm):
         x = _req(x.contiguous(), torch.float32, "linear input")
-        Z = torch.addmm(lin_b.detach(), x, lin_w.detach().t())
+        Z = _linear_fwd(x, lin_w, lin_b)
         out, mean, rstd = _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm)
         ctx.save_for_backward(x, Z, mean, rstd)
         ctx.p = (lin_w, lin_b, scale, offset, idx, act, do_norm)
@@ -247,7 +317,7 @@ class _LinearActNorm(torch.autograd.Function):
         lin_w, lin_b, scale, offset, idx, act, do_norm = ctx.p
         dZ = _act_norm_bwd_raw(dOut.contiguous(), Z, scale, offset, lin_b, idx, mean, rstd, act, do_norm)
         _accum_wgrad(lin_w, dZ, x)
-        dX = dZ @ lin_w.detach() if ctx.needs_input_grad[0] else None
+        dX = _linear_dgrad(dZ, lin_w) if ctx.needs_input_grad[0] else None
         return dX, None, None, None, None, None, None, None
 
 
@@ -265,8 +335,8 @@ class _SageLayer(torch.autograd.Function):
         x = _req(x.contiguous(), torch.float32, "sage input")
         agg = torch.empty_like(x)
         check(lib.shadow_spmm_csr_fwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(x), _p(agg), adj.n, x.shape[1], 0.0, _stream(x)))
-        Zs = torch.addmm(bs.detach(), x, ws.detach().t())
-        Zn = torch.addmm(bn.detach(), agg, wn.detach().t())
+        Zs = _linear_fwd(x, ws, bs)
+        Zn = _linear_fwd(agg, wn, bn)
         out, mean_s, rstd_s = _act_norm_fwd_raw(Zs, scale, offset, 0, act, do_norm)
         _, mean_n, rstd_n = _act_norm_fwd_raw(Zn, scale, offset, 1, act, do_norm, out=out, accumulate=True)
         ctx.save_for_backward(x, agg, Zs, Zn, mean_s, rstd_s, mean_n, rstd_n)
@@ -284,8 +354,8 @@ class _SageLayer(torch.autograd.Function):
         _accum_wgrad(wn, dZn, agg)
         if not ctx.needs_input_grad[0]:
             return (None,) * 10
-        dX = dZs @ ws.detach()
-        dAgg = dZn @ wn.detach()
+        dX = _linear_dgrad(dZs, ws)
+        dAgg = _linear_dgrad(dZn, wn)
         check(lib.shadow_spmm_csr_bwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(dAgg), _p(dX), adj.n, dX.shape[1], _stream(dX)))
         return (dX,) + (None,) * 9
 

@@ -282,3 +282,62 @@ def test_aug_onehots_match_reference_formulas():
     d = drnl.astype(np.int64).copy(); d[d >= 255] = 0; d[d > 25] = 0
     want = np.zeros((d.size, 26)); want[np.arange(d.size), d] = 1
     assert np.array_equal(MB.drnl2onehot(torch.as_tensor(drnl.view(np.int32)).cuda(), 26).cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("M,N,K", [(4832, 256, 256), (4832, 256, 100), (77, 47, 256), (1, 1, 1), (130, 70, 33), (64, 64, 32), (65, 129, 257)])
+def test_tensor_core_linear_products_match_fp64(M, N, K):
+    """shadow_gemm_tf32x3_f32 (csrc/gemm.cu): the three products of nn.Linear -- forward x W^T + b, dgrad dZ W, wgrad dZ^T x (split along
+    the batch, atomics) -- are fp32-accurate (3xTF32 error compensation), checked against an fp64 product.  Tolerance: 2e-5 of the
+    row-by-column magnitude (one plain TF32 pass would be ~5e-4)."""
+    from shadow_gnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g)
+    b = torch.randn(N, device="cuda", generator=g)
+    dz = torch.randn(M, N, device="cuda", generator=g)
+
+    def check(got, want64, a64, b64, what):
+        scale = (a64.abs() @ b64.abs()).clamp_min(1e-30)
+        err = ((got.double() - want64).abs() / scale).max().item()
+        assert err < 2e-5, f"{what}: scaled error {err:.3e}"
+    xd, wd, dzd = x.double(), w.double(), dz.double()
+    check(ops.gemm(x, w, bias=b) - b, xd @ wd.t(), xd, wd.t(), "forward")
+    check(ops.gemm(x, w), xd @ wd.t(), xd, wd.t(), "forward (no bias)")
+    check(ops.gemm(dz, w, b_kn=True), dzd @ wd, dzd, wd, "dgrad")
+    for split in (1, max(1, M // 160), 7):
+        gacc = torch.zeros(N, K, device="cuda")
+        ops.gemm(dz, x, trans_a=True, b_kn=True, out=gacc, accumulate=True, split_k=split)
+        check(gacc, dzd.t() @ xd, dzd.t().abs(), xd.abs(), f"wgrad split {split}")
+
+
+@pytest.mark.parametrize("M,N,K", [(4832, 256, 256), (4832, 256, 100), (672, 256, 256), (33, 64, 128), (1024, 48, 256)])
+def test_tcgen05_linear_products_match_fp64(M, N, K):
+    """csrc/gemm_umma.cu (tcgen05 + TMEM + TMA, fp32 emulated by 9 bf16 products): forward incl. the bias (C operand with row stride 0),
+    dgrad and the batched wgrad slices against fp64; the emulation keeps ~fp32 accuracy (tolerance 2e-5 of the |a|.|b| magnitude)"""
+    import ctypes as C
+    from shadow_gnn_b200._lib import lib, check as chk
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g)
+    b = torch.randn(N, device="cuda", generator=g)
+    dz = torch.randn(M, N, device="cuda", generator=g)
+
+    def close(got, want64, mag, what):
+        err = ((got.double() - want64).abs() / mag.clamp_min(1e-30)).max().item()
+        assert err < 2e-5, f"{what}: scaled error {err:.3e}"
+    xd, wd, dzd = x.double(), w.double(), dz.double()
+    Z = torch.full((M, N), float("nan"), device="cuda")
+    chk(lib.shadow_linear_umma_fwd_f32(p(x), K, p(w), K, p(b), p(Z), N, M, N, K, st))
+    close(Z, xd @ wd.t() + b.double(), xd.abs() @ wd.abs().t() + b.double().abs(), "forward + bias")
+    chk(lib.shadow_linear_umma_fwd_f32(p(x), K, p(w), K, None, p(Z), N, M, N, K, st))
+    close(Z, xd @ wd.t(), xd.abs() @ wd.abs().t(), "forward")
+    dX = torch.full((M, K), float("nan"), device="cuda")
+    chk(lib.shadow_linear_umma_dgrad_f32(p(dz), N, p(w), K, p(dX), K, M, K, N, st))
+    close(dX, dzd @ wd, dzd.abs() @ wd.abs(), "dgrad")
+    if M % 16 == 0:
+        part = torch.full((16, N, K), float("nan"), device="cuda")
+        chk(lib.shadow_linear_umma_wgrad_f32(p(dz), N, p(x), K, p(part), M // 16, 16, N, K, st))
+        close(part.sum(0), dzd.t() @ xd, dzd.abs().t() @ xd.abs(), "wgrad")
+    torch.cuda.synchronize()
