@@ -177,6 +177,10 @@ int shadow_edge_vals_sym_normalize(const int32_t *row_span, const int32_t *col, 
  *   accumulate = 1: C += ... with fp32 atomics (C initialised by the caller; required for split_k > 1, which cuts K into split_k slices). */
 int shadow_gemm_tf32x3_f32(const float *A, int32_t lda, int32_t trans_a, const float *B, int32_t ldb, int32_t b_kn, float *C, int32_t ldc,
                            const float *bias, int32_t M, int32_t N, int32_t K, int32_t accumulate, int32_t split_k, void *cuda_stream);
+/* two products of identical shape and layout in one launch (the self and the neighbour branch of a GraphSAGE layer, layers.py:474-483) */
+int shadow_gemm_tf32x3_pair_f32(const float *A0, const float *A1, int32_t lda, int32_t trans_a, const float *B0, const float *B1, int32_t ldb,
+                                int32_t b_kn, float *C0, float *C1, int32_t ldc, const float *bias0, const float *bias1, int32_t M, int32_t N,
+                                int32_t K, int32_t accumulate, int32_t split_k, void *cuda_stream);
 /* The same three products on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA-staged operands; fp32 operands split
  * into 3 bf16 terms in the kernel, nine-term products accumulated in fp32 => fp32-level accuracy).  csrc/gemm_umma.cu.  All leading
  * dimensions, K and N must be multiples of 4 floats and the pointers 16-byte aligned (TMA); otherwise SHADOW_EINVAL and the caller uses

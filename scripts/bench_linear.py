@@ -15,7 +15,9 @@ for K in (256, 100):
     w.grad = torch.zeros_like(w)
     for mode in ("umma", "tf32x3", "cublas"):
         ops._LINEAR = mode; ops._TC_LINEAR = mode != "cublas"
-        fns = {"fwd": lambda: ops._linear_fwd(x, w, b), "dgrad": lambda: ops._linear_dgrad(dz, w), "wgrad": lambda: ops._accum_wgrad(w, dz, x)}
+        fns = {"fwd": lambda: ops._linear_fwd(x, w, b), "dgrad": lambda: ops._linear_dgrad(dz, w), "wgrad": lambda: ops._accum_wgrad(w, dz, x),
+               "fwd2": lambda: ops._linear_fwd_pair(x, w, b, x, w, b), "dgrad2": lambda: ops._linear_dgrad_pair(dz, w, dz, w),
+               "wgrad2": lambda: ops._accum_wgrad_pair(w, dz, x, w, dz, x)}
         for name, fn in fns.items():
             for _ in range(5):
                 fn()

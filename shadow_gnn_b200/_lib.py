@@ -49,7 +49,7 @@ SYMBOLS = [
     "shadow_edge_vals_fill", "shadow_edge_vals_dropedge", "shadow_edge_vals_row_normalize", "shadow_edge_vals_sym_normalize",
     "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32",
     "shadow_gat_fwd_f32", "shadow_gat_bwd_f32", "shadow_segment_pool_fwd_f32", "shadow_segment_pool_bwd_f32",
-    "shadow_adam_clip_step_f32", "shadow_gemm_tf32x3_f32",
+    "shadow_adam_clip_step_f32", "shadow_gemm_tf32x3_f32", "shadow_gemm_tf32x3_pair_f32",
     "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32",
 ]
 
@@ -98,6 +98,7 @@ lib.shadow_gat_bwd_f32.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
 lib.shadow_segment_pool_fwd_f32.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]
 lib.shadow_segment_pool_bwd_f32.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]
 lib.shadow_gemm_tf32x3_f32.argtypes = [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
+lib.shadow_gemm_tf32x3_pair_f32.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_fwd_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_dgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_wgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]

@@ -111,16 +111,24 @@ struct TileB {
   }
 };
 
+// Two products of the same shape can share one launch (GraphSAGE's self / neighbour branch: twice the resident warps for the MMA pipe,
+// half the launches): problem = blockIdx.z % nprob, k-slice = blockIdx.z / nprob.
+struct GemmPair { const float *A[2]; const float *B[2]; float *C[2]; const float *bias[2]; int nprob; };
+
 template <bool TA, bool BKN, bool VEC>
-__global__ void __launch_bounds__(128) gemm_tf32x3_kernel(const float *__restrict__ A, const int lda, const float *__restrict__ B, const int ldb,
-                                                          float *__restrict__ C, const int ldc, const float *__restrict__ bias, const int M,
+__global__ void __launch_bounds__(128) gemm_tf32x3_kernel(const GemmPair P, const int lda, const int ldb, const int ldc, const int M,
                                                           const int N, const int K, const int k_per_split, const int atomic_out) {
+  const int prob = blockIdx.z % P.nprob, zsplit = blockIdx.z / P.nprob;
+  const float *__restrict__ A = P.A[prob];
+  const float *__restrict__ B = P.B[prob];
+  float *__restrict__ C = P.C[prob];
+  const float *__restrict__ bias = P.bias[prob];
   __shared__ __align__(16) float As[GB_M][GB_K + 4];                                       // [m][k]
   __shared__ __align__(16) float Bs[BKN ? GB_K : GB_N][BKN ? GB_N + 8 : GB_K + 4];          // [k][n] or [n][k]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   const int m0 = blockIdx.x * GB_M, n0 = blockIdx.y * GB_N;
-  const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+  const int kb = zsplit * k_per_split, ke = min(K, kb + k_per_split);
   float acc[2][4][4];
 #pragma unroll
   for (int i = 0; i < 2; i++)
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(128) gemm_tf32x3_kernel(const float *__restric
     __syncthreads();
   }
   // ---- epilogue: accumulator (16 x 8): c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1) ----
-  const bool add_bias = bias != nullptr && blockIdx.z == 0;
+  const bool add_bias = bias != nullptr && zsplit == 0;
 #pragma unroll
   for (int mi = 0; mi < 2; mi++)
 #pragma unroll
@@ -192,33 +200,49 @@ __global__ void __launch_bounds__(128) gemm_tf32x3_kernel(const float *__restric
 }
 
 template <bool TA, bool BKN>
-static void launch_gemm(bool vec, dim3 grid, cudaStream_t st, const float *A, int lda, const float *B, int ldb, float *C, int ldc, const float *bias, int M,
-                        int N, int K, int kps, int atomic_out) {
-  if (vec) gemm_tf32x3_kernel<TA, BKN, true><<<grid, 128, 0, st>>>(A, lda, B, ldb, C, ldc, bias, M, N, K, kps, atomic_out);
-  else gemm_tf32x3_kernel<TA, BKN, false><<<grid, 128, 0, st>>>(A, lda, B, ldb, C, ldc, bias, M, N, K, kps, atomic_out);
+static void launch_gemm(bool vec, dim3 grid, cudaStream_t st, const GemmPair &P, int lda, int ldb, int ldc, int M, int N, int K, int kps, int atomic_out) {
+  if (vec) gemm_tf32x3_kernel<TA, BKN, true><<<grid, 128, 0, st>>>(P, lda, ldb, ldc, M, N, K, kps, atomic_out);
+  else gemm_tf32x3_kernel<TA, BKN, false><<<grid, 128, 0, st>>>(P, lda, ldb, ldc, M, N, K, kps, atomic_out);
 }
 
-extern "C" int shadow_gemm_tf32x3_f32(const float *A, int32_t lda, int32_t trans_a, const float *B, int32_t ldb, int32_t b_kn, float *C, int32_t ldc,
-                                      const float *bias, int32_t M, int32_t N, int32_t K, int32_t accumulate, int32_t split_k, void *cuda_stream) {
-  if (!A || !B || !C || M < 0 || N < 0 || K < 0) FAIL(SHADOW_EINVAL, "shadow_gemm_tf32x3_f32: bad argument");
+static int gemm_dispatch(const GemmPair &P, int32_t lda, int32_t trans_a, int32_t ldb, int32_t b_kn, int32_t ldc, int32_t M, int32_t N, int32_t K,
+                         int32_t accumulate, int32_t split_k, void *cuda_stream) {
+  for (int i = 0; i < P.nprob; i++)
+    if (!P.A[i] || !P.B[i] || !P.C[i]) FAIL(SHADOW_EINVAL, "shadow_gemm_tf32x3: NULL operand");
+  if (M < 0 || N < 0 || K < 0) FAIL(SHADOW_EINVAL, "shadow_gemm_tf32x3: negative dimension");
   if (M == 0 || N == 0) return 0;
   int splits = std::max(1, split_k);
   int kps = ((K + splits - 1) / splits + GB_K - 1) / GB_K * GB_K;
   if (kps <= 0) kps = GB_K;
   splits = std::max(1, (K + kps - 1) / kps);
-  if (splits > 1 && !accumulate) FAIL(SHADOW_EINVAL, "shadow_gemm_tf32x3_f32: split_k > 1 needs accumulate = 1 (C += ..., C initialised by the caller)");
-  const dim3 grid((M + GB_M - 1) / GB_M, (N + GB_N - 1) / GB_N, splits);
+  if (splits > 1 && !accumulate) FAIL(SHADOW_EINVAL, "shadow_gemm_tf32x3: split_k > 1 needs accumulate = 1 (C += ..., C initialised by the caller)");
+  const dim3 grid((M + GB_M - 1) / GB_M, (N + GB_N - 1) / GB_N, splits * P.nprob);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int atomic_out = accumulate ? 1 : 0;
   // 128-bit tile moves need: 16-byte aligned bases, leading dimensions multiples of 4, and the contiguous extent of each operand
   // (K for row-major A / weight-layout B, M for transposed A, N for [K][N] B) a multiple of 4; C rows even for the paired stores
   auto al16 = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
-  const bool vec = al16(A) && al16(B) && al16(C) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 2 == 0) && ((trans_a ? M : K) % 4 == 0) &&
-                   ((b_kn ? N : K) % 4 == 0) && (kps % 4 == 0);
-  if (!trans_a && !b_kn) launch_gemm<false, false>(vec, grid, st, A, lda, B, ldb, C, ldc, bias, M, N, K, kps, atomic_out);
-  else if (!trans_a && b_kn) launch_gemm<false, true>(vec, grid, st, A, lda, B, ldb, C, ldc, bias, M, N, K, kps, atomic_out);
-  else if (trans_a && b_kn) launch_gemm<true, true>(vec, grid, st, A, lda, B, ldb, C, ldc, bias, M, N, K, kps, atomic_out);
-  else launch_gemm<true, false>(vec, grid, st, A, lda, B, ldb, C, ldc, bias, M, N, K, kps, atomic_out);
+  bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 2 == 0) && ((trans_a ? M : K) % 4 == 0) && ((b_kn ? N : K) % 4 == 0) && (kps % 4 == 0);
+  for (int i = 0; i < P.nprob; i++) vec = vec && al16(P.A[i]) && al16(P.B[i]) && al16(P.C[i]);
+  if (!trans_a && !b_kn) launch_gemm<false, false>(vec, grid, st, P, lda, ldb, ldc, M, N, K, kps, atomic_out);
+  else if (!trans_a && b_kn) launch_gemm<false, true>(vec, grid, st, P, lda, ldb, ldc, M, N, K, kps, atomic_out);
+  else if (trans_a && b_kn) launch_gemm<true, true>(vec, grid, st, P, lda, ldb, ldc, M, N, K, kps, atomic_out);
+  else launch_gemm<true, false>(vec, grid, st, P, lda, ldb, ldc, M, N, K, kps, atomic_out);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+extern "C" int shadow_gemm_tf32x3_f32(const float *A, int32_t lda, int32_t trans_a, const float *B, int32_t ldb, int32_t b_kn, float *C, int32_t ldc,
+                                      const float *bias, int32_t M, int32_t N, int32_t K, int32_t accumulate, int32_t split_k, void *cuda_stream) {
+  GemmPair P;
+  P.A[0] = P.A[1] = A; P.B[0] = P.B[1] = B; P.C[0] = P.C[1] = C; P.bias[0] = P.bias[1] = bias; P.nprob = 1;
+  return gemm_dispatch(P, lda, trans_a, ldb, b_kn, ldc, M, N, K, accumulate, split_k, cuda_stream);
+}
+
+extern "C" int shadow_gemm_tf32x3_pair_f32(const float *A0, const float *A1, int32_t lda, int32_t trans_a, const float *B0, const float *B1, int32_t ldb,
+                                           int32_t b_kn, float *C0, float *C1, int32_t ldc, const float *bias0, const float *bias1, int32_t M, int32_t N,
+                                           int32_t K, int32_t accumulate, int32_t split_k, void *cuda_stream) {
+  GemmPair P;
+  P.A[0] = A0; P.A[1] = A1; P.B[0] = B0; P.B[1] = B1; P.C[0] = C0; P.C[1] = C1; P.bias[0] = bias0; P.bias[1] = bias1; P.nprob = 2;
+  return gemm_dispatch(P, lda, trans_a, ldb, b_kn, ldc, M, N, K, accumulate, split_k, cuda_stream);
 }

@@ -275,6 +275,47 @@ def _accum_wgrad(w, dZ, x):
         gemm(dZ, x, trans_a=True, b_kn=True, out=g, accumulate=True, split_k=max(1, n // 160))
 
 
+def _pair_ok(*ts):
+    return _LINEAR == "tf32x3" and all(t.is_contiguous() and t.dtype == torch.float32 for t in ts)
+
+
+def _linear_fwd_pair(x0, w0, b0, x1, w1, b1):
+    """(x0 W0^T + b0, x1 W1^T + b1), one launch when both products have the same shape"""
+    if _pair_ok(x0, x1, w0, w1) and x0.shape == x1.shape and w0.shape == w1.shape:
+        w0, w1, b0, b1 = w0.detach(), w1.detach(), b0.detach(), b1.detach()
+        M, K = x0.shape
+        N = w0.shape[0]
+        Z0 = torch.empty((M, N), dtype=torch.float32, device=x0.device)
+        Z1 = torch.empty_like(Z0)
+        check(lib.shadow_gemm_tf32x3_pair_f32(_p(x0), _p(x1), K, 0, _p(w0), _p(w1), K, 0, _p(Z0), _p(Z1), N, _p(b0), _p(b1), M, N, K, 0, 1, _stream(x0)))
+        return Z0, Z1
+    return _linear_fwd(x0, w0, b0), _linear_fwd(x1, w1, b1)
+
+
+def _linear_dgrad_pair(dZ0, w0, dZ1, w1):
+    if _pair_ok(dZ0, dZ1, w0, w1) and dZ0.shape == dZ1.shape and w0.shape == w1.shape:
+        w0, w1 = w0.detach(), w1.detach()
+        M, K = dZ0.shape
+        N = w0.shape[1]
+        d0 = torch.empty((M, N), dtype=torch.float32, device=dZ0.device)
+        d1 = torch.empty_like(d0)
+        check(lib.shadow_gemm_tf32x3_pair_f32(_p(dZ0), _p(dZ1), K, 0, _p(w0), _p(w1), N, 1, _p(d0), _p(d1), N, None, None, M, N, K, 0, 1, _stream(dZ0)))
+        return d0, d1
+    return _linear_dgrad(dZ0, w0), _linear_dgrad(dZ1, w1)
+
+
+def _accum_wgrad_pair(w0, dZ0, x0, w1, dZ1, x1):
+    if _pair_ok(dZ0, dZ1, x0, x1) and dZ0.shape == dZ1.shape and x0.shape == x1.shape:
+        g0, g1 = _grad_of(w0), _grad_of(w1)
+        n, N_out, K_in = x0.shape[0], dZ0.shape[1], x0.shape[1]
+        if g0.is_contiguous() and g1.is_contiguous():
+            check(lib.shadow_gemm_tf32x3_pair_f32(_p(dZ0), _p(dZ1), N_out, 1, _p(x0), _p(x1), K_in, 1, _p(g0), _p(g1), K_in, None, None, N_out, K_in, n, 1,
+                                                  max(1, n // 160), _stream(x0)))
+            return
+    _accum_wgrad(w0, dZ0, x0)
+    _accum_wgrad(w1, dZ1, x1)
+
+
 def _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm, out=None, accumulate=False):
     n, D = Z.shape
     out = torch.empty_like(Z) if out is None else out
@@ -335,8 +376,7 @@ class _SageLayer(torch.autograd.Function):
         x = _req(x.contiguous(), torch.float32, "sage input")
         agg = torch.empty_like(x)
         check(lib.shadow_spmm_csr_fwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(x), _p(agg), adj.n, x.shape[1], 0.0, _stream(x)))
-        Zs = _linear_fwd(x, ws, bs)
-        Zn = _linear_fwd(agg, wn, bn)
+        Zs, Zn = _linear_fwd_pair(x, ws, bs, agg, wn, bn)
         out, mean_s, rstd_s = _act_norm_fwd_raw(Zs, scale, offset, 0, act, do_norm)
         _, mean_n, rstd_n = _act_norm_fwd_raw(Zn, scale, offset, 1, act, do_norm, out=out, accumulate=True)
         ctx.save_for_backward(x, agg, Zs, Zn, mean_s, rstd_s, mean_n, rstd_n)
@@ -350,12 +390,10 @@ class _SageLayer(torch.autograd.Function):
         dOut = dOut.contiguous()
         dZs = _act_norm_bwd_raw(dOut, Zs, scale, offset, bs, 0, mean_s, rstd_s, act, do_norm)
         dZn = _act_norm_bwd_raw(dOut, Zn, scale, offset, bn, 1, mean_n, rstd_n, act, do_norm)
-        _accum_wgrad(ws, dZs, x)
-        _accum_wgrad(wn, dZn, agg)
+        _accum_wgrad_pair(ws, dZs, x, wn, dZn, agg)
         if not ctx.needs_input_grad[0]:
             return (None,) * 10
-        dX = _linear_dgrad(dZs, ws)
-        dAgg = _linear_dgrad(dZn, wn)
+        dX, dAgg = _linear_dgrad_pair(dZs, ws, dZn, wn)
         check(lib.shadow_spmm_csr_bwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(dAgg), _p(dX), adj.n, dX.shape[1], _stream(dX)))
         return (dX,) + (None,) * 9
 

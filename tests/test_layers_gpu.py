@@ -341,3 +341,29 @@ def test_tcgen05_linear_products_match_fp64(M, N, K):
         chk(lib.shadow_linear_umma_wgrad_f32(p(dz), N, p(x), K, p(part), M // 16, 16, N, K, st))
         close(part.sum(0), dzd.t() @ xd, dzd.abs().t() @ xd.abs(), "wgrad")
     torch.cuda.synchronize()
+
+
+def test_tensor_core_linear_pair_launch_matches_single_launches():
+    """the two-problems-per-launch variant (GraphSAGE self / neighbour branch) gives bit-identical results to two single launches
+    for forward and dgrad, and the same sums (up to atomics order) for wgrad"""
+    from shadow_gnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 1000, 256, 100
+    x0, x1 = torch.randn(M, K, device="cuda", generator=g), torch.randn(M, K, device="cuda", generator=g)
+    w0, w1 = torch.randn(N, K, device="cuda", generator=g), torch.randn(N, K, device="cuda", generator=g)
+    b0, b1 = torch.randn(N, device="cuda", generator=g), torch.randn(N, device="cuda", generator=g)
+    d0, d1 = torch.randn(M, N, device="cuda", generator=g), torch.randn(M, N, device="cuda", generator=g)
+    old = ops._LINEAR
+    ops._LINEAR = "tf32x3"
+    try:
+        Z0, Z1 = ops._linear_fwd_pair(x0, w0, b0, x1, w1, b1)
+        assert torch.equal(Z0, ops.gemm(x0, w0, bias=b0)) and torch.equal(Z1, ops.gemm(x1, w1, bias=b1))
+        e0, e1 = ops._linear_dgrad_pair(d0, w0, d1, w1)
+        assert torch.equal(e0, ops.gemm(d0, w0, b_kn=True)) and torch.equal(e1, ops.gemm(d1, w1, b_kn=True))
+        p0, p1 = torch.nn.Parameter(w0.clone()), torch.nn.Parameter(w1.clone())
+        ops._accum_wgrad_pair(p0, d0, x0, p1, d1, x1)
+        for got, d, x in ((p0.grad, d0, x0), (p1.grad, d1, x1)):
+            want = d.double().t() @ x.double()
+            assert ((got.double() - want).abs() / (d.double().abs().t() @ x.double().abs())).max().item() < 2e-5
+    finally:
+        ops._LINEAR = old
