@@ -338,7 +338,11 @@ def sampler_phase(ctx, steps, warmup):
     ctx.barrier()
     ms = ev0.elapsed_time(ev1)
     k_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
-    a1, a2 = algorithmic_bytes(last, ctx.deg, F, last.num_subg)      # last step's batch stands for the average step
+    # algorithmic bytes: the last step's batch gives the bytes per subgraph (the roots differ from launch to launch, their distribution does
+    # not); a launch of the timed region processed nsub / steps subgraphs on average (the last launch of an epoch is shorter)
+    a1_last, a2_last = algorithmic_bytes(last, ctx.deg, F, last.num_subg)
+    units = nsub / steps
+    a1, a2 = a1_last / last.num_subg * units, a2_last / last.num_subg * units
     avg_n, avg_e = last.total_nodes / last.num_subg, last.total_edges / last.num_subg
     log("sampler phase: timed region done", ms)
     # e2e through the reference-facing boundary with HOST buffers: roots from pinned host memory, every array that
@@ -377,8 +381,8 @@ def sampler_phase(ctx, steps, warmup):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        if tj.get("units_per_launch") == last.num_subg:
-            traffic = tj.get("ppr_induce_warp_kernel_dram_bytes_per_launch")
+        if tj.get("units_per_launch"):      # ncu capture of one launch of `units_per_launch` subgraphs, scaled to this run's average launch
+            traffic = int(tj.get("ppr_induce_warp_kernel_dram_bytes_per_launch") * units / tj["units_per_launch"])
     return dict(
         value=n_all / (ms_all * 1e-3), unit="subgraphs/s", ms_per_step=ms_all / steps, steps=steps, superbatch=P, per_gpu_targets=int(roots_host.size),
         avg_nodes_per_subgraph=avg_n, avg_edges_per_subgraph=avg_e, ppr_push_setup_s=t_ppr, gpu_launches=5 * steps,
@@ -386,10 +390,10 @@ def sampler_phase(ctx, steps, warmup):
         e2e={"value": ne_all / e2e_all, "unit": "subgraphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
              "note": "roots from pinned host memory; CSR, node ids, edge ids, targets, ppr copied back to pinned host memory; features stay in HBM"},
         roofline={"kernel": "ppr_induce_warp_kernel", "bound": "hbm", "achieved": (a1 / 1e9) / (k_ms * 1e-3), "peak": peak, "unit": "GB/s",
-                  "frac": (a1 / 1e9) / (k_ms * 1e-3) / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": a1,
-                  "kernel_ms": k_ms, "units_per_launch": last.num_subg,
+                  "frac": (a1 / 1e9) / (k_ms * 1e-3) / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(a1),
+                  "kernel_ms": k_ms, "units_per_launch": units,
                   "note": "algorithmic bytes = SURVEY.md 8(d): (B_ppr + B_induce) per subgraph x subgraphs per launch; kernel_ms = CUDA events around every sampler launch of the timed region, i.e. ppr_induce_warp_kernel plus its helpers (ppr_count_kernel, scan_counts_kernel, the redo launch of sample_induce_kernel: ~6 % of the time)"},
-        roofline_gather={"kernel": "gather_rows_vec4_kernel", "bound": "hbm", "algorithmic_bytes_per_launch": a2})
+        roofline_gather={"kernel": "gather_rows_vec4_kernel", "bound": "hbm", "algorithmic_bytes_per_launch": int(a2)})
 
 
 def train_phase(ctx, steps, warmup):
