@@ -103,53 +103,103 @@ __global__ void sym_scale_kernel(const int2 *__restrict__ row_span, const int *_
 // ------------------------------------------------------------------------------------------------
 // NV = float4 chunks per lane (F <= 128*NV): the whole output row lives in registers, col[]/val[] are read once, and the
 // edge loop is unrolled by 4 so that a row of the batch with ~150 in-scope neighbours is not a 150-deep latency chain.
+// accumulate val[p] * X[col[p],:] for p = p_begin, p_begin + p_stride, ... < p_end in chunks of `chunk` consecutive edges
+// (chunk <= 32): one coalesced load brings the (col, val) pairs of a chunk, they are broadcast by shuffle so that the X-row loads
+// depend on nothing in memory and up to UB of them are in flight per lane
+template <int NV>
+__device__ __forceinline__ void spmm_accumulate(float4 (&acc)[NV], const int *__restrict__ col, const int col_off, const float *__restrict__ val,
+                                                const float *__restrict__ X, const int F, const int F4, const int p_begin, const int p_end,
+                                                const int chunk, const int p_stride, const int lane) {
+  constexpr int UB = NV <= 2 ? 8 : (NV == 4 ? 4 : 2);           // X-row loads in flight per lane = UB * NV float4
+  for (int p0 = p_begin; p0 < p_end; p0 += p_stride) {
+    const int cnt = min(chunk, p_end - p0);
+    const int pl = p0 + lane;
+    const int c_l = lane < cnt ? col[pl] - col_off : 0;
+    const float w_l = lane < cnt ? (val ? val[pl] : 1.f) : 0.f;
+    for (int u0 = 0; u0 < cnt; u0 += UB) {
+      float4 x[UB][NV];
+      float w[UB];
+#pragma unroll
+      for (int u = 0; u < UB; u++) {
+        const int c = __shfl_sync(0xffffffffu, c_l, (u0 + u) & 31);
+        w[u] = (u0 + u < cnt) ? __shfl_sync(0xffffffffu, w_l, (u0 + u) & 31) : 0.f;
+        const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)c * F);
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+          const int f = lane + 32 * k;
+          x[u][k] = (f < F4 && w[u] != 0.f) ? xr[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; u++)
+#pragma unroll
+        for (int k = 0; k < NV; k++) { acc[k].x += w[u] * x[u][k].x; acc[k].y += w[u] * x[u][k].y; acc[k].z += w[u] * x[u][k].z; acc[k].w += w[u] * x[u][k].w; }
+    }
+  }
+}
+
+// Y = beta*Y + A X.  One warp per row, the whole output row in registers -- except for LONG rows: in a shaDow batch the root's row holds
+// ~140 in-scope neighbours while the other rows hold one or two, and a single warp walking 140 X rows eight at a time is the critical
+// path of the whole launch (~18 dependent L2 round trips).  Rows longer than SPMM_LONG edges are therefore left to the end of the CTA's
+// row group and split over all of its warps (8 consecutive edges per warp and round), partial rows summed through shared memory in a
+// fixed order (deterministic).  NV <= 2 (F <= 256); wider rows keep the one-warp path.
+#define SPMM_LONG 24
 template <int NV>
 __global__ void __launch_bounds__(LAYER_BLOCK) spmm_fwd_vec_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
                                                                    const float *__restrict__ val, const float *__restrict__ X, float *__restrict__ Y,
                                                                    int n, int F, float beta /*Y = beta*Y + A X*/) {
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  constexpr bool SPLIT = NV <= 2;
+  __shared__ float4 part[SPLIT ? LAYER_BLOCK / 32 : 1][SPLIT ? 32 * NV : 1];
+  __shared__ int long_rows[LAYER_BLOCK / 32];
+  __shared__ int n_long;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int F4 = F >> 2;
-  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
-    const int2 sp = row_span[i];
-    float4 acc[NV];
+  for (int base = blockIdx.x * wpb; base < n; base += gridDim.x * wpb) {
+    if (SPLIT) { if (threadIdx.x == 0) n_long = 0; __syncthreads(); }
+    const int i = base + warp;
+    if (i < n) {
+      const int2 sp = row_span[i];
+      if (SPLIT && sp.y - sp.x > SPMM_LONG) { if (lane == 0) long_rows[atomicAdd(&n_long, 1)] = i; }
+      else {
+        float4 acc[NV];
 #pragma unroll
-    for (int k = 0; k < NV; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p0 = sp.x; p0 < sp.y; p0 += 32) {
-      // one coalesced load brings 32 (col, val) pairs; they are broadcast by shuffle so that the X-row loads below depend on
-      // nothing in memory and up to 8 of them are in flight per lane (a root row has ~140 in-scope neighbours)
-      const int pl = p0 + lane;
-      const int c_l = pl < sp.y ? col[pl] - col_off : 0;
-      const float w_l = pl < sp.y ? (val ? val[pl] : 1.f) : 0.f;
-      const int cnt = min(32, sp.y - p0);
-      constexpr int UB = NV <= 2 ? 8 : (NV == 4 ? 4 : 2);       // X-row loads in flight per lane = UB * NV float4
-      for (int u0 = 0; u0 < cnt; u0 += UB) {
-        float4 x[UB][NV];
-        float w[UB];
+        for (int k = 0; k < NV; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        spmm_accumulate<NV>(acc, col, col_off, val, X, F, F4, sp.x, sp.y, 32, 32, lane);
 #pragma unroll
-        for (int u = 0; u < UB; u++) {
-          const int c = __shfl_sync(0xffffffffu, c_l, (u0 + u) & 31);
-          w[u] = (u0 + u < cnt) ? __shfl_sync(0xffffffffu, w_l, (u0 + u) & 31) : 0.f;
-          const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)c * F);
-#pragma unroll
-          for (int k = 0; k < NV; k++) {
-            const int f = lane + 32 * k;
-            x[u][k] = (f < F4 && w[u] != 0.f) ? xr[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < NV; k++) {
+          const int f = lane + 32 * k;
+          if (f < F4) {
+            float4 *y = reinterpret_cast<float4 *>(Y + (size_t)i * F) + f;
+            float4 r = acc[k];
+            if (beta != 0.f) { const float4 o = *y; r.x += beta * o.x; r.y += beta * o.y; r.z += beta * o.z; r.w += beta * o.w; }
+            *y = r;
           }
         }
-#pragma unroll
-        for (int u = 0; u < UB; u++)
-#pragma unroll
-          for (int k = 0; k < NV; k++) { acc[k].x += w[u] * x[u][k].x; acc[k].y += w[u] * x[u][k].y; acc[k].z += w[u] * x[u][k].z; acc[k].w += w[u] * x[u][k].w; }
       }
     }
+    if (SPLIT) {
+      __syncthreads();
+      const int nl = n_long;
+      for (int q = 0; q < nl; q++) {
+        // rows are taken in ascending order so that the result does not depend on which warp registered a row first
+        int r = 0;                                       // q-th smallest entry of long_rows (nl <= 8)
+        for (int a = 0; a < nl; a++) { int rank = 0; for (int b2 = 0; b2 < nl; b2++) rank += long_rows[b2] < long_rows[a]; if (rank == q) r = long_rows[a]; }
+        const int2 sp = row_span[r];
+        float4 acc[NV];
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-      const int f = lane + 32 * k;
-      if (f < F4) {
-        float4 *y = reinterpret_cast<float4 *>(Y + (size_t)i * F) + f;
-        float4 r = acc[k];
-        if (beta != 0.f) { const float4 o = *y; r.x += beta * o.x; r.y += beta * o.y; r.z += beta * o.z; r.w += beta * o.w; }
-        *y = r;
+        for (int k = 0; k < NV; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        spmm_accumulate<NV>(acc, col, col_off, val, X, F, F4, sp.x + warp * 8, sp.y, 8, 8 * wpb, lane);
+#pragma unroll
+        for (int k = 0; k < NV; k++) part[warp][lane + 32 * k] = acc[k];
+        __syncthreads();
+        for (int f = threadIdx.x; f < F4; f += blockDim.x) {
+          float4 rsum = part[0][f];
+          for (int w2 = 1; w2 < wpb; w2++) { const float4 o = part[w2][f]; rsum.x += o.x; rsum.y += o.y; rsum.z += o.z; rsum.w += o.w; }
+          float4 *y = reinterpret_cast<float4 *>(Y + (size_t)r * F) + f;
+          if (beta != 0.f) { const float4 o = *y; rsum.x += beta * o.x; rsum.y += beta * o.y; rsum.z += beta * o.z; rsum.w += beta * o.w; }
+          *y = rsum;
+        }
+        __syncthreads();
       }
     }
   }
