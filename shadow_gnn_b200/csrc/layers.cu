@@ -324,10 +324,8 @@ __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *
                                                                    const float *__restrict__ rstd_in, float *__restrict__ dZ, int lddz,
                                                                    float *__restrict__ dscale, float *__restrict__ doffset, float *__restrict__ dbias,
                                                                    int n, int D, int act, int do_norm) {
-  extern __shared__ float sh[];               // [3*D] column partials of this CTA: dscale, doffset, dbias
+  extern __shared__ float sh[];               // [warps][3*D] column partials of every warp: dscale, doffset, dbias (summed in a fixed order)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int f = threadIdx.x; f < 3 * D; f += blockDim.x) sh[f] = 0.f;
-  __syncthreads();
   float ps[NPL], po[NPL], pb[NPL];
 #pragma unroll
   for (int k = 0; k < NPL; k++) { ps[k] = 0.f; po[k] = 0.f; pb[k] = 0.f; }
@@ -359,15 +357,19 @@ __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *
       for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) { const float dz = g[k] * act_df(z[k], a[k], act); dZ[(size_t)i * lddz + f] = dz; pb[k] += dz; } }
     }
   }
+  float *mine = sh + (size_t)(threadIdx.x >> 5) * 3 * D;
 #pragma unroll
   for (int k = 0; k < NPL; k++) {
     const int f = lane + 32 * k;
-    if (f < D) { if (do_norm) { atomicAdd(&sh[f], ps[k]); atomicAdd(&sh[D + f], po[k]); } if (dbias) atomicAdd(&sh[2 * D + f], pb[k]); }
+    if (f < D) { mine[f] = ps[k]; mine[D + f] = po[k]; mine[2 * D + f] = pb[k]; }
   }
   __syncthreads();
-  for (int f = threadIdx.x; f < D; f += blockDim.x) {
-    if (do_norm) { atomicAdd(&dscale[f], sh[f]); atomicAdd(&doffset[f], sh[D + f]); }
-    if (dbias) atomicAdd(&dbias[f], sh[2 * D + f]);
+  for (int f = threadIdx.x; f < 3 * D; f += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < wpb; w++) v += sh[(size_t)w * 3 * D + f];
+    if (f < D) { if (do_norm) atomicAdd(&dscale[f], v); }
+    else if (f < 2 * D) { if (do_norm) atomicAdd(&doffset[f - D], v); }
+    else if (dbias) atomicAdd(&dbias[f - 2 * D], v);
   }
 }
 
@@ -591,7 +593,14 @@ extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const flo
                                        int32_t act, int32_t do_norm, void *stream) {
   if (n <= 0) return 0;
   if (D > 32 * NORM_MAX_PER_LANE) FAIL(SHADOW_EINVAL, "norm_feat: D=%d exceeds %d", D, 32 * NORM_MAX_PER_LANE);
-#define LAUNCH_BWD(NPL) act_norm_bwd_kernel<NPL><<<grid_for(n, WPB, 1184), LAYER_BLOCK, 3 * D * sizeof(float), ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale, doffset, dbias, n, D, act, do_norm)
+  // every CTA ends with 3*D global atomics onto the same 3*D addresses; 148 / 296 / 592 / 1184 CTAs measured within noise of each other
+  static const int cap = getenv("SHADOW_ANB_CAP") ? std::max(1, atoi(getenv("SHADOW_ANB_CAP"))) : 592;
+  const size_t anb_smem = (size_t)WPB * 3 * D * sizeof(float);
+#define LAUNCH_BWD(NPL)                                                                                                                       \
+  do {                                                                                                                                        \
+    if (anb_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(act_norm_bwd_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)anb_smem)); \
+    act_norm_bwd_kernel<NPL><<<grid_for(n, WPB, cap), LAYER_BLOCK, anb_smem, ST(stream)>>>(dOut, ldo, Z, ldz, scale, mean, rstd, dZ, lddz, dscale, doffset, dbias, n, D, act, do_norm); \
+  } while (0)
   if (D <= 32) LAUNCH_BWD(1); else if (D <= 64) LAUNCH_BWD(2); else if (D <= 128) LAUNCH_BWD(4); else if (D <= 256) LAUNCH_BWD(8);
   else if (D <= 512) LAUNCH_BWD(16); else LAUNCH_BWD(32);
 #undef LAUNCH_BWD
