@@ -9,7 +9,14 @@ cd "$(dirname "$0")"
 OUT=${OUT:-../libshadow_b200.so}
 NVCC=${NVCC:-nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2"
-CUTLASS_INC=${CUTLASS_INC:-$(python -c "import flashinfer, os; print(os.path.join(os.path.dirname(flashinfer.__file__), 'data', 'cutlass', 'include'))")}
+# CUTLASS / CuTe headers vendored in the image's site-packages (no import of the package needed)
+if [ -z "$CUTLASS_INC" ]; then
+  SITE=$(python -c "import sysconfig; print(sysconfig.get_paths()['purelib'])")
+  for d in "$SITE/flashinfer/data/cutlass/include" "$SITE/tilelang/3rdparty/cutlass/include"; do
+    if [ -f "$d/cutlass/gemm/collective/builders/sm100_9xBF16_umma_builder.inl" ]; then CUTLASS_INC=$d; break; fi
+  done
+fi
+if [ -z "$CUTLASS_INC" ]; then echo "build.sh: no CUTLASS >= 4.x header tree with the sm100 FastFP32 builder found (set CUTLASS_INC)" >&2; exit 1; fi
 mkdir -p _obj
 pids=""
 for v in 0 1 2; do
