@@ -33,8 +33,13 @@
 #ifndef WARP_DB
 #define WARP_DB 0              // 1: scan stages double-buffered in registers
 #endif
+#ifndef WARP_OVK
+#define WARP_OVK 3             // overflow keys the straight-line scan variant checks from registers (more overflow keys: looping variant)
+#endif
 #ifndef WARP_BK
-#define WARP_BK 4              // keys per hash bucket: 4 (16-byte probe, 1 bucket per key) or 2 (8-byte probe, 8 buckets per key)
+#define WARP_BK 2              // keys per hash bucket: 2 (8-byte probe, ~6 shared-memory wavefronts per warp-wide probe, 4 buckets per key:
+                               // 1-2 keys per subgraph overflow their bucket and ride in registers) or 4 (16-byte probe, ~10 wavefronts,
+                               // 1 bucket per key, overflow in one subgraph out of ten).  65,536 subgraphs: 1.40 ms vs 1.51 ms
 #endif
 #define WARP_OVF_CAP 8
 #define WARP_CS (4 * WARP_CH)                                  // slots per chunk
@@ -59,8 +64,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, int lane) {
   }
   return x;
 }
-// membership: 4-key buckets, one 16-byte shared-memory load per probe; at <= 0.6 keys per bucket a fifth key in one bucket (-> overflow
-// list, slower scan variant) shows up in about one subgraph in ten
+// membership: buckets of WARP_BK keys, one shared-memory load per probe.  A key whose bucket is full goes to a short overflow list: up to
+// WARP_OVK of them are checked from registers by the straight-line scan variant, longer lists select the looping variant
 #if WARP_BK == 4
 typedef uint4 bucket_t;
 __device__ __forceinline__ bool probe4(const bucket_t *hb, const int hshift, const uint32_t key) {
@@ -122,6 +127,7 @@ __device__ __forceinline__ void scan_load(ScanStage &S, const uint32_t c0, const
 // The caller guarantees room for a whole stage, so the OVF == false variant is straight-line code: the windows' probes interleave.
 template <bool ADD_SELF, bool OVF>
 __device__ __forceinline__ void scan_process(const ScanStage &S, uint32_t &cnt, const bucket_t *hb, const int hshift, const uint32_t novf,
+                                             const uint32_t (&ovk)[WARP_OVK > 0 ? WARP_OVK : 1],
                                              const uint32_t *ovf, const uint32_t *nodes, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
                                              const uint32_t lt) {
 #pragma unroll
@@ -133,6 +139,12 @@ __device__ __forceinline__ void scan_process(const ScanStage &S, uint32_t &cnt, 
     for (int h = 0; h < WARP_CH; h++) { nb[4 * h] = S.q[u][h].x; nb[4 * h + 1] = S.q[u][h].y; nb[4 * h + 2] = S.q[u][h].z; nb[4 * h + 3] = S.q[u][h].w; }
 #pragma unroll
     for (int e = 0; e < WARP_CS; e++) hit[e] = probe4(hb, hshift, nb[e]);
+    if (!OVF && WARP_OVK > 0) {                                        // up to WARP_OVK overflow keys ride in registers (NONE32 = unused)
+#pragma unroll
+      for (int j = 0; j < WARP_OVK; j++)
+#pragma unroll
+        for (int e = 0; e < WARP_CS; e++) hit[e] |= ovk[j] == nb[e];
+    }
     if (OVF) {                                                         // keys that did not fit their bucket
 #pragma unroll 1
       for (uint32_t j = 1; j <= novf; j++) {
@@ -362,7 +374,10 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       int rbase = 0;                                    // cp[rbase] <= first chunk of the window <= cp[rbase+1]
       const uint32_t step = 32u * WARP_U, room = 32u * WARP_U * WARP_CS;      // a stage can keep at most `room` entries
       ScanStage SA;
-      if (novf == 0) {
+      uint32_t ovk[WARP_OVK > 0 ? WARP_OVK : 1];
+#pragma unroll
+      for (int j = 0; j < (WARP_OVK > 0 ? WARP_OVK : 1); j++) ovk[j] = (WARP_OVK > 0 && (uint32_t)j < novf) ? ovf[1 + j] : NONE32;
+      if (novf <= WARP_OVK) {
 #if WARP_DB
         // stages double-buffered in registers: the loads of stage i+1 are in flight while stage i is probed
         ScanStage SB;
@@ -372,17 +387,17 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
           if (cnt + 2u * room > ecap) { bail = true; break; }
           const bool more = c0 + step < total;
           if (more) scan_load(SB, c0 + step, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, false>(SA, cnt, hb, hshift, 0u, ovf, nodes, rc, sc_ent, sc_row, lt);
+          scan_process<ADD_SELF, false>(SA, cnt, hb, hshift, 0u, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
           if (!more) break;
           if (c0 + 2u * step < total) scan_load(SA, c0 + 2u * step, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, false>(SB, cnt, hb, hshift, 0u, ovf, nodes, rc, sc_ent, sc_row, lt);
+          scan_process<ADD_SELF, false>(SB, cnt, hb, hshift, 0u, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
         }
 #else
 #pragma unroll 1
         for (uint32_t c0 = 0; c0 < total; c0 += step) {
           if (cnt + room > ecap) { bail = true; break; }
           scan_load(SA, c0, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, false>(SA, cnt, hb, hshift, 0u, ovf, nodes, rc, sc_ent, sc_row, lt);
+          scan_process<ADD_SELF, false>(SA, cnt, hb, hshift, 0u, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
         }
 #endif
       } else {
@@ -390,7 +405,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
         for (uint32_t c0 = 0; c0 < total; c0 += step) {
           if (cnt + room > ecap) { bail = true; break; }
           scan_load(SA, c0, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, true>(SA, cnt, hb, hshift, novf, ovf, nodes, rc, sc_ent, sc_row, lt);
+          scan_process<ADD_SELF, true>(SA, cnt, hb, hshift, novf, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
         }
       }
     }

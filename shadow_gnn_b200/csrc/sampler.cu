@@ -188,9 +188,9 @@ static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, int ecap_mu
   // that overflows is not an error, it takes the redo launch; the multiplier grows when more than 2 % of a launch had to be redone
   const char *env = getenv("SHADOW_WARP_ECAP_MULT");
   *w_ecap = (env ? std::max(0, atoi(env)) : ecap_mult) * caps.ncap + 32 * WARP_U * WARP_CS * (WARP_DB ? 2 : 1);
-  // 4-key buckets: >= 1 bucket per key; 2-key buckets: >= 6 per key (same overflow rate, twice the table)
+  // 4-key buckets: >= 1 bucket per key; 2-key buckets: >= 3 per key (4 KB either way for k = 150)
   const char *envb = getenv("SHADOW_WARP_BUCKET_MULT");
-  *w_hbuckets = std::max(16, next_pow2((envb ? std::max(1, atoi(envb)) : (WARP_BK == 4 ? 1 : 6)) * caps.ncap));
+  *w_hbuckets = std::max(16, next_pow2((envb ? std::max(1, atoi(envb)) : (WARP_BK == 4 ? 1 : 3)) * caps.ncap));
   int lg = 0; while ((1 << lg) < *w_hbuckets) lg++;
   *w_hshift = 32 - lg;
   W->hkeys = take((size_t)*w_hbuckets * 4 * WARP_BK);
