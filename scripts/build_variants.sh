@@ -5,8 +5,9 @@ set -e
 cd "$(dirname "$0")/../shadow_gnn_b200"
 mkdir -p variants
 build() { name=$1; shift; OUT=../variants/lib_$name.so EXTRA="$*" PTXAS_V=1 bash csrc/build.sh 2>&1 | grep -A2 "ppr_induce_warp" | grep "Used" | sed "s/^/$name: /"; }
-build u4c1m28k2r3 -DWARP_U=4 -DWARP_CH=1 -DWARP_MIN_BLOCKS=28 -DWARP_BK=2 -DWARP_OVK=3 &
-build u4c1m28k2r2 -DWARP_U=4 -DWARP_CH=1 -DWARP_MIN_BLOCKS=28 -DWARP_BK=2 -DWARP_OVK=2 &
-build u4c1m24k2r4 -DWARP_U=4 -DWARP_CH=1 -DWARP_MIN_BLOCKS=24 -DWARP_BK=2 -DWARP_OVK=4 &
+build u2c1m28db -DWARP_U=2 -DWARP_CH=1 -DWARP_MIN_BLOCKS=28 -DWARP_DB=1 &
+build u4c1m24db -DWARP_U=4 -DWARP_CH=1 -DWARP_MIN_BLOCKS=24 -DWARP_DB=1 &
+build u3c1m28db -DWARP_U=3 -DWARP_CH=1 -DWARP_MIN_BLOCKS=28 -DWARP_DB=1 &
+build u6c1m24 -DWARP_U=6 -DWARP_CH=1 -DWARP_MIN_BLOCKS=24 &
 wait
 ls -la variants

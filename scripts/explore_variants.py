@@ -60,8 +60,8 @@ def worker():
 def main():
     vdir = os.path.join(ROOT, "shadow_gnn_b200", "variants")
     libs = [None] + sorted(os.path.join(vdir, f) for f in os.listdir(vdir) if f.endswith(".so")) if os.path.isdir(vdir) else [None]
-    knobs_default = [{"SHADOW_WARP_BUCKET_MULT": 3}, {"SHADOW_WARP_BUCKET_MULT": 6}]
-    jobs = [(None, 16384, [{}]), (None, 65536, [{}])] + [(lib, 16384, knobs_default) for lib in libs if lib] + [(lib, 65536, knobs_default[:1]) for lib in libs if lib]
+    knobs_default = [{}]
+    jobs = [(None, 65536, [{}])] + [(lib, 65536, knobs_default) for lib in libs if lib]
     for lib, P_, kn in jobs:
         env = dict(os.environ)
         env["EXPLORE_WORKER"] = "1"
