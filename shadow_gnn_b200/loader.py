@@ -1,0 +1,190 @@
+"""Data ingest for the hot path: shaDow's on-disk dataset format -> what `MinibatchShallowExtractor` consumes.
+
+Drop-in for `graph_engine.frontend.loader.load_data` (para_graph_sampler/graph_engine/frontend/loader.py:18-121) for node tasks:
+same arguments, same files (`split.npy`, `label_full.npy`, `feat_full.npy` / `feat_full_norm_{all,train}.npy`,
+`adj_{full,train}_{raw,undirected}.{npz,npy}`, `cpp/adj_*_{indptr,indices,data}.bin`), same decisions (transductive vs inductive
+adjacency, prestored undirected adjacency preferred, feature standardisation fitted on all / on the training rows), same result
+fields (`RawGraph`: adj_full, adj_train, feat_full, label_full, node_set, edge_set, bin_adj_files).
+
+What is different:
+  * `to_undirected_csr` (frontend/graph_utils.py:19-45) is a per-row Python loop over `np.union1d` in the reference (minutes for
+    ogbn-products); here it is one sparse pattern union with the same result: rows sorted, unique, all-ones boolean data, uint32
+    index arrays when they fit (`get_adj_dtype`, graph_utils.py:11-16);
+  * the StandardScaler fit/transform (loader.py:104-112) is restated in numpy (float64 statistics, population variance, zero-variance
+    columns left unscaled -- sklearn's documented behaviour), so scikit-learn is not needed on the training box;
+  * the dataset download / conversion step (`convert2shaDow`, needs `ogb` and the network) is out of scope: missing files raise.
+Link-prediction datasets (edge sets) are not handled here (the device minibatch covers node tasks).
+"""
+import os
+from dataclasses import dataclass
+from typing import Any, Dict, Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+TRAIN, VALID, TEST = 0, 1, 2          # graph_engine/frontend/__init__.py
+
+
+@dataclass
+class RawGraph:
+    """frontend/graph.py:14-64"""
+    adj_full: sp.csr_matrix
+    adj_train: Optional[sp.csr_matrix]
+    feat_full: Any
+    label_full: Any
+    node_set: Optional[Dict[int, np.ndarray]]
+    edge_set: Optional[Dict[Any, Any]]
+    bin_adj_files: Optional[Dict[int, Optional[Dict[str, str]]]]
+
+    def __post_init__(self):
+        if self.feat_full is not None:
+            assert self.feat_full.shape[0] == self.num_nodes, \
+                f"[RawGraph]: unmatched feature size ({self.feat_full.shape[0]}) and graph size ({self.num_nodes})"
+        if self.label_full is not None:
+            assert self.label_full.shape[0] == self.num_nodes, \
+                f"[RawGraph]: unmatched label size ({self.label_full.shape[0]}) and graph size ({self.num_nodes})"
+
+    @property
+    def entity_set(self):
+        return self.edge_set if self.node_set is None else self.node_set
+
+    @property
+    def num_nodes(self):
+        return self.adj_full.indptr.size - 1
+
+    @property
+    def num_edges(self):
+        return self.adj_full.indices.size
+
+
+def get_adj_dtype(adj=None, num_nodes=-1, num_edges=-1):
+    """graph_utils.py:11-16"""
+    if adj is not None:
+        num_nodes, num_edges = adj.shape[0], adj.size
+    return np.uint32 if max(num_nodes, num_edges) < 2 ** 32 else np.int64
+
+
+def to_undirected_csr(adj):
+    """Pattern of A + A^T as CSR with sorted, unique rows and broadcast all-ones boolean data (graph_utils.py:19-45)."""
+    adj = adj.tocsr()
+    n = adj.shape[0]
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(adj.indptr.astype(np.int64)))
+    cols = adj.indices.astype(np.int64)
+    key = np.unique(np.concatenate([rows * n + cols, cols * n + rows]))
+    r, c = key // n, key % n
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(r, minlength=n), out=indptr[1:])
+    data = np.broadcast_to(np.ones(1, dtype=bool), c.size)
+    und = sp.csr_matrix((data, c, indptr), shape=adj.shape)
+    dt = get_adj_dtype(adj=und)
+    und.indptr = und.indptr.astype(dt, copy=False)
+    und.indices = und.indices.astype(dt, copy=False)
+    return und
+
+
+def _load_adj(prefix, dataset, type_, split_, surfix=""):
+    """loader.py:124-149: .npz (scipy) or a pickled {'indptr','indices'[,'data']} dict stored as .npy; None when absent"""
+    assert split_ in ("full", "train") and type_ in ("raw", "undirected")
+    base = f"{prefix}/{dataset}/adj_{split_}_{type_}{surfix}."
+    if os.path.isfile(base + "npz"):
+        return sp.load_npz(base + "npz")
+    if os.path.isfile(base + "npy"):
+        d = np.load(base + "npy", allow_pickle=True)
+        if isinstance(d, np.ndarray):
+            d = d[()]
+        assert isinstance(d, dict)
+        indptr, indices = d["indptr"], d["indices"]
+        data = d["data"] if "data" in d else np.broadcast_to(np.ones(1, dtype=bool), indices.size)
+        n = indptr.size - 1
+        return sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    return None
+
+
+def validate_bin_file(bin_adj_files):
+    """loader.py:152-160: all-or-nothing; a missing data file becomes ''"""
+    for _md, df in bin_adj_files.items():
+        assert set(df.keys()) == {"indptr", "indices", "data"}
+        if not os.path.isfile(df["indptr"]) or not os.path.isfile(df["indices"]):
+            return {m: None for m in bin_adj_files}
+        if not os.path.isfile(df["data"]):
+            df["data"] = ""
+    return bin_adj_files
+
+
+def standardize(feats, fit_rows=None):
+    """StandardScaler().fit(feats[fit_rows]).transform(feats) (loader.py:104-112): float64 mean / population variance per column,
+    columns with zero variance are only centred"""
+    fit = feats if fit_rows is None else feats[fit_rows]
+    fit64 = np.asarray(fit, dtype=np.float64)
+    mean = fit64.mean(axis=0)
+    var = fit64.var(axis=0)
+    scale = np.sqrt(var)
+    scale[scale < 10 * np.finfo(np.float64).eps] = 1.0           # sklearn's _handle_zeros_in_scale
+    out = np.asarray(feats, dtype=np.float64)
+    return (out - mean) / scale
+
+
+def load_data(prefix, dataset, config_data, printf=lambda txt, style=None: print(txt)):
+    """loader.py:18-121 for node-classification datasets.  `config_data`: transductive, to_undirected, norm_feat (and coalesce)."""
+    import torch
+    printf("Loading training data..")
+    d = f"{prefix['local']}/{dataset}"
+    for f in ("split.npy", "label_full.npy", "feat_full.npy"):
+        if not os.path.isfile(f"{d}/{f}"):
+            raise FileNotFoundError(f"{d}/{f} is missing: convert the dataset to the shaDow format first (graph_engine.frontend.data_converter; "
+                                    "needs ogb + network, out of scope here)")
+    role = np.load(f"{d}/split.npy", allow_pickle=True)
+    role = role[()] if isinstance(role, np.ndarray) else role
+    assert isinstance(role, dict)
+    if not all(k in role for k in (TRAIN, VALID, TEST)):
+        raise NotImplementedError("link-prediction splits (edge sets) are not handled by this loader")
+    node_set = {k: np.asarray(role[k], dtype=np.int64) for k in (TRAIN, VALID, TEST)}
+    label_full = torch.from_numpy(np.load(f"{d}/label_full.npy"))
+    bin_adj_files = {md: {"indptr": None, "indices": None, "data": None} for md in (TRAIN, VALID, TEST)}
+
+    def fill(mode_, split_, type_):
+        for x in ("indptr", "indices", "data"):
+            bin_adj_files[mode_][x] = f"{d}/cpp/adj_{split_}_{type_}_{x}.bin"
+    if "coalesce" in config_data and not config_data["coalesce"]:
+        raise NotImplementedError
+    kind = "undirected" if config_data["to_undirected"] else "raw"
+
+    def adj_of(split_):
+        a = _load_adj(prefix["local"], dataset, kind, split_)
+        if a is None and kind == "undirected":            # no prestored undirected adjacency: convert the raw one
+            raw = _load_adj(prefix["local"], dataset, "raw", split_)
+            if raw is None:
+                raise FileNotFoundError(f"{d}/adj_{split_}_raw.np[yz] is missing")
+            a = to_undirected_csr(raw)
+        if a is None:
+            raise FileNotFoundError(f"{d}/adj_{split_}_{kind}.np[yz] is missing")
+        return a
+    adj_full = adj_of("full")
+    for md in (VALID, TEST):
+        fill(md, "full", kind)
+    if config_data["transductive"]:
+        adj_train = adj_full
+        fill(TRAIN, "full", kind)
+    else:
+        adj_train = adj_of("train")
+        fill(TRAIN, "train", kind)
+        train_set = set(node_set[TRAIN].tolist())
+        touched = set(adj_train.indices.tolist()) if kind == "undirected" else set(adj_train.nonzero()[0].tolist())
+        assert touched.issubset(train_set), "the training adjacency touches non-training nodes"
+    bin_adj_files = validate_bin_file(bin_adj_files)
+    printf(f"SETTING TO {'TRANS' if config_data['transductive'] else 'IN'}DUCTIVE LEARNING", style="red")
+
+    mode_norm = "all" if config_data["transductive"] else "train"
+    if config_data["norm_feat"] and os.path.isfile(f"{d}/feat_full_norm_{mode_norm}.npy"):
+        feats = np.load(f"{d}/feat_full_norm_{mode_norm}.npy")
+        printf(f"Loading '{mode_norm}'-normalized features", style="yellow")
+    else:
+        feats = np.load(f"{d}/feat_full.npy")
+        if config_data["norm_feat"]:
+            feats = standardize(feats, None if config_data["transductive"] else node_set[TRAIN])
+            printf(f"Normalizing node features (mode = {mode_norm})", style="yellow")
+        else:
+            printf("Not normalizing node features", style="yellow")
+    feats = torch.from_numpy(np.ascontiguousarray(feats)).type(torch.get_default_dtype())
+    printf("Done loading training data..")
+    return RawGraph(adj_full, adj_train, feats, label_full, node_set, None, bin_adj_files)
