@@ -125,11 +125,62 @@ def respool(p, feats, targets, sizes, type_res, type_pool, act, k=None):      # 
     return norm_feat(ACT[act](x @ p["nn.1.weight"].T + p["nn.1.bias"]), p["scale"], p["offset"])
 
 
-def deepgnn(p, x, A, targets, aggr, act, heads, num_layers):                  # models.py:169-204, 1 branch, center pooling, no residue
+def branch_embedding(p, x, A, targets, aggr, act, heads, num_layers, branch=0, aug=None):
+    """one branch of DeepGNN.forward up to the L2-normalised root embedding (models.py:181-201): aug embeddings summed into the
+    features (feature_augment_ops == 'sum', models.py:186-189), conv stack, center pooling without residue"""
     h = x
+    for ia, onehot in enumerate(aug or []):
+        h = h + onehot @ p[f"aug_layers.{branch}.{ia}.weight"].T + p[f"aug_layers.{branch}.{ia}.bias"]
     for l in range(num_layers):
-        pl = {k[len(f"conv_layers.0.{l}."):]: v for k, v in p.items() if k.startswith(f"conv_layers.0.{l}.")}
-        h = sage(pl, h, A, act) if aggr == "sage" else gat(pl, h, A, act, heads)
-    emb = F.normalize(h[targets], p=2, dim=1)
+        pre = f"conv_layers.{branch}.{l}."
+        pl = {k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}
+        h = {"sage": lambda: sage(pl, h, A, act), "gcn": lambda: gcn(pl, h, A, act), "gat": lambda: gat(pl, h, A, act, heads)}[aggr]()
+    return F.normalize(h[targets], p=2, dim=1)
+
+
+def classifier(p, emb):
     pc = {k[len("classifier.0."):]: v for k, v in p.items() if k.startswith("classifier.0.")}
     return norm_feat(emb @ pc["f_lin.weight"].T + pc["f_lin.bias"], pc["scale"][0], pc["offset"][0])
+
+
+def deepgnn(p, x, A, targets, aggr, act, heads, num_layers, aug=None):         # models.py:169-204, 1 branch, center pooling, no residue
+    return classifier(p, branch_embedding(p, x, A, targets, aggr, act, heads, num_layers, 0, aug))
+
+
+def ensemble_aggregator(p, Xs, act="leakyrelu"):                             # layers.py:276-289 (type_dropout none / eval)
+    omega = torch.cat([(ACT[act](X @ p["f_lin.weight"].T + p["f_lin.bias"]) @ p["q"]).view(-1, 1) for X in Xs], 1)
+    w = F.softmax(omega, dim=1)
+    return sum(w[:, i:i + 1] * X for i, X in enumerate(Xs))
+
+
+def deepgnn_ensemble(p, xs, As, targets, aggr, act, heads, num_layers):        # models.py:179-203 with >= 2 branches
+    embs = [branch_embedding(p, x, A, t, aggr, act, heads, num_layers, b) for b, (x, A, t) in enumerate(zip(xs, As, targets))]
+    pe = {k[len("ensembler."):]: v for k, v in p.items() if k.startswith("ensembler.")}
+    return classifier(p, ensemble_aggregator(pe, embs))
+
+
+def rw_vals_dropedge(indptr, drop_idx):
+    """adj_norm_rw on the torch path with a given draw (graph_utils.py:81-95): value of every CSR position"""
+    import numpy as np
+    e = int(indptr[-1])
+    v = np.ones(e, np.float32)
+    v[np.asarray(drop_idx)] = 0
+    rows = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))
+    deg = np.bincount(rows, weights=v, minlength=len(indptr) - 1).astype(np.float32)
+    return v / np.maximum(deg, 1)[rows]
+
+
+def sym_vals_dropedge(indptr, indices, drop_idx):
+    """adj_norm_sym with a given draw (graph_utils.py:112-123,139-142) on a structurally symmetric CSR with sorted rows: an edge survives
+    iff both directions survived (csr data + csc data == 2), then D^-1/2 A D^-1/2 with D = clip(rowsum, 1)"""
+    import numpy as np
+    import scipy.sparse as sp
+    n, e = len(indptr) - 1, int(indptr[-1])
+    m = np.ones(e, np.float32)
+    m[np.asarray(drop_idx)] = 0
+    adj_m = sp.csr_matrix((m, np.asarray(indices), np.asarray(indptr)), shape=(n, n))
+    both = adj_m.data + adj_m.tocsc().data
+    v = (both == 2).astype(np.float32)
+    rows = np.repeat(np.arange(n), np.diff(indptr))
+    d = np.maximum(np.bincount(rows, weights=v, minlength=n), 1).astype(np.float64) ** -0.5
+    return (d[rows] * v * d[np.asarray(indices)]).astype(np.float32)

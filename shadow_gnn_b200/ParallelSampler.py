@@ -233,6 +233,7 @@ class ParallelSampler:
             int(num_subgraphs_ensemble), int(seed), self.device, int(num_ring), C.byref(h)))
         self._h = h
         self.num_ensemble = int(num_subgraphs_ensemble)
+        self._user_stream = False
 
     @classmethod
     def from_device_csr(cls, indptr, indices, num_sampler_per_batch, num_subgraphs_ensemble=1, seed=-1, *,
@@ -253,6 +254,7 @@ class ParallelSampler:
                                             self.device, int(num_ring), C.byref(h)))
         self._h = h
         self.num_ensemble = int(num_subgraphs_ensemble)
+        self._user_stream = False
         return self
 
     def __del__(self, _destroy=lib.shadow_sampler_destroy):
@@ -292,6 +294,8 @@ class ParallelSampler:
         return int(lib.shadow_sampler_last_redo_count(self._h))
 
     def set_stream(self, cuda_stream):
+        """pin the sampler to one stream (default: whatever torch's current stream is at each call)"""
+        self._user_stream = True
         check(lib.shadow_sampler_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def set_num_sampler_per_batch(self, n):
@@ -322,6 +326,12 @@ class ParallelSampler:
         check(lib.shadow_sampler_shuffle_targets_dev(self._h, C.c_void_p(targets_i32.data_ptr()), targets_i32.numel()))
 
     def _launch(self, configs_samplers, configs_aug):
+        # the sampler works on torch's CURRENT stream, so its kernels (and the lazy canonicalisation launched on first access of rowptr /
+        # indices) are ordered with the consumers (gather_rows, ops.*) even under torch.cuda.stream(...); a ring slot is only rewritten
+        # `num_ring` calls later on the same stream
+        import torch
+        if not self._user_stream:
+            lib.shadow_sampler_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         n = len(configs_samplers)
         arr = (_lib.SamplerCfg * n)()
         for i, (cfg, aug) in enumerate(zip(configs_samplers, configs_aug)):

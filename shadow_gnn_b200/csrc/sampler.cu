@@ -248,7 +248,9 @@ static int sampler_common_init(shadow_sampler *s, int per_batch, int num_ens, in
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   s->num_sms = prop.multiProcessorCount;
-  s->rng.seed(seed < 0 ? (uint32_t)time(nullptr) : (uint32_t)seed);     // PS.h:49-53
+  if (seed < 0) seed = (int)((uint32_t)time(nullptr) & 0x7fffffffu);     // PS.h:49-53: srand(time) -- resolved ONCE, so glibc replay and Philox agree
+  s->seed = seed;
+  s->rng.seed((uint32_t)seed);
   s->ring.assign(num_ring, std::vector<Result>(num_ens));
   for (auto &slot : s->ring)
     for (auto &r : slot) CUDA_TRY(cudaMallocHost(&r.totals_host, 4 * sizeof(long long)));
@@ -277,12 +279,15 @@ extern "C" int shadow_sampler_create(const uint32_t *indptr_host, const uint32_t
   if (indptr_host[0] != 0 || indptr_host[num_nodes] != num_edges) FAIL(SHADOW_EINVAL, "indptr[0] != 0 or indptr[N] != nnz (G.h:29-30)");
   shadow_sampler *s = new shadow_sampler();
   int rc = sampler_common_init(s, num_sampler_per_batch, num_subgraphs_ensemble, seed, device, num_ring);
-  if (rc) { delete s; return rc; }
+  if (rc) { shadow_sampler_destroy(s); return rc; }
   s->N = num_nodes; s->E = num_edges; s->owns_graph = true;
-  CUDA_TRY(cudaMalloc(&s->indptr, ((size_t)num_nodes + 1) * 4));
-  CUDA_TRY(cudaMalloc(&s->indices, ((size_t)num_edges + 1) * 4));
-  CUDA_TRY(cudaMemcpy(s->indptr, indptr_host, ((size_t)num_nodes + 1) * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(s->indices, indices_host, (size_t)num_edges * 4, cudaMemcpyHostToDevice));
+  if (cudaMalloc(&s->indptr, ((size_t)num_nodes + 1) * 4) != cudaSuccess || cudaMalloc(&s->indices, ((size_t)num_edges + 1) * 4) != cudaSuccess ||
+      cudaMemcpy(s->indptr, indptr_host, ((size_t)num_nodes + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(s->indices, indices_host, (size_t)num_edges * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    shadow_set_error("CUDA error uploading the graph: %s", cudaGetErrorString(cudaGetLastError()));
+    shadow_sampler_destroy(s);
+    return SHADOW_ECUDA;
+  }
   *out = s;
   return 0;
 }
@@ -294,7 +299,7 @@ extern "C" int shadow_sampler_create_dev(const uint32_t *indptr_dev, const uint3
   CUDA_TRY(cudaSetDevice(device));
   shadow_sampler *s = new shadow_sampler();
   int rc = sampler_common_init(s, num_sampler_per_batch, num_subgraphs_ensemble, seed, device, num_ring);
-  if (rc) { delete s; return rc; }
+  if (rc) { shadow_sampler_destroy(s); return rc; }
   s->N = num_nodes; s->E = num_edges; s->owns_graph = false;
   s->indptr = const_cast<uint32_t *>(indptr_dev); s->indices = const_cast<uint32_t *>(indices_dev);
   *out = s;
@@ -321,7 +326,15 @@ extern "C" int shadow_sampler_destroy(shadow_sampler *s) {
   delete s;
   return 0;
 }
-extern "C" int shadow_sampler_set_stream(shadow_sampler *s, void *st) { if (!s) FAIL(SHADOW_EINVAL, "NULL sampler"); s->stream = (cudaStream_t)st; return 0; }
+extern "C" int shadow_sampler_set_stream(shadow_sampler *s, void *st) {
+  if (!s) FAIL(SHADOW_EINVAL, "NULL sampler");
+  if (s->stream != (cudaStream_t)st) {                 // launches still in flight on the old stream are waited for before anything runs on the new one
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->stream = (cudaStream_t)st;
+  }
+  return 0;
+}
 extern "C" uint32_t shadow_sampler_num_nodes(const shadow_sampler *s) { return s->N; }
 extern "C" uint32_t shadow_sampler_num_edges(const shadow_sampler *s) { return s->graph_dropped ? 0 : s->E; }
 extern "C" uint32_t shadow_sampler_num_nodes_target(const shadow_sampler *s) { return s->T; }

@@ -111,17 +111,28 @@ def validate_bin_file(bin_adj_files):
     return bin_adj_files
 
 
-def standardize(feats, fit_rows=None):
-    """StandardScaler().fit(feats[fit_rows]).transform(feats) (loader.py:104-112): float64 mean / population variance per column,
-    columns with zero variance are only centred"""
-    fit = feats if fit_rows is None else feats[fit_rows]
-    fit64 = np.asarray(fit, dtype=np.float64)
-    mean = fit64.mean(axis=0)
-    var = fit64.var(axis=0)
-    scale = np.sqrt(var)
+def standardize(feats, fit_rows=None, chunk=1 << 18):
+    """StandardScaler().fit(feats[fit_rows]).transform(feats) (loader.py:104-112): mean / population variance per column accumulated in
+    float64 over row chunks (no float64 copy of the matrix: papers100M-scale features would not fit twice), columns with zero variance are
+    only centred; the transform runs in the INPUT dtype like sklearn's (float32 in, float32 out)"""
+    feats = np.asarray(feats)
+    dt = feats.dtype if feats.dtype in (np.float32, np.float64) else np.float64
+    rows = np.arange(feats.shape[0]) if fit_rows is None else np.asarray(fit_rows)
+    s1 = np.zeros(feats.shape[1], np.float64)
+    for a in range(0, rows.size, chunk):
+        s1 += feats[rows[a:a + chunk]].astype(np.float64).sum(axis=0)
+    mean = s1 / max(rows.size, 1)
+    s2 = np.zeros(feats.shape[1], np.float64)
+    for a in range(0, rows.size, chunk):
+        d = feats[rows[a:a + chunk]].astype(np.float64) - mean
+        s2 += (d * d).sum(axis=0)
+    scale = np.sqrt(s2 / max(rows.size, 1))
     scale[scale < 10 * np.finfo(np.float64).eps] = 1.0           # sklearn's _handle_zeros_in_scale
-    out = np.asarray(feats, dtype=np.float64)
-    return (out - mean) / scale
+    out = np.empty(feats.shape, dt)
+    m, sc = mean.astype(dt), scale.astype(dt)
+    for a in range(0, feats.shape[0], chunk):
+        out[a:a + chunk] = (feats[a:a + chunk].astype(dt) - m) / sc
+    return out
 
 
 def load_data(prefix, dataset, config_data, printf=lambda txt, style=None: print(txt)):

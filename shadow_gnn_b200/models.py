@@ -115,6 +115,8 @@ class DeepGNN(nn.Module):
             self.optimizer = FlatAdamClip(list(self.parameters()), lr=self.lr, max_norm=5.0)
             import torch.distributed as dist
             self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            if self._world > 1:        # replicas must start from the same weights whatever each rank's RNG state was
+                dist.broadcast(self.optimizer.flat, src=0)
         return self.optimizer
 
     # ---- models.py:209-237 ----

@@ -7,6 +7,7 @@ Dropout uses torch's graph-safe Philox state; dropedge reads its stream position
 (csrc/layers.cu: dropedge_kernel), so every replay drops different edges.  Batches that do not fit the captured capacity (the short
 batch at the end of an epoch, an unusually large scope) run through the eager `DeepGNN.step`.
 """
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -18,6 +19,9 @@ from .parallel import allreduce_flat_gradients
 class GraphedTrainer:
     def __init__(self, model, minibatch, row_cap, edge_cap, mode=TRAIN):
         assert minibatch.num_ensemble == 1 and not minibatch.aug_feats, "the graphed step covers the single-branch, no-augmentation path"
+        pools = {rp.type_pool for rp in model.res_pool_layers}
+        assert "sort" not in pools, "sort pooling has data-dependent shapes (repeat_interleave): use the eager DeepGNN.step"
+        self._needs_sizes = pools != {"center"}
         self.model, self.mb, self.mode = model, minibatch, mode
         self.B = minibatch._cfg_ensemble["batch_size"]
         dev, Fd = minibatch.dev_torch, minibatch.feat_full.shape[1]
@@ -28,7 +32,9 @@ class GraphedTrainer:
         self.val = torch.zeros(self.edge_cap, dtype=torch.float32, device=dev)
         self.feat = torch.zeros((self.row_cap, Fd), dtype=torch.float32, device=dev)
         self.target = torch.zeros(self.B, dtype=torch.int64, device=dev)
-        self.label = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        lf = minibatch.label_full
+        self.label = torch.zeros((self.B,) + tuple(lf.shape[1:]), dtype=lf.dtype, device=dev)      # class ids [B] or multi-hot rows [B, C]
+        # rows per subgraph of the loaded batch (max / mean / sum pooling segments; padding rows lie behind the last segment)
         self.sizes = torch.ones((1, self.B), dtype=torch.int64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.graph = None
@@ -69,10 +75,13 @@ class GraphedTrainer:
         # with several ranks the gradient all-reduce sits between the captured fwd/bwd and the (eager, 3-launch) optimizer step
 
     def _load_static(self, sb, bs):
+        a = sb.cursor
         rowptr, indices, lo, e0, feat, target = sb.take_canonical(bs)
         n, e = rowptr.numel() - 1, indices.numel()
         if n > self.row_cap or e > self.edge_cap:
             return False
+        if self._needs_sizes:
+            self.sizes.copy_(torch.from_numpy(np.diff(sb.node_ptr_host[a:a + bs + 1])).view(1, -1))
         torch.sub(rowptr, e0, out=self.rowptr[:n + 1])
         self.rowptr[n + 1:] = e                              # padding rows: empty
         self.span[:, 0] = self.rowptr[:-1]
