@@ -131,7 +131,7 @@ def algorithmic_bytes(batch, deg, F, P):
 class CpuRef:
     def __init__(self, g_host, roots, threads):
         from oracle import oracle as O
-        self.O, self.g, self.threads = O, g_host, threads
+        self.O, self.g, self.threads, self.roots = O, g_host, threads, np.asarray(roots)
         indptr, indices = g_host["indptr"], g_host["indices"]
         ref = O.load_ref()
         log("cpu arm: start", roots.size, "roots", threads, "threads", "reference .so" if ref is not None else "oracle port")
@@ -147,15 +147,16 @@ class CpuRef:
                 os.dup2(saved, 1); os.close(devnull)
             s.shuffle_targets(roots.tolist())
             self.kind = "reference"
-            self._call = lambda: s.parallel_sampler_ensemble([SAMPLER_CFG], [set()])[0]
+            self._call = lambda roots_only=False: s.parallel_sampler_ensemble([dict(SAMPLER_CFG, return_target_only="true") if roots_only else SAMPLER_CFG], [set()])[0]
             self._conv = lambda vec: O.ref_subgraphs(vec)
         else:
             s = O.OracleSampler(indptr, indices, 500, threads, 1)
             s.preproc_ppr_approximate(roots, PPR_K, PPR_ALPHA, PPR_EPS)
             s.shuffle_targets(roots)
             cfg = O.cfg_from_cpp_config(SAMPLER_CFG)
+            cfg_roots = O.cfg_from_cpp_config(dict(SAMPLER_CFG, return_target_only="true"))
             self.kind = "port"
-            self._call = lambda: s.sample(cfg)
+            self._call = lambda roots_only=False: s.sample(cfg_roots if roots_only else cfg)
             self._conv = lambda b: b.subgraphs()
         self.sampler = s
         log("cpu arm: sampler + PPR tables ready")
@@ -178,23 +179,35 @@ class CpuRef:
             del x
         return dict(value=n_sub / t_full, cpp_call_only=n_sub / t_cpp, n=n_sub, seconds=t_full)
 
-    def train_arm(self, labels_all, steps, warmup, C):
+    def train_arm(self, labels_all, steps, warmup, C, device="cpu", cache_mode="record"):
+        """the reference's training loop (oracle/train_ref.py): sampler (500 roots per call) -> per-root cache -> pool -> collate -> model step.
+        device "cpu": everything on the host cores; "cuda": model + full feature tensor on the GPU (`--gpu 0`, full_tensor_on_gpu),
+        sampler / cache / collation on the host exactly as the reference runs.  cache_mode: "record" (epoch 0), "reuse" (epochs >= 1 of the
+        deterministic PPR sampler: no sampling, subgraphs from the per-root dict), "nocache" (`--nocache all`)."""
         import torch
-        from oracle.train_ref import RefModel
+        from oracle.train_ref import RefModel, RefMinibatch
         torch.set_num_threads(self.threads)
-        feat = torch.from_numpy(self.g["feat"])
         B = TRAIN_CFG["batch"]
-        model = RefModel(feat.shape[1], TRAIN_CFG["dim"], C, TRAIN_CFG["layers"], TRAIN_CFG["dropout"], TRAIN_CFG["dropedge"], TRAIN_CFG["lr"])
-        pool, t_total, n = [], 0.0, 0
+        dev = torch.device(device)
+        feat = torch.from_numpy(self.g["feat"]).to(dev)
+        torch.manual_seed(0)
+        model = RefModel(feat.shape[1], TRAIN_CFG["dim"], C, TRAIN_CFG["layers"], TRAIN_CFG["dropout"], TRAIN_CFG["dropedge"], TRAIN_CFG["lr"], device=device)
+        mb = RefMinibatch(self._call, self._conv, self.roots, labels_all, feat, B, PPR_K, int(self.g["indices"].size), dev,
+                          "record" if cache_mode == "reuse" else cache_mode)
+        self.sampler.shuffle_targets(self.roots.tolist() if self.kind == "reference" else self.roots)      # root cursor back to 0
+        if cache_mode == "reuse":                    # epoch 0 (untimed here): every root's subgraph goes into the dict, then the pool is dropped
+            for _ in range((self.roots.size + 499) // 500):
+                mb.par_graph_sample()
+            mb.pool.clear()
+            mb.set_mode("reuse")
+        sync = (lambda: torch.cuda.synchronize()) if dev.type == "cuda" else (lambda: None)
+        t_total, n = 0.0, 0
         for it in range(warmup + steps):
+            sync()
             t0 = time.perf_counter()
-            while len(pool) < B:
-                pool.extend(self._conv(self._call()))               # minibatch.py:450-451
-            sub, pool = pool[:B], pool[B:]
-            col = self.O.cat_to_block_diagonal(sub)                 # graph.py:280-320
-            x = feat[torch.as_tensor(col["node"].astype(np.int64))]   # minibatch.py:469
-            y = torch.as_tensor(labels_all[col["node"][col["target"]].astype(np.int64)])
-            model.step(col, x, y)
+            adj, x, target, y = mb.one_batch()
+            loss = model.step(adj, x, target, y)
+            float(loss)                              # the reference logs the loss every batch (main.py:156-163): a device->host read
             t1 = time.perf_counter()
             if it >= warmup:
                 t_total += t1 - t0; n += B
@@ -228,26 +241,41 @@ WORKLOAD = ("{g} 5-layer GraphSAGE-256, PPR(k=150,eps=1e-5) sampler, batch 32 pe
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU implementation of the path on the host cores, bounded sample"""
+    """`--impl reference`: the reference's own implementation of the path on this box, bounded sample.  The sampler is the unmodified
+    reference C++ (oracle/_ref, all host threads, 500 roots per call); the minibatch loop and the model restate the reference's Python
+    (oracle/train_ref.py -- the reference's Python tree cannot travel to the GPU box).  Variants timed: the model on the host cores
+    (`cpu_baseline`) and, when a GPU is visible, the reference as its users run it -- model + feature tensor on the GPU -- in its three
+    cache modes: epoch 0, cached epochs >= 1, `--nocache all`.  `value` = the FASTEST variant: the claim is made against it."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
+    import torch
     threads = os.cpu_count() or 1
     gh = host_graph(args)
     B = TRAIN_CFG["batch"]
     steps, warm = min(args.steps, 60), min(args.warmup, 3)
-    n_roots = min(gh["train"].size, B * (steps + warm) + 500 * 8)
+    n_roots = min(gh["train"].size, ((B * (steps + warm) + 499) // 500 + 2) * 500)
     ref = CpuRef(gh, gh["train"][:n_roots], threads)
     line = {"impl": "reference", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "data": "synthetic"}
     samp = ref.sampler_arm(5, 1) if args.task in ("full", "sampler") else None
     if args.task in ("full", "train"):
         labels = np.random.default_rng(7).integers(0, gh["C"], gh["N"])
-        tr = ref.train_arm(labels, steps, warm, gh["C"])
-        line.update(metric="train_samples_per_sec", value=tr["value"], unit="samples/s", ms_per_step=1e3 * tr["seconds"] / steps, dtype="f32",
+        variants = {}
+        tr = ref.train_arm(labels, min(steps, 40), warm, gh["C"], "cpu", "record")
+        variants["model_on_host_cores_epoch0"] = tr["value"]
+        cpu_val, cpu_n = tr["value"], tr["n"]
+        if torch.cuda.is_available():
+            for name, mode in (("model_on_gpu_epoch0", "record"), ("model_on_gpu_cached_epochs", "reuse"), ("model_on_gpu_nocache", "nocache")):
+                variants[name] = ref.train_arm(labels, steps, warm, gh["C"], "cuda", mode)["value"]
+        best = max(variants, key=variants.get)
+        line.update(metric="train_samples_per_sec", value=variants[best], unit="samples/s", ms_per_step=1e3 * B / variants[best], dtype="f32",
+                    variants=variants, fastest_variant=best,
                     config={"workload": WORKLOAD.format(g=args.graph),
-                            "step": "one training batch; reference sampler called for 500 roots at a time (shaDow/minibatch.py:397); model = the reference's torch library calls on the host cores"},
-                    cpu_baseline={"value": tr["value"], "unit": "samples/s", "cores": threads, "kind": ref.kind, "sample": f"{tr['n']} targets of the same target order"},
-                    e2e={"value": tr["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+                            "step": "one training batch; reference sampler called for 500 roots at a time (shaDow/minibatch.py:397), per-root subgraph cache, pool, "
+                                    "cat_to_block_diagonal, feat_full[node], DeepGNN.step with the reference's torch library calls; value = fastest of `variants`"},
+                    cpu_baseline={"value": cpu_val, "unit": "samples/s", "cores": threads, "kind": ref.kind,
+                                  "sample": f"{cpu_n} targets of the same target order; sampler = unmodified reference C++, loop + model = port of the reference's Python on the host cores"},
+                    e2e={"value": variants[best], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         if samp:
             line["sampler"] = {"value": samp["value"], "unit": "subgraphs/s", "cpp_call_only": samp["cpp_call_only"], "sample": f"{samp['n']} roots"}
     else:
@@ -323,6 +351,7 @@ def sampler_phase(ctx, steps, warmup):
         step(i)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     nsub = 0
     ctx.barrier()
     ev0.record()
@@ -331,13 +360,16 @@ def sampler_phase(ctx, steps, warmup):
         s._launch([SAMPLER_CFG], [set()])
         kev[i][1].record()
         b = PS.DeviceBatch(s, 0)
+        gev[i][0].record()
         PS.gather_rows(ctx.feat, b.orig_node, out=out_feat[i % 2][:b.total_nodes])
+        gev[i][1].record()
         nsub += b.num_subg
         last = b
     ev1.record()
     ctx.barrier()
     ms = ev0.elapsed_time(ev1)
     k_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
+    g_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in gev]))
     # algorithmic bytes: the last step's batch gives the bytes per subgraph (the roots differ from launch to launch, their distribution does
     # not); a launch of the timed region processed nsub / steps subgraphs on average (the last launch of an epoch is shorter)
     a1_last, a2_last = algorithmic_bytes(last, ctx.deg, F, last.num_subg)
@@ -393,7 +425,9 @@ def sampler_phase(ctx, steps, warmup):
                   "frac": (a1 / 1e9) / (k_ms * 1e-3) / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(a1),
                   "kernel_ms": k_ms, "units_per_launch": units,
                   "note": "algorithmic bytes = SURVEY.md 8(d): (B_ppr + B_induce) per subgraph x subgraphs per launch; kernel_ms = CUDA events around every sampler launch of the timed region, i.e. ppr_induce_warp_kernel plus its helpers (ppr_count_kernel, scan_counts_kernel, the redo launch of sample_induce_kernel: ~6 % of the time)"},
-        roofline_gather={"kernel": "gather_rows_vec4_kernel", "bound": "hbm", "algorithmic_bytes_per_launch": int(a2)})
+        roofline_gather={"kernel": "gather_rows_vec4_kernel", "bound": "hbm", "achieved": (a2 / 1e9) / (g_ms * 1e-3), "peak": peak, "unit": "GB/s",
+                         "frac": (a2 / 1e9) / (g_ms * 1e-3) / peak, "traffic": None, "kernel_ms": g_ms, "algorithmic_bytes_per_launch": int(a2),
+                         "note": "B_gather = 2 * 4 * F * |V| (read + write of every gathered feature row); CUDA events around each gather launch of the timed region"})
 
 
 def train_phase(ctx, steps, warmup):
@@ -407,8 +441,10 @@ def train_phase(ctx, steps, warmup):
     share = ctx.share.numpy()
     cfg = {"batch_size": B, "configs": [{"method": "ppr", "k": [PPR_K], "threshold": [0.0], "epsilon": [PPR_EPS]}]}
     adjs = {m: (ctx.g["indptr"], ctx.g["indices"]) for m in range(3)}
+    # the timed region must contain sampling whatever --steps is: at least 4 super-batch refills (sampler + gather + canonical CSR) fall inside it
+    sb_train = max(B, min(args.superbatch_train, B * max(1, steps // 4)))
     mb = MB.MinibatchShallowExtractor(args.graph, None, adjs, {0: share, 1: share[:B], 2: share[:B]}, cfg, set(), None, ctx.feat, labels, F, True, 1,
-                                      seed_cpp=1, num_subg_per_batch=args.superbatch_train)
+                                      seed_cpp=1, num_subg_per_batch=sb_train)
     model = DeepGNN(F, F, C, 0, ARCH, [], 1, dict(dropout=TRAIN_CFG["dropout"], dropedge=TRAIN_CFG["dropedge"], lr=TRAIN_CFG["lr"], ensemble_dropout="none"),
                     "node").to(dev)
     nparams = sum(p.numel() for p in model.parameters())
@@ -434,28 +470,30 @@ def train_phase(ctx, steps, warmup):
     ctx.barrier()
     ev0.record()
     nsamp = 0
+    refills0 = mb.num_sampler_calls
     for _ in range(steps):
         nsamp += one_step()[1]
     ev1.record()
+    refills = mb.num_sampler_calls - refills0
     ctx.barrier()
     ms = ev0.elapsed_time(ev1)
     log("train phase: timed region done", ms)
     # e2e: the user-facing step with HOST inputs: this step's target ids + labels come from pinned host memory, the loss goes back
     e2e_steps = max(5, min(steps, 300))
-    tgt_host = torch.from_numpy(share.astype(np.int64)).pin_memory()
-    lab_host = labels.cpu()[tgt_host].pin_memory()
+    lab_epoch_host = mb.label_epoch[MB.TRAIN].cpu().pin_memory()      # labels of the current epoch order (re-pinned when the epoch rolls over)
     loss_host = torch.zeros(1).pin_memory()
-    stage_t = torch.zeros(B, dtype=torch.int64, device=dev)
     ctx.barrier()
     t0 = time.perf_counter()
     ne2e = 0
+    epoch_ids = mb.entity_epoch[MB.TRAIN]
     for i in range(e2e_steps):
-        lo = (i * B) % (share.size - B)
-        stage_t.copy_(tgt_host[lo:lo + B], non_blocking=True)                 # H2D: the step's targets
         roll()
+        if mb.entity_epoch[MB.TRAIN] is not epoch_ids:        # new epoch order: its labels are staged again
+            epoch_ids = mb.entity_epoch[MB.TRAIN]
+            lab_epoch_host = mb.label_epoch[MB.TRAIN].cpu().pin_memory()
         a = mb.idx_entity_evaluated[MB.TRAIN]
-        if a + B <= mb.label_epoch[MB.TRAIN].numel():
-            mb.label_epoch[MB.TRAIN][a:a + B].copy_(lab_host[lo:lo + B], non_blocking=True)   # H2D: the step's labels, consumed by the step
+        if a + B <= mb.label_epoch[MB.TRAIN].numel():           # H2D: this step's labels (consumed by the step's loss); the step's target ids
+            mb.label_epoch[MB.TRAIN][a:a + B].copy_(lab_epoch_host[a:a + B], non_blocking=True)   # travel with the epoch's target list (uploaded when it is shuffled)
         loss, n = one_step()
         loss_host.copy_(loss.reshape(1), non_blocking=True)                   # D2H: the step's loss
         torch.cuda.synchronize()
@@ -467,8 +505,9 @@ def train_phase(ctx, steps, warmup):
     return dict(value=n_all / (ms_all * 1e-3), unit="samples/s", ms_per_step=ms_all / steps, nparams=nparams,
                 graph_steps=getattr(trainer, "graph_steps", 0), eager_steps=getattr(trainer, "eager_steps", steps),
                 gpu_launches=mine * steps + 7 * (steps * B // args.superbatch_train + 1),      # per super-batch: count, scan, fast path, redo, gather, 2 x canonical CSR
-                e2e={"value": ne_all / e2e_all, "unit": "samples/s", "h2d_bytes_per_step": B * 16, "d2h_bytes_per_step": 4,
-                     "note": "targets + labels from pinned host memory each step, loss read back each step"})
+                superbatch=sb_train, refills_in_timed_region=int(refills),
+                e2e={"value": ne_all / e2e_all, "unit": "samples/s", "h2d_bytes_per_step": B * 8 + B * 4, "d2h_bytes_per_step": 4,
+                     "note": "labels from pinned host memory each step, loss read back each step; the epoch's target ids are uploaded once per epoch (4 B per target)"})
 
 
 def run_ours(args):
@@ -489,7 +528,7 @@ def run_ours(args):
             line.update(metric="train_samples_per_sec", value=tr["value"], unit="samples/s", ms_per_step=tr["ms_per_step"], dtype="f32", e2e=tr["e2e"],
                         gpu_launches=tr["gpu_launches"] + (samp["gpu_launches"] if samp else 0),
                         config={"workload": WORKLOAD.format(g=args.graph), "params": tr["nparams"], "global_batch": TRAIN_CFG["batch"] * world,
-                                "sampler_superbatch": args.superbatch_train, "l2": l2,
+                                "sampler_superbatch": tr["superbatch"], "sampler_refills_in_timed_region": tr["refills_in_timed_region"], "l2": l2,
                                 "step_execution": "eager" if args.eager else f"whole-step CUDA graph ({tr['graph_steps']} graph / {tr['eager_steps']} eager steps incl. warm-up)",
                                 "parallelism": f"dp{world}: targets partitioned, graph/PPR tables/features replicated, one NCCL all-reduce of the flat {tr['nparams'] * 4} B gradient bucket per step"})
             if samp:

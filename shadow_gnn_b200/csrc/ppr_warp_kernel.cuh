@@ -6,17 +6,23 @@
 //   * a warp owns a subgraph end to end, so there is no CTA barrier and no cross-warp scan anywhere;
 //   * the node set comes from the id-sorted PPR row, which also carries (row start, degree) of every neighbour -- captured once
 //     when the tables are installed -- so the random 8-byte indptr reads (a 64-byte DRAM fetch each) disappear;
-//   * the row scan runs over a FLAT space of chunks: all rows of the subgraph are cut into aligned chunks of 4*WARP_CH slots, lane L of
-//     window w takes chunk 32w+L whatever row it belongs to (rows are resolved 32 chunks at a time with one REDUX), loads it with
-//     WARP_CH 128-bit streaming loads and probes the shared-memory hash once per slot.  Short rows no longer idle lanes (a
-//     row-granular 128-byte item keeps 82 % of the lanes busy on the S-products stand-in, a 512-byte one only 43 %);
+//   * the row scan runs over a FLAT space of chunks: all rows of the subgraph are cut into 16-byte aligned chunks of 4 slots, lane L of
+//     window w takes chunk 32w+L whatever row it belongs to (rows are resolved 32 chunks at a time with one REDUX) and loads it with one
+//     128-bit streaming load: short rows do not idle lanes;
+//   * MEMBERSHIP IS A TWO-LEVEL TEST (round 2).  Level 1, once per scanned slot, is a 1024-bit blocked Bloom filter that lives in ONE
+//     REGISTER per lane (lane w holds word w): the word is fetched with a single SHFL indexed by the slot's hash and two independent
+//     bits of it are tested.  No shared-memory bank is touched and nothing is compacted per slot: a lane only ORs the verdicts of its 4
+//     slots, and ONE ballot per window of 128 slots appends the (~30 %) chunks that may hold a member -- keys + packed (row, offset) --
+//     to a small shared-memory queue.  Level 2 runs on full warps of 32 queued chunks: the exact 2-key-bucket probe, the row-range check
+//     (alignment padding of a chunk belongs to the neighbouring rows) and the ordered append of round 1, now on a third of the chunks.
+//     The round-1 kernel ran the exact probe (~6 shared-memory wavefronts, ~25 instructions) for every scanned slot and was bound by
+//     issue slots and the shared-memory pipe (69 % each);
 //   * with no self-edge insertion the PS.cpp:401 slot (one past the row) is simply one more slot of the row, and the staged stream
 //     IS the CSR: emit is a straight copy with the sub id resolved per kept edge;
 //   * kept edges are staged in a per-warp scratch region in GLOBAL memory that the warp reuses for every subgraph (it stays in L2), per-row
-//     counts come from one shared-memory atomic per lane: 7 KB of shared memory per warp instead of 12, i.e. 28 instead of 18 warps/SM;
+//     counts come from one shared-memory atomic per lane;
 //   * the node count of a subgraph is a function of its table row alone, so a small count kernel + a one-block scan fix node_ptr[] before
-//     this kernel starts: no decoupled look-back (with ~2,500 subgraphs in flight in lock-step the nearest inclusive prefix was ~75
-//     windows of 32 tickets back: 17 % of all instructions of the first version were that walk).
+//     this kernel starts: no decoupled look-back.
 // A subgraph that does not fit the per-warp scratch (or whose hash overflow list is full) is not an error: its index goes on a
 // redo list and the generic CTA kernel, launched right behind in redo mode, builds it into the rows this kernel reserved.
 #pragma once
@@ -26,26 +32,18 @@
 #ifndef WARP_U
 #define WARP_U 4               // chunk windows in flight per warp (32 chunks each)
 #endif
-#ifndef WARP_CH
-#define WARP_CH 1              // 16-byte loads per lane and window: a chunk is 4*WARP_CH slots
-#endif
 #ifndef WARP_MIN_BLOCKS
-#define WARP_MIN_BLOCKS 28     // one warp per CTA: resident warps per SM the register budget must allow
+#define WARP_MIN_BLOCKS 20     // one warp per CTA: resident warps per SM the register budget must allow
 #endif
 #ifndef WARP_DB
-#define WARP_DB 0              // 1: scan stages double-buffered in registers
+#define WARP_DB 1              // 1: the loads of stage i+1 are issued before stage i is processed (two stages of registers)
 #endif
-#ifndef WARP_OVK
-#define WARP_OVK 3             // overflow keys the straight-line scan variant checks from registers (more overflow keys: looping variant)
+#define WARP_CS 4              // slots per chunk (one 128-bit load)
+#define WARP_CSH 2
+#define WARP_QCAP 64           // chunk queue: < 32 left over + at most 32 new per window
+#ifndef WARP_OVF_CAP
+#define WARP_OVF_CAP 16        // keys whose 2-key bucket was full
 #endif
-#ifndef WARP_BK
-#define WARP_BK 2              // keys per hash bucket: 2 (8-byte probe, ~6 shared-memory wavefronts per warp-wide probe, 4 buckets per key:
-                               // 1-2 keys per subgraph overflow their bucket and ride in registers) or 4 (16-byte probe, ~10 wavefronts,
-                               // 1 bucket per key, overflow in one subgraph out of ten).  65,536 subgraphs: 1.40 ms vs 1.51 ms
-#endif
-#define WARP_OVF_CAP 8
-#define WARP_CS (4 * WARP_CH)                                  // slots per chunk
-#define WARP_CSH (WARP_CH == 1 ? 2 : (WARP_CH == 2 ? 3 : 4))   // log2(WARP_CS)
 
 __device__ __forceinline__ uint32_t lanemask_le() {
   uint32_t m;
@@ -66,37 +64,51 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, int lane) {
   }
   return x;
 }
-// membership: buckets of WARP_BK keys, one shared-memory load per probe.  A key whose bucket is full goes to a short overflow list: up to
-// WARP_OVK of them are checked from registers by the straight-line scan variant, longer lists select the looping variant
-#if WARP_BK == 4
-typedef uint4 bucket_t;
-__device__ __forceinline__ bool probe4(const bucket_t *hb, const int hshift, const uint32_t key) {
-  const uint4 kk = hb[(key * 2654435761u) >> hshift];
-  return (kk.x == key) | (kk.y == key) | (kk.z == key) | (kk.w == key);
-}
-#else
-typedef uint2 bucket_t;   // 2-key buckets: ~6 instead of ~10 shared-memory wavefronts per warp-wide probe, but twice the table for the same overflow rate
-__device__ __forceinline__ bool probe4(const bucket_t *hb, const int hshift, const uint32_t key) {
-  const uint2 kk = hb[(key * 2654435761u) >> hshift];
-  return (kk.x == key) | (kk.y == key);
-}
-#endif
 
-// One stage of the scan = WARP_U windows of 32 chunks, all loads issued before the first use.
+// ---- level 1: blocked Bloom filter, NF words per lane (32 * NF words = 1024 * NF bits), one SHFL per word-register, 2 bits per key ----
+__device__ __forceinline__ uint32_t bloom_hash(uint32_t key) { return key * 2654435761u; }
+__device__ __forceinline__ uint32_t bloom_hash2(uint32_t key) { return __umulhi(key, 0x85EBCA6Bu); }
+template <int NF>
+__device__ __forceinline__ uint32_t bloom_word_index(uint32_t h) { return h >> (NF == 1 ? 27 : (NF == 2 ? 26 : 25)); }
+__device__ __forceinline__ uint32_t bloom_bits(uint32_t h, uint32_t g) { return __funnelshift_l(0u, 1u, h) | __funnelshift_l(0u, 1u, g); }   // 1 << h % 32 | 1 << g % 32
+// bit 0 of the result: both bits of `key` are set in its filter word
+template <int NF>
+__device__ __forceinline__ uint32_t bloom_test(const uint32_t (&f)[NF], uint32_t key) {
+  const uint32_t h = bloom_hash(key), g = bloom_hash2(key), w = bloom_word_index<NF>(h);
+  uint32_t fv = __shfl_sync(0xffffffffu, f[0], (int)w);       // source lane = w mod 32
+  if (NF >= 2) { const uint32_t f1 = __shfl_sync(0xffffffffu, f[NF >= 2 ? 1 : 0], (int)w); fv = (w & 32u) ? f1 : fv; }
+  if (NF == 4) {
+    const uint32_t f2 = __shfl_sync(0xffffffffu, f[NF == 4 ? 2 : 0], (int)w), f3 = __shfl_sync(0xffffffffu, f[NF == 4 ? 3 : 0], (int)w);
+    fv = (w & 64u) ? ((w & 32u) ? f3 : f2) : fv;
+  }
+  return __funnelshift_r(fv, 0u, h) & __funnelshift_r(fv, 0u, g);        // (fv >> h % 32) & (fv >> g % 32)
+}
+
+// ---- level 2: exact membership in buckets of 2 keys (one 8-byte shared-memory load); a key whose bucket was full sits in a short overflow list ----
+__device__ __forceinline__ bool probe2(const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf, const uint32_t key) {
+  const uint2 kk = hb[bloom_hash(key) >> hshift];
+  bool hit = (kk.x == key) | (kk.y == key);
+#pragma unroll 1
+  for (uint32_t j = 0; j < novf; j++) hit |= ovl[j] == key;
+  return hit;
+}
+
+#define WARP_OFFBITS 19                                // candidate code = row << 19 | (slot - row start + 3): rows < 8192, scanned length < 2^19 - 8
+#define WARP_OFFMASK ((1u << WARP_OFFBITS) - 1u)
 struct ScanStage {
-  uint4 q[WARP_U][WARP_CH];
-  uint32_t jb[WARP_U], s[WARP_U], d[WARP_U], rw[WARP_U];
+  uint4 q[WARP_U];
+  uint32_t code[WARP_U];                             // code of the first slot of my chunk (WARP_OFFMASK for an idle lane: offset beyond any row)
 };
 
+// The aligned 16-byte chunk that holds the last slot of the array may reach up to 12 bytes past indices[E-1]: still inside the allocation
+// (CUDA allocations are 256-byte granular and the array starts 16-byte aligned); those slots are >= E, outside every row range.
 __device__ __forceinline__ void scan_load(ScanStage &S, const uint32_t c0, const uint32_t total, int &rbase, const int n, const int lane,
-                                          const uint32_t le, const uint32_t *cp, const uint2 *rs, const uint4 *ind4, const uint32_t *indices,
-                                          const uint32_t E, const uint32_t E_al) {
+                                          const uint32_t le, const uint32_t *cp, const uint2 *rs, const uint4 *ind4) {
 #pragma unroll
   for (int u = 0; u < WARP_U; u++) {
     const uint32_t cw = c0 + 32u * u;
-#pragma unroll
-    for (int h = 0; h < WARP_CH; h++) S.q[u][h] = make_uint4(0u, 0u, 0u, 0u);
-    S.jb[u] = 0; S.s[u] = 0; S.d[u] = 0; S.rw[u] = 0;
+    S.q[u] = make_uint4(NONE32, NONE32, NONE32, NONE32);
+    S.code[u] = WARP_OFFMASK;
     if (cw < total) {
       // rows that start inside this window: lane j looks at row rbase+1+j, one REDUX turns the starts into a bit mask
       const uint32_t rel = cp[min(rbase + 1 + lane, n)] - cw;
@@ -105,74 +117,79 @@ __device__ __forceinline__ void scan_load(ScanStage &S, const uint32_t c0, const
       rbase += __popc(mask);
       const uint32_t c = cw + lane;
       if (c < total) {
-        const uint2 r = rs[row];
-        const uint32_t b = ((r.x >> WARP_CSH) + (c - cp[row])) << WARP_CSH;      // first slot of my chunk (16*WARP_CH-byte aligned)
-        S.jb[u] = b; S.s[u] = r.x; S.d[u] = r.y; S.rw[u] = (uint32_t)row;
-        if (b < E_al) {
-#pragma unroll
-          for (int h = 0; h < WARP_CH; h++) S.q[u][h] = ldg_stream_u4(ind4 + (b >> 2) + h);
-        } else {                                                               // the last, partial chunk of the array
-          uint32_t tmp[WARP_CS];
-#pragma unroll
-          for (int e = 0; e < WARP_CS; e++) tmp[e] = (b + e < E) ? indices[b + e] : 0u;
-#pragma unroll
-          for (int h = 0; h < WARP_CH; h++) S.q[u][h] = make_uint4(tmp[4 * h], tmp[4 * h + 1], tmp[4 * h + 2], tmp[4 * h + 3]);
-        }
+        const uint32_t rx = rs[row].x, cc = c - cp[row];                         // my chunk is the cc-th aligned chunk of its row
+        S.code[u] = ((uint32_t)row << WARP_OFFBITS) | ((cc << WARP_CSH) + 3u - (rx & 3u));
+        S.q[u] = ldg_stream_u4(ind4 + (rx >> WARP_CSH) + cc);
       }
     }
   }
 }
 
-// Probe one stage and append the kept slots to the staged stream (a per-warp scratch region in global memory that lives in L2).
-// Stream order = window, lane, slot = ascending full-graph slot = CSR order (PS.cpp:420-422).  Per-row facts (kept count; with a
-// self-edge insertion also "kept entries below v" and "v itself kept") are accumulated with one shared-memory atomic per lane.
-// The caller guarantees room for a whole stage, so the OVF == false variant is straight-line code: the windows' probes interleave.
-template <bool ADD_SELF, bool OVF>
-__device__ __forceinline__ void scan_process(const ScanStage &S, uint32_t &cnt, const bucket_t *hb, const int hshift, const uint32_t novf,
-                                             const uint32_t (&ovk)[WARP_OVK > 0 ? WARP_OVK : 1],
-                                             const uint32_t *ovf, const uint32_t *nodes, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
-                                             const uint32_t lt) {
+// Level 2 on the queued chunks [first .. first+count) (count <= 32): exact probe + row-range check per slot, kept edges appended to the
+// staged stream (a per-warp scratch region in global memory that lives in L2).  Stream order = queue order (window, lane), then slot
+// = ascending full-graph slot = CSR order (PS.cpp:420-422).  Per-row facts (kept count; with a self-edge insertion also "kept entries
+// below v" and "v itself kept") are accumulated with one shared-memory atomic per lane.
+template <bool ADD_SELF>
+__device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t *cq_code, const uint32_t first, const uint32_t count,
+                                            const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf, const uint32_t *nodes,
+                                            const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row, uint32_t &cnt, const int lane,
+                                            const uint32_t lt) {
+  const bool active = (uint32_t)lane < count;
+  uint4 q = make_uint4(NONE32, NONE32, NONE32, NONE32);
+  uint32_t code = WARP_OFFMASK;
+  if (active) { q = cq_keys[first + lane]; code = cq_code[first + lane]; }
+  const uint32_t row = code >> WARP_OFFBITS, off0 = (code & WARP_OFFMASK) - 3u;
+  const uint2 r = rs[row];
+  const uint32_t nb[WARP_CS] = {q.x, q.y, q.z, q.w};
+  bool hit[WARP_CS];
+  uint32_t bal[WARP_CS], at = cnt, tot = 0, inc = 0;
+  uint32_t v = 0;
+  if (ADD_SELF) v = nodes[row];
 #pragma unroll
-  for (int u = 0; u < WARP_U; u++) {
-    const uint32_t o = S.jb[u] - S.s[u];            // slots outside [s, s+len) (alignment padding, idle lanes) never match
-    uint32_t nb[WARP_CS];
-    bool hit[WARP_CS];
-#pragma unroll
-    for (int h = 0; h < WARP_CH; h++) { nb[4 * h] = S.q[u][h].x; nb[4 * h + 1] = S.q[u][h].y; nb[4 * h + 2] = S.q[u][h].z; nb[4 * h + 3] = S.q[u][h].w; }
-#pragma unroll
-    for (int e = 0; e < WARP_CS; e++) hit[e] = probe4(hb, hshift, nb[e]);
-    if (!OVF && WARP_OVK > 0) {                                        // up to WARP_OVK overflow keys ride in registers (NONE32 = unused)
-#pragma unroll
-      for (int j = 0; j < WARP_OVK; j++)
-#pragma unroll
-        for (int e = 0; e < WARP_CS; e++) hit[e] |= ovk[j] == nb[e];
-    }
-    if (OVF) {                                                         // keys that did not fit their bucket
+  for (int e = 0; e < WARP_CS; e++) { const uint2 kk = hb[bloom_hash(nb[e]) >> hshift]; hit[e] = (kk.x == nb[e]) | (kk.y == nb[e]); }
 #pragma unroll 1
-      for (uint32_t j = 1; j <= novf; j++) {
-        const uint32_t kv = ovf[j];
+  for (uint32_t j = 0; j < novf; j++) {                // keys that did not fit their bucket (1-2 per subgraph)
+    const uint32_t kv = ovl[j];
 #pragma unroll
-        for (int e = 0; e < WARP_CS; e++) hit[e] |= kv == nb[e];
-      }
-    }
-    uint32_t bal[WARP_CS], at = cnt, tot = 0, inc = 0;
-    uint32_t v = 0;
-    if (ADD_SELF) v = nodes[S.rw[u]];
+    for (int e = 0; e < WARP_CS; e++) hit[e] |= kv == nb[e];
+  }
 #pragma unroll
-    for (int e = 0; e < WARP_CS; e++) {
-      hit[e] = hit[e] && (o + (uint32_t)e < S.d[u]);
-      bal[e] = __ballot_sync(0xffffffffu, hit[e]);
-      at += __popc(bal[e] & lt); tot += __popc(bal[e]);
-      if (ADD_SELF) inc += hit[e] ? (1u + (nb[e] < v ? (1u << 14) : 0u) + (nb[e] == v ? (1u << 28) : 0u)) : 0u;
-      else inc += hit[e] ? 1u : 0u;
-    }
+  for (int e = 0; e < WARP_CS; e++) {
+    hit[e] = hit[e] && (off0 + (uint32_t)e) < r.y;    // member of the node set, slot inside [s, s + len)
+    bal[e] = __ballot_sync(0xffffffffu, hit[e]);
+    at += __popc(bal[e] & lt); tot += __popc(bal[e]);
+    if (ADD_SELF) inc += hit[e] ? (1u + (nb[e] < v ? (1u << 14) : 0u) + (nb[e] == v ? (1u << 28) : 0u)) : 0u;
+    else inc += hit[e] ? 1u : 0u;
+  }
 #pragma unroll
-    for (int e = 0; e < WARP_CS; e++) {
-      if (hit[e]) { sc_ent[at] = make_uint2(nb[e], S.jb[u] + (uint32_t)e); if (ADD_SELF) sc_row[at] = (unsigned short)S.rw[u]; }
-      at += hit[e] ? 1u : 0u;
-    }
-    if (inc) atomicAdd(&rc[S.rw[u]], inc);
-    cnt += tot;
+  for (int e = 0; e < WARP_CS; e++) {
+    if (hit[e]) { sc_ent[at] = make_uint2(nb[e], r.x + off0 + (uint32_t)e); if (ADD_SELF) sc_row[at] = (unsigned short)row; }
+    at += hit[e] ? 1u : 0u;
+  }
+  if (inc) atomicAdd(&rc[row], inc);
+  cnt += tot;
+}
+
+// Level 1 on one window: a lane ORs the Bloom verdicts of its 4 slots; ONE ballot appends the chunks that may hold a member to the queue,
+// a full warp of queued chunks is drained at once.
+template <bool ADD_SELF, int NF>
+__device__ __forceinline__ void scan_window(const uint32_t any, const uint4 q, const uint32_t code, uint4 *cq_keys, uint32_t *cq_code,
+                                            uint32_t &qn, const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf,
+                                            const uint32_t *nodes, const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
+                                            uint32_t &cnt, const int lane, const uint32_t lt) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, any != 0u);
+  if (any) { const uint32_t at = qn + __popc(bal & lt); cq_keys[at] = q; cq_code[at] = code; }
+  qn += __popc(bal);
+  if (qn >= 32u) {
+    __syncwarp();
+    drain_batch<ADD_SELF>(cq_keys, cq_code, 0u, 32u, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+    const uint32_t left = qn - 32u;                  // < 32: move the tail to the front
+    uint4 tk = make_uint4(0u, 0u, 0u, 0u); uint32_t tc = 0;
+    if ((uint32_t)lane < left) { tk = cq_keys[32 + lane]; tc = cq_code[32 + lane]; }
+    __syncwarp();
+    if ((uint32_t)lane < left) { cq_keys[lane] = tk; cq_code[lane] = tc; }
+    qn = left;
+    __syncwarp();
   }
 }
 
@@ -259,15 +276,19 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int *__restrict
   }
 }
 
-template <bool ADD_SELF>
+// NF = Bloom words per lane (1: ncap <= 192, 2: <= 448, 4 above)
+template <bool ADD_SELF, int NF>
 __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(const SampleParams P) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   uint32_t *const nodes = (uint32_t *)(smem_dyn + P.WL.nodes);
   uint2 *const rs = (uint2 *)(smem_dyn + P.WL.rs);                 // {row start, scanned length} of every node
   uint32_t *const cp = (uint32_t *)(smem_dyn + P.WL.cp);           // chunk prefix during the scan, local indptr afterwards
   uint32_t *const rc = (uint32_t *)(smem_dyn + P.WL.rc);           // per row: kept | kept below v << 14 | v kept << 28
-  uint32_t *const hk = (uint32_t *)(smem_dyn + P.WL.hkeys);
+  uint32_t *const hk = (uint32_t *)(smem_dyn + P.WL.hkeys);        // exact membership: buckets of 2 keys
   uint32_t *const ovf = (uint32_t *)(smem_dyn + P.WL.ovf);         // [0] = count, [1..WARP_OVF_CAP] = keys whose bucket was full
+  uint32_t *const fw = (uint32_t *)(smem_dyn + P.WL.bloom);        // Bloom words while they are built (32 * NF)
+  uint4 *const cq_keys = (uint4 *)(smem_dyn + P.WL.queue);         // chunk queue: the 4 keys of a chunk ...
+  uint32_t *const cq_code = (uint32_t *)(cq_keys + WARP_QCAP);     // ... and row << 19 | offset of its first slot in the row + 3
   uint32_t *const rlo = (uint32_t *)(smem_dyn + P.WL.rlo);         // ADD_SELF only: first staged entry / insert position / bug column per row
   uint32_t *const rins = (uint32_t *)(smem_dyn + P.WL.rins);
   uint32_t *const rbug = (uint32_t *)(smem_dyn + P.WL.rbug);
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
   // for every subgraph, so the region stays in L2; keeping it out of shared memory is worth ~10 more resident warps per SM.
   uint2 *const sc_ent = (uint2 *)(P.w_scratch + (size_t)blockIdx.x * P.w_scratch_stride);
   unsigned short *const sc_row = (unsigned short *)(sc_ent + P.w_ecap);
-  const bucket_t *const hb = (const bucket_t *)hk;
+  const uint2 *const hb = (const uint2 *)hk;
   const uint4 *const ind4 = (const uint4 *)P.indices;
   const int lane = threadIdx.x;
   const uint32_t FULL = 0xffffffffu;
@@ -284,7 +305,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
   const int hshift = P.w_hshift;
   const uint32_t ecap = (uint32_t)P.w_ecap;
   const bool ext = !ADD_SELF && !P.fixed_mode;                     // PS.cpp:401: slot `e` is tested whenever no self edge is inserted
-  const uint32_t E = P.num_edges, E_al = E & ~(uint32_t)(WARP_CS - 1);
+  const uint32_t E = P.num_edges;
 
   // The header of a subgraph (ticket -> root, rows reserved -> table extent) is a chain of dependent global round trips; it is fetched
   // one subgraph ahead, each link issued where the previous one has had a whole phase to arrive.
@@ -336,9 +357,11 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     }
     const int n = (int)run + 1;                         // == node_ptr[p+1] - node_ptr[p]
 
-    // ---------------- B: membership hash, chunk prefix ----------------
+    // ---------------- B: Bloom filter + exact table, chunk prefix ----------------
 #pragma unroll 1
-    for (uint32_t i = lane; i < nbuckets * WARP_BK / 4; i += 32) reinterpret_cast<uint4 *>(hk)[i] = make_uint4(NONE32, NONE32, NONE32, NONE32);
+    for (uint32_t i = lane; i < nbuckets / 2; i += 32) reinterpret_cast<uint4 *>(hk)[i] = make_uint4(NONE32, NONE32, NONE32, NONE32);
+#pragma unroll
+    for (int j = 0; j < NF; j++) fw[32 * j + lane] = 0u;
     if (lane == 0) ovf[0] = 0;
     __syncwarp();
     uint32_t total = 0;                                 // chunks of the subgraph
@@ -348,12 +371,13 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       uint32_t ch = 0;
       if (i < n) {
         const uint32_t v = nodes[i];
-        const uint32_t b = (v * 2654435761u) >> hshift;
-        bool done = false;
-#pragma unroll
-        for (int j = 0; j < WARP_BK; j++)
-          if (!done && atomicCAS(&hk[WARP_BK * b + j], NONE32, v) == NONE32) done = true;
-        if (!done) { const uint32_t q = atomicAdd(&ovf[0], 1u); if (q < WARP_OVF_CAP) ovf[1 + q] = v; }
+        const uint32_t h = bloom_hash(v);
+        atomicOr(&fw[bloom_word_index<NF>(h)], bloom_bits(h, bloom_hash2(v)));
+        const uint32_t b = h >> hshift;
+        if (atomicCAS(&hk[2 * b], NONE32, v) != NONE32 && atomicCAS(&hk[2 * b + 1], NONE32, v) != NONE32) {
+          const uint32_t q = atomicAdd(&ovf[0], 1u);
+          if (q < WARP_OVF_CAP) ovf[1 + q] = v;
+        }
         uint2 r = rs[i];
         if (ext && r.x + r.y < E) { r.y += 1; rs[i] = r; }                                       // the PS.cpp:401 slot joins the row
         ch = r.y ? (((r.x + r.y + (WARP_CS - 1)) >> WARP_CSH) - (r.x >> WARP_CSH)) : 1u;          // aligned chunks; every row owns >= 1
@@ -365,51 +389,46 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     }
     if (lane == 0) cp[n] = total;
     __syncwarp();
+    uint32_t f[NF];
+#pragma unroll
+    for (int j = 0; j < NF; j++) f[j] = fw[32 * j + lane];
     p_next = __shfl_sync(FULL, (int)tk_next, 0);
     if (p_next < P.num_subg) { t_next = P.roots[p_next]; node_base_next = P.node_ptr[p_next]; cut_next = P.w_cut[p_next]; }    // consumed after the scan
     const uint32_t novf = ovf[0];
+    const uint32_t *const ovl = ovf + 1;
     bool bail = novf > WARP_OVF_CAP;
 
     // ---------------- C: one pass over the rows in chunk space ----------------
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, qn = 0;
     if (!bail) {
       int rbase = 0;                                    // cp[rbase] <= first chunk of the window <= cp[rbase+1]
-      const uint32_t step = 32u * WARP_U, room = 32u * WARP_U * WARP_CS;      // a stage can keep at most `room` entries
+      const uint32_t step = 32u * WARP_U, room = 32u * (WARP_U + 1) * WARP_CS;      // what a stage can keep at most (incl. the queue's tail)
       ScanStage SA;
-      uint32_t ovk[WARP_OVK > 0 ? WARP_OVK : 1];
-#pragma unroll
-      for (int j = 0; j < (WARP_OVK > 0 ? WARP_OVK : 1); j++) ovk[j] = (WARP_OVK > 0 && (uint32_t)j < novf) ? ovf[1 + j] : NONE32;
-      if (novf <= WARP_OVK) {
 #if WARP_DB
-        // stages double-buffered in registers: the loads of stage i+1 are in flight while stage i is probed
-        ScanStage SB;
-        scan_load(SA, 0u, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-#pragma unroll 1
-        for (uint32_t c0 = 0; c0 < total; c0 += 2u * step) {
-          if (cnt + 2u * room > ecap) { bail = true; break; }
-          const bool more = c0 + step < total;
-          if (more) scan_load(SB, c0 + step, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, false>(SA, cnt, hb, hshift, 0u, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
-          if (!more) break;
-          if (c0 + 2u * step < total) scan_load(SA, c0 + 2u * step, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, false>(SB, cnt, hb, hshift, 0u, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
-        }
-#else
-#pragma unroll 1
-        for (uint32_t c0 = 0; c0 < total; c0 += step) {
-          if (cnt + room > ecap) { bail = true; break; }
-          scan_load(SA, c0, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, false>(SA, cnt, hb, hshift, 0u, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
-        }
+      ScanStage SB;
+      scan_load(SA, 0u, total, rbase, n, lane, le, cp, rs, ind4);
 #endif
-      } else {
 #pragma unroll 1
-        for (uint32_t c0 = 0; c0 < total; c0 += step) {
-          if (cnt + room > ecap) { bail = true; break; }
-          scan_load(SA, c0, total, rbase, n, lane, le, cp, rs, ind4, P.indices, E, E_al);
-          scan_process<ADD_SELF, true>(SA, cnt, hb, hshift, novf, ovk, ovf, nodes, rc, sc_ent, sc_row, lt);
-        }
+      for (uint32_t c0 = 0; c0 < total; c0 += step) {
+        if (cnt + room > ecap) { bail = true; break; }
+#if WARP_DB
+        if (c0 + step < total) scan_load(SB, c0 + step, total, rbase, n, lane, le, cp, rs, ind4);      // in flight while SA is processed
+#else
+        scan_load(SA, c0, total, rbase, n, lane, le, cp, rs, ind4);
+#endif
+        uint32_t any[WARP_U];                           // all Bloom tests of the stage first: 4 * WARP_U independent SHFLs in flight
+#pragma unroll
+        for (int u = 0; u < WARP_U; u++)
+          any[u] = (bloom_test<NF>(f, SA.q[u].x) | bloom_test<NF>(f, SA.q[u].y) | bloom_test<NF>(f, SA.q[u].z) | bloom_test<NF>(f, SA.q[u].w)) & 1u;
+#pragma unroll
+        for (int u = 0; u < WARP_U; u++)
+          scan_window<ADD_SELF, NF>(any[u], SA.q[u], SA.code[u], cq_keys, cq_code, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+#if WARP_DB
+#pragma unroll
+        for (int u = 0; u < WARP_U; u++) { SA.q[u] = SB.q[u]; SA.code[u] = SB.code[u]; }
+#endif
       }
+      if (!bail && qn) { __syncwarp(); drain_batch<ADD_SELF>(cq_keys, cq_code, 0u, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt); }
     }
     __syncwarp();
     if (p_next < P.num_subg) { off_next = P.ppr_ptr[t_next]; row_end_next = P.ppr_ptr[t_next + 1]; }      // consumed before the emit
@@ -433,9 +452,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
               const uint32_t e = rs[i].x + rs[i].y;
               if (e < E) {
                 const uint32_t nb = __ldg(P.indices + e);
-                bool h = probe4(hb, hshift, nb);
-                for (uint32_t j = 1; j <= novf; j++) h |= ovf[j] == nb;
-                if (h) bsub = sub_of(nodes, n, nb);
+                if (probe2(hb, hshift, ovl, novf, nb)) bsub = sub_of(nodes, n, nb);
               }
             }
             rins[i] = present ? NONE32 : ((w >> 14) & 0x3fffu); rbug[i] = bsub;

@@ -181,29 +181,42 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
 }
 
 // per-warp workspace of the single-root PPR fast path (ppr_warp_kernel.cuh)
-static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, int ecap_mult, WarpLayout *W, int *w_ecap, int *w_hbuckets, int *w_hshift) {
+static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, int ecap_mult, WarpLayout *W, int *w_ecap, int *w_nf, int *w_hbuckets, int *w_hshift) {
   uint32_t off = 0;
   auto take = [&](size_t bytes) { uint32_t r = off; off = align16(off + (uint32_t)bytes); return r; };
   // staged edges per warp (global scratch, L2-resident): ecap_mult (16 to start with) per node + one full stage of head room.  A subgraph
   // that overflows is not an error, it takes the redo launch; the multiplier grows when more than 2 % of a launch had to be redone
   const char *env = getenv("SHADOW_WARP_ECAP_MULT");
-  *w_ecap = (env ? std::max(0, atoi(env)) : ecap_mult) * caps.ncap + 32 * WARP_U * WARP_CS * (WARP_DB ? 2 : 1);
-  // 4-key buckets: >= 1 bucket per key; 2-key buckets: >= 3 per key (4 KB either way for k = 150)
+  *w_ecap = (env ? std::max(0, atoi(env)) : ecap_mult) * caps.ncap + 32 * (WARP_U + 1) * WARP_CS;
+  // Bloom words per lane: 1,024 bits per word-register, 2 bits per key: ~7 bits per key keep the false-positive rate near 6 %
+  const char *envf = getenv("SHADOW_WARP_NF");
+  int nf = caps.ncap <= 192 ? 1 : (caps.ncap <= 448 ? 2 : 4);
+  if (envf && (atoi(envf) == 1 || atoi(envf) == 2 || atoi(envf) == 4)) nf = atoi(envf);
+  *w_nf = nf;
+  // exact table: 2-key buckets, >= 3 buckets per key (4 KB for k = 150): 1-2 keys per subgraph overflow their bucket
   const char *envb = getenv("SHADOW_WARP_BUCKET_MULT");
-  *w_hbuckets = std::max(16, next_pow2((envb ? std::max(1, atoi(envb)) : (WARP_BK == 4 ? 1 : 3)) * caps.ncap));
+  *w_hbuckets = std::max(16, next_pow2((envb ? std::max(1, atoi(envb)) : 3) * caps.ncap));
   int lg = 0; while ((1 << lg) < *w_hbuckets) lg++;
   *w_hshift = 32 - lg;
-  W->hkeys = take((size_t)*w_hbuckets * 4 * WARP_BK);
+  W->hkeys = take((size_t)*w_hbuckets * 8);
+  W->queue = take((size_t)WARP_QCAP * 20);                   // chunk queue: uint4 keys + packed (row, offset) codes
   W->rs = take((size_t)caps.ncap * 8);
   W->nodes = take((size_t)caps.ncap * 4);
   W->cp = take(((size_t)caps.ncap + 1) * 4);
   W->rc = take((size_t)caps.ncap * 4);
   W->ovf = take((1 + WARP_OVF_CAP) * 4);
+  W->bloom = take((size_t)32 * nf * 4);                      // Bloom words while they are built
   const bool ins = c.add_self_edge != 0;
   W->rlo = take(ins ? (size_t)caps.ncap * 4 : 0);
   W->rins = take(ins ? (size_t)caps.ncap * 4 : 0);
   W->rbug = take(ins ? (size_t)caps.ncap * 4 : 0);
   W->bytes = off;
+}
+
+typedef void (*warp_kernel_t)(const SampleParams);
+template <bool A>
+static warp_kernel_t pick_warp_kernel(int nf) {
+  return nf == 1 ? ppr_induce_warp_kernel<A, 1> : (nf == 2 ? ppr_induce_warp_kernel<A, 2> : ppr_induce_warp_kernel<A, 4>);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -563,13 +576,15 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   // single-root PPR without hop/drnl labels: one warp per subgraph (ppr_warp_kernel.cuh); whatever does not fit its on-chip
   // staging is rebuilt by the generic kernel in redo mode, launched right behind (it exits at once when the list is empty)
   bool fast = c.method == SHADOW_PPR && c.num_roots == 1 && s->ppr_sorted && !(c.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) && !use_gws &&
-              (((uintptr_t)s->indices & 15) == 0) && caps.ncap <= 8192 && !getenv("SHADOW_NO_WARP_PPR");
+              (((uintptr_t)s->indices & 15) == 0) && caps.ncap <= 8191 && !getenv("SHADOW_NO_WARP_PPR");
   int w_ecap = 0;
-  if (fast) { plan_warp(caps, c, s->warp_ecap_mult, &K.WL, &w_ecap, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024; }
+  int w_nf = 1;
+  if (fast) { long long d; int rcd = graph_dmax(s, &d); if (rcd) return rcd; fast = d + 8 < (1ll << WARP_OFFBITS); }      // packed candidate codes
+  if (fast) { plan_warp(caps, c, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024; }
   if (P > 0) {
     if (use_gws) sample_induce_kernel<true><<<grid, SAMPLER_BLOCK, 0, s->stream>>>(K);
     else if (fast) {
-      auto kern = K.add_self ? ppr_induce_warp_kernel<true> : ppr_induce_warp_kernel<false>;
+      warp_kernel_t kern = K.add_self ? pick_warp_kernel<true>(w_nf) : pick_warp_kernel<false>(w_nf);
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.WL.bytes));
       int wps = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wps, kern, 32, K.WL.bytes));

@@ -28,7 +28,7 @@ struct WsLayout {          // byte offsets of the per-CTA workspace (shared memo
 };
 
 struct WarpLayout {        // byte offsets of the per-warp workspace of ppr_induce_warp_kernel (ppr_warp_kernel.cuh)
-  uint32_t nodes, rs, cp, rc, hkeys, ovf, rlo, rins, rbug;
+  uint32_t nodes, rs, cp, rc, hkeys, ovf, bloom, queue, rlo, rins, rbug;
   uint32_t bytes;
 };
 

@@ -168,6 +168,7 @@ class MinibatchShallowExtractor:
         self.dtype = torch.get_default_dtype()
         self.dim_1hot_hop, self.dim_1hot_ppr, self.dim_1hot_drnl = 5 + 2, 1, 25 + 1        # minibatch.py:246-248
         self.profiler = None
+        self.num_sampler_calls = 0
 
     # ------------------------------------------------------------------ epoch protocol (minibatch.py:252-343)
     def _get_cur_batch_size(self, mode):
@@ -267,6 +268,7 @@ class MinibatchShallowExtractor:
     def par_graph_sample(self, mode):
         """one sampler call -> one super-batch per ensemble branch, features gathered, aug one-hots built (minibatch.py:403-426,469-477)"""
         s = self.graph_sampler[mode]
+        self.num_sampler_calls += 1
         augs = [set(self.aug_feats) & {"hops", "pprs", "drnls"} for _ in self.sampler_cfgs[mode]]
         batches = s.sample_to_device(self.sampler_cfgs[mode], augs)
         for i, b in enumerate(batches):

@@ -316,8 +316,8 @@ def _ppr_tables(indptr, indices, k, eps=1e-5):
     return O.ppr_rows_to_csr(N, alln, nb, sc, ln)
 
 
-@pytest.mark.parametrize("env", [dict(), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_WARP_BUCKET_MULT=1),
-                                 dict(SHADOW_WARP_ECAP_MULT=1, SHADOW_WARP_BUCKET_MULT=1), dict(SHADOW_NO_WARP_PPR=1)])
+@pytest.mark.parametrize("env", [dict(), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_WARP_NF=2, SHADOW_WARP_BUCKET_MULT=1),
+                                 dict(SHADOW_WARP_ECAP_MULT=1, SHADOW_WARP_NF=4), dict(SHADOW_NO_WARP_PPR=1)])
 def test_ppr_warp_path_and_redo_vs_oracle(env):
     """the fast path, its staging-overflow and bucket-overflow hand-over (redo launch of the generic kernel) and the generic
     kernel alone all reproduce the oracle bit for bit: bug-compatible and fixed mode, self edge on/off, thresholds, k=1"""
