@@ -199,6 +199,20 @@ int shadow_spmm_csr_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t
                             int32_t n, int32_t F, float beta, void *cuda_stream);
 int shadow_spmm_csr_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *dY, float *dX,
                             int32_t n, int32_t F, void *cuda_stream);
+/* The Linear of a shaDow layer with its epilogue, hand-written for the 5th-generation tensor cores (csrc/linear_tc.cu: TMA-staged operands,
+ * tcgen05.mma.kind::tf32 with the accumulator in TMEM, error-compensated 3xTF32 products = fp32-level accuracy, epilogue out of tcgen05.ld).
+ * Replaces nn.Linear + F_ACT + norm_feat of shaDow/layers.py:329-338,421,451-452,474-483 (one or two branches per launch: the self and the
+ * neighbour branch of GraphSAGE) and, with act = 1 (identity), do_norm = 0 and W = the transposed weight, the input-gradient product.
+ *   Z   = X[M,K] W[N,K]^T + bias           (saved when Z != NULL)
+ *   o   = norm_feat(act(Z)) over the N <= 256 features (mean / rstd saved when do_norm), or act(Z)
+ *   out = o (out_mode 0) | out + o (1) | atomically added into a zeroed buffer (2: both branches write one tensor)
+ * All pointers 16-byte aligned, leading dimensions and N multiples of 4 floats; otherwise SHADOW_EINVAL. */
+typedef struct shadow_linear_branch {
+  const float *X, *W, *bias, *scale, *offset;
+  float *Z, *out, *mean, *rstd;
+} shadow_linear_branch;
+int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbranch, int64_t ldx, int64_t ldw, int64_t ldz, int64_t ldo, int32_t M,
+                         int32_t N, int32_t K, int32_t act, int32_t do_norm, int32_t out_mode, void *cuda_stream);
 /* act + norm_feat (layers.py:329-338; F_ACT layers.py:26-39): act ids 0 relu, 1 I, 2 elu, 3 tanh, 4 leakyrelu(0.2) */
 int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float *scale, const float *offset, float *out, int32_t ldo,
                             float *mean, float *rstd, int32_t n, int32_t D, int32_t act, int32_t do_norm, int32_t accumulate,

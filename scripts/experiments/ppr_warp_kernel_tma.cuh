@@ -30,30 +30,24 @@
 
 // tuning macros (measured on the S-products stand-in, scripts/explore_variants.py; defaults = the fastest build)
 #ifndef WARP_U
-#define WARP_U 6               // chunk windows in flight per warp (32 chunks each)
+#define WARP_U 4               // chunk windows (32 chunks each) whose Bloom tests are issued together
 #endif
 #ifndef WARP_MIN_BLOCKS
-#define WARP_MIN_BLOCKS 24     // one warp per CTA: resident warps per SM the register budget must allow
+#define WARP_MIN_BLOCKS 20     // one warp per CTA: resident warps per SM the register budget must allow
 #endif
-#ifndef WARP_DB
-#define WARP_DB 0              // 1: the loads of stage i+1 are issued before stage i is processed (two stages of registers)
+#ifndef WARP_K
+#define WARP_K 128             // chunks per TMA stage (2 KB); a multiple of 32 * WARP_U
 #endif
-#define WARP_CS 4              // slots per chunk (one 128-bit load)
+#define WARP_NST 2             // stages: one being scanned, one in flight
+#define WARP_CS 4              // slots per chunk (16 bytes)
 #define WARP_CSH 2
-#define WARP_QCAP 64           // chunk queue: < 32 left over + at most 32 new per window
-#ifndef WARP_OVF_CAP
-#define WARP_OVF_CAP 16        // keys whose 2-key bucket was full
-#endif
+#define WARP_QCAP 192          // candidate queue: < 32 left over + at most 128 new per window (+ head room)
+#define WARP_CBITS 19          // chunks of one subgraph < 2^19 (plan: ncap * (dmax / 4 + 2) must fit)
 
 __device__ __forceinline__ uint32_t lanemask_le() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
   return m;
-}
-__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, int lane) {
@@ -65,17 +59,37 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, int lane) {
   return x;
 }
 
+// ---- 1-D TMA: cp.async.bulk global -> shared, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- level 1: blocked Bloom filter, NF words per lane (32 * NF words = 1024 * NF bits), one SHFL per word-register, 2 bits per key ----
 __device__ __forceinline__ uint32_t bloom_hash(uint32_t key) { return key * 2654435761u; }
-__device__ __forceinline__ uint32_t bloom_hash2(uint32_t key) { return __umulhi(key, 2654435761u); }     // high half of the same product: one IMAD.WIDE gives both
+__device__ __forceinline__ uint32_t bloom_hash2(uint32_t key) { return __umulhi(key, 0x85EBCA6Bu); }
 template <int NF>
 __device__ __forceinline__ uint32_t bloom_word_index(uint32_t h) { return h >> (NF == 1 ? 27 : (NF == 2 ? 26 : 25)); }
 __device__ __forceinline__ uint32_t bloom_bits(uint32_t h, uint32_t g) { return __funnelshift_l(0u, 1u, h) | __funnelshift_l(0u, 1u, g); }   // 1 << h % 32 | 1 << g % 32
 // bit 0 of the result: both bits of `key` are set in its filter word
 template <int NF>
 __device__ __forceinline__ uint32_t bloom_test(const uint32_t (&f)[NF], uint32_t key) {
-  const unsigned long long pr = (unsigned long long)key * 2654435761ull;
-  const uint32_t h = (uint32_t)pr, g = (uint32_t)(pr >> 32), w = bloom_word_index<NF>(h);
+  const uint32_t h = bloom_hash(key), g = bloom_hash2(key), w = bloom_word_index<NF>(h);
   uint32_t fv = __shfl_sync(0xffffffffu, f[0], (int)w);       // source lane = w mod 32
   if (NF >= 2) { const uint32_t f1 = __shfl_sync(0xffffffffu, f[NF >= 2 ? 1 : 0], (int)w); fv = (w & 32u) ? f1 : fv; }
   if (NF == 4) {
@@ -85,113 +99,109 @@ __device__ __forceinline__ uint32_t bloom_test(const uint32_t (&f)[NF], uint32_t
   return __funnelshift_r(fv, 0u, h) & __funnelshift_r(fv, 0u, g);        // (fv >> h % 32) & (fv >> g % 32)
 }
 
-// ---- level 2: exact membership in buckets of 2 keys (one 8-byte shared-memory load); a key whose bucket was full sits in a short overflow list ----
-__device__ __forceinline__ bool probe2(const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf, const uint32_t key) {
-  const uint2 kk = hb[bloom_hash(key) >> hshift];
-  bool hit = (kk.x == key) | (kk.y == key);
-#pragma unroll 1
-  for (uint32_t j = 0; j < novf; j++) hit |= ovl[j] == key;
-  return hit;
-}
-
-#define WARP_OFFBITS 19                                // candidate code = row << 19 | (slot - row start + 3): rows < 8192, scanned length < 2^19 - 8
-#define WARP_OFFMASK ((1u << WARP_OFFBITS) - 1u)
-struct ScanStage {
-  uint4 q[WARP_U];
-  uint32_t code[WARP_U];                             // code of the first slot of my chunk (WARP_OFFMASK for an idle lane: offset beyond any row)
-};
-
-// The aligned 16-byte chunk that holds the last slot of the array may reach up to 12 bytes past indices[E-1]: still inside the allocation
-// (CUDA allocations are 256-byte granular and the array starts 16-byte aligned); those slots are >= E, outside every row range.
-__device__ __forceinline__ void scan_load(ScanStage &S, const uint32_t c0, const uint32_t total, int &rbase, const int n, const int lane,
-                                          const uint32_t le, const uint32_t *cp, const uint2 *rs, const uint4 *ind4) {
-#pragma unroll
-  for (int u = 0; u < WARP_U; u++) {
-    const uint32_t cw = c0 + 32u * u;
-    S.q[u] = make_uint4(NONE32, NONE32, NONE32, NONE32);
-    S.code[u] = WARP_OFFMASK;
-    if (cw < total) {
-      // rows that start inside this window: lane j looks at row rbase+1+j, one REDUX turns the starts into a bit mask
-      const uint32_t rel = cp[min(rbase + 1 + lane, n)] - cw;
-      const uint32_t mask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-      const int row = min(rbase + __popc(mask & le), n - 1);
-      rbase += __popc(mask);
-      const uint32_t c = cw + lane;
-      if (c < total) {
-        const uint32_t rx = rs[row].x, cc = c - cp[row];                         // my chunk is the cc-th aligned chunk of its row
-        S.code[u] = ((uint32_t)row << WARP_OFFBITS) | ((cc << WARP_CSH) + 3u - (rx & 3u));
-        S.q[u] = ldg_stream_u4(ind4 + (rx >> WARP_CSH) + cc);
-      }
-    }
-  }
-}
-
-// Level 2 on the queued chunks [first .. first+count) (count <= 32): exact probe + row-range check per slot, kept edges appended to the
-// staged stream (a per-warp scratch region in global memory that lives in L2).  Stream order = queue order (window, lane), then slot
-// = ascending full-graph slot = CSR order (PS.cpp:420-422).  Per-row facts (kept count; with a self-edge insertion also "kept entries
-// below v" and "v itself kept") are accumulated with one shared-memory atomic per lane.
+// ---- level 2, on 32 queued candidate SLOTS at a time (one per lane): two interleaved bisections -- the row that owns the slot's chunk (over
+// the chunk prefix cp[]) and the key's place in the sorted node list (exact membership AND the sub id, no hash table) -- then the row-range
+// check (the alignment padding of a chunk belongs to the neighbouring rows).  Kept edges are appended to the staged stream {sub id, full-graph
+// slot} (a per-warp scratch region in global memory that lives in L2).  Queue order = (window, lane, slot) = ascending full-graph slot inside
+// every row = CSR order (PS.cpp:420-422).  Per-row facts (kept count; with a self-edge insertion also "kept entries below v" and "v itself
+// kept") are accumulated with one shared-memory atomic per kept edge. ----
 template <bool ADD_SELF>
-__device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t *cq_code, const uint32_t first, const uint32_t count,
-                                            const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf, const uint32_t *nodes,
-                                            const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row, uint32_t &cnt, const int lane,
-                                            const uint32_t lt) {
+__device__ __forceinline__ void drain_batch(const uint2 *cq, const uint32_t count, const uint32_t *nodes, const uint32_t *cp, const int n,
+                                            const uint32_t topstep, const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
+                                            uint32_t &cnt, const int lane, const uint32_t lt) {
   const bool active = (uint32_t)lane < count;
-  uint4 q = make_uint4(NONE32, NONE32, NONE32, NONE32);
-  uint32_t code = WARP_OFFMASK;
-  if (active) { q = cq_keys[first + lane]; code = cq_code[first + lane]; }
-  const uint32_t row = code >> WARP_OFFBITS, off0 = (code & WARP_OFFMASK) - 3u;
-  const uint2 r = rs[row];
-  const uint32_t nb[WARP_CS] = {q.x, q.y, q.z, q.w};
-  bool hit[WARP_CS];
-  uint32_t bal[WARP_CS], at = cnt, tot = 0, inc = 0;
-  uint32_t v = 0;
-  if (ADD_SELF) v = nodes[row];
-#pragma unroll
-  for (int e = 0; e < WARP_CS; e++) { const uint2 kk = hb[bloom_hash(nb[e]) >> hshift]; hit[e] = (kk.x == nb[e]) | (kk.y == nb[e]); }
+  uint2 ent = make_uint2(NONE32, 0u);                  // {key, flat slot = chunk * 4 + position in the chunk}
+  if (active) ent = cq[lane];
+  const uint32_t key = ent.x, c = ent.y >> WARP_CSH;
+  uint32_t row = 0, sub = 0, kv = nodes[0];            // last row with cp[row] <= c (cp[n] = total > c); last node with nodes[sub] <= key
 #pragma unroll 1
-  for (uint32_t j = 0; j < novf; j++) {                // keys that did not fit their bucket (1-2 per subgraph)
-    const uint32_t kv = ovl[j];
-#pragma unroll
-    for (int e = 0; e < WARP_CS; e++) hit[e] |= kv == nb[e];
+  for (uint32_t step = topstep; step; step >>= 1) {
+    const uint32_t ir = min(row + step, (uint32_t)n), is = min(sub + step, (uint32_t)n - 1u);
+    const uint32_t cv = cp[ir], nv = nodes[is];
+    if (cv <= c) row = ir;
+    if (nv <= key) { sub = is; kv = nv; }
   }
-#pragma unroll
-  for (int e = 0; e < WARP_CS; e++) {
-    hit[e] = hit[e] && (off0 + (uint32_t)e) < r.y;    // member of the node set, slot inside [s, s + len)
-    bal[e] = __ballot_sync(0xffffffffu, hit[e]);
-    at += __popc(bal[e] & lt); tot += __popc(bal[e]);
-    if (ADD_SELF) inc += hit[e] ? (1u + (nb[e] < v ? (1u << 14) : 0u) + (nb[e] == v ? (1u << 28) : 0u)) : 0u;
-    else inc += hit[e] ? 1u : 0u;
+  const uint2 r = rs[row];
+  const uint32_t off = ent.y - (cp[row] << WARP_CSH) - (r.x & 3u);        // slot relative to the row start (wraps for the padding in front of it)
+  const bool hit = active && kv == key && off < r.y;                       // member of the node set, slot inside [s, s + len)
+  const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+  if (hit) {
+    const uint32_t at = cnt + __popc(bal & lt);
+    sc_ent[at] = make_uint2(sub, r.x + off);
+    if (ADD_SELF) { sc_row[at] = (unsigned short)row; atomicAdd(&rc[row], 1u + (sub < row ? (1u << 14) : 0u) + (sub == row ? (1u << 28) : 0u)); }   // ids sorted: sub < row <=> id < v
+    else atomicAdd(&rc[row], 1u);
   }
-#pragma unroll
-  for (int e = 0; e < WARP_CS; e++) {
-    if (hit[e]) { sc_ent[at] = make_uint2(nb[e], r.x + off0 + (uint32_t)e); if (ADD_SELF) sc_row[at] = (unsigned short)row; }
-    at += hit[e] ? 1u : 0u;
-  }
-  if (inc) atomicAdd(&rc[row], inc);
-  cnt += tot;
+  cnt += __popc(bal);
 }
 
-// Level 1 on one window: a lane ORs the Bloom verdicts of its 4 slots; ONE ballot appends the chunks that may hold a member to the queue,
-// a full warp of queued chunks is drained at once.
-template <bool ADD_SELF, int NF>
-__device__ __forceinline__ void scan_window(const uint32_t any, const uint4 q, const uint32_t code, uint4 *cq_keys, uint32_t *cq_code,
-                                            uint32_t &qn, const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf,
-                                            const uint32_t *nodes, const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
+// sub id of `key` in the sorted node list, or NONE32
+__device__ __forceinline__ uint32_t find_sub(const uint32_t *nodes, const int n, const uint32_t topstep, const uint32_t key) {
+  uint32_t sub = 0, kv = nodes[0];
+#pragma unroll 1
+  for (uint32_t step = topstep; step; step >>= 1) {
+    const uint32_t is = min(sub + step, (uint32_t)n - 1u), nv = nodes[is];
+    if (nv <= key) { sub = is; kv = nv; }
+  }
+  return kv == key ? sub : NONE32;
+}
+
+// Level 1 on one window: the Bloom verdict of each of a lane's 4 slots; 4 ballots append the slots that may hold a member to the queue in
+// (lane, slot) order; full warps of queued candidates are drained at once.
+template <bool ADD_SELF>
+__device__ __forceinline__ void scan_window(const uint32_t v0, const uint32_t v1, const uint32_t v2, const uint32_t v3, const uint4 q,
+                                            const uint32_t code, uint2 *cq, uint32_t &qn, const uint32_t *nodes, const uint32_t *cp, const int n,
+                                            const uint32_t topstep, const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
                                             uint32_t &cnt, const int lane, const uint32_t lt) {
-  const uint32_t bal = __ballot_sync(0xffffffffu, any != 0u);
-  if (any) { const uint32_t at = qn + __popc(bal & lt); cq_keys[at] = q; cq_code[at] = code; }
-  qn += __popc(bal);
+  const uint32_t b0 = __ballot_sync(0xffffffffu, v0 != 0u), b1 = __ballot_sync(0xffffffffu, v1 != 0u);
+  const uint32_t b2 = __ballot_sync(0xffffffffu, v2 != 0u), b3 = __ballot_sync(0xffffffffu, v3 != 0u);
+  uint32_t at = qn + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+  if (v0) cq[at] = make_uint2(q.x, code);
+  at += v0;
+  if (v1) cq[at] = make_uint2(q.y, code + 1u);
+  at += v1;
+  if (v2) cq[at] = make_uint2(q.z, code + 2u);
+  at += v2;
+  if (v3) cq[at] = make_uint2(q.w, code + 3u);
+  qn += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
   if (qn >= 32u) {
     __syncwarp();
-    drain_batch<ADD_SELF>(cq_keys, cq_code, 0u, 32u, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
-    const uint32_t left = qn - 32u;                  // < 32: move the tail to the front
-    uint4 tk = make_uint4(0u, 0u, 0u, 0u); uint32_t tc = 0;
-    if ((uint32_t)lane < left) { tk = cq_keys[32 + lane]; tc = cq_code[32 + lane]; }
+    uint32_t head = 0;
+#pragma unroll 1
+    do {
+      drain_batch<ADD_SELF>(cq + head, 32u, nodes, cp, n, topstep, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+      head += 32u; qn -= 32u;
+    } while (qn >= 32u);
+    uint2 tk = make_uint2(0u, 0u);                   // < 32 left: move the tail to the front
+    if ((uint32_t)lane < qn) tk = cq[head + lane];
     __syncwarp();
-    if ((uint32_t)lane < left) { cq_keys[lane] = tk; cq_code[lane] = tc; }
-    qn = left;
+    if ((uint32_t)lane < qn) cq[lane] = tk;
     __syncwarp();
   }
+}
+
+// One TMA stage = chunks [c0, hi_c) of the subgraph's flat chunk space.  The rows tile that space back to back, so every row (piece) that
+// falls into the stage is ONE cp.async.bulk issued by one lane: source = the row's aligned chunks in the full-graph CSR, destination = its place
+// in the stage buffer.  rb = the row that owns chunk c0 on entry, the row that owns chunk hi_c on exit.
+__device__ __forceinline__ void issue_stage(const uint32_t c0, const uint32_t hi_c, int &rb, const int n, const uint32_t total, const int lane,
+                                            const uint32_t *cp, const uint2 *rs, const uint4 *ind4, const uint32_t last_chunk, uint4 *buf, uint64_t *bar) {
+  if (lane == 0) mbar_expect_tx(bar, (hi_c - c0) * 16u);
+  __syncwarp();
+  int rb_next = rb;
+#pragma unroll 1
+  for (int r0 = rb;; r0 += 32) {
+    const int r = r0 + lane;
+    uint32_t lo = total, hi = total;
+    if (r < n) { lo = cp[r]; hi = cp[r + 1]; }
+    if (lo < hi_c) {                                    // (hi > c0 holds for every row from rb on; every row owns >= 1 chunk)
+      const uint32_t a = max(lo, c0), b = min(hi, hi_c);
+      // (an empty row behind the last edge owns a chunk too: its source is clamped to the last chunk of the array)
+      bulk_g2s(buf + (a - c0), ind4 + min(rs[r].x >> WARP_CSH, last_chunk) + (a - lo), (b - a) * 16u, bar);
+    }
+    const uint32_t own = __ballot_sync(0xffffffffu, lo <= hi_c && hi_c < hi);       // at most one row owns chunk hi_c
+    if (own) rb_next = r0 + __ffs(own) - 1;
+    if (!__shfl_sync(0xffffffffu, lo < hi_c ? 1 : 0, 31)) break;                     // rows are ordered by their first chunk
+  }
+  rb = rb_next;
 }
 
 // first position IN SCORE ORDER whose score fails the relative threshold (PS.cpp:584), or size_neigh; warp-uniform result
@@ -285,28 +295,32 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
   uint2 *const rs = (uint2 *)(smem_dyn + P.WL.rs);                 // {row start, scanned length} of every node
   uint32_t *const cp = (uint32_t *)(smem_dyn + P.WL.cp);           // chunk prefix during the scan, local indptr afterwards
   uint32_t *const rc = (uint32_t *)(smem_dyn + P.WL.rc);           // per row: kept | kept below v << 14 | v kept << 28
-  uint32_t *const hk = (uint32_t *)(smem_dyn + P.WL.hkeys);        // exact membership: buckets of 2 keys
-  uint32_t *const ovf = (uint32_t *)(smem_dyn + P.WL.ovf);         // [0] = count, [1..WARP_OVF_CAP] = keys whose bucket was full
   uint32_t *const fw = (uint32_t *)(smem_dyn + P.WL.bloom);        // Bloom words while they are built (32 * NF)
-  uint4 *const cq_keys = (uint4 *)(smem_dyn + P.WL.queue);         // chunk queue: the 4 keys of a chunk ...
-  uint32_t *const cq_code = (uint32_t *)(cq_keys + WARP_QCAP);     // ... and row << 19 | offset of its first slot in the row + 3
+  uint2 *const cq = (uint2 *)(smem_dyn + P.WL.queue);              // candidate queue: {key, flat slot} of every slot that passed the Bloom filter
+  uint4 *const stage = (uint4 *)(smem_dyn + P.WL.stage);           // WARP_NST TMA stage buffers of WARP_K chunks
+  uint64_t *const bars = (uint64_t *)(smem_dyn + P.WL.bars);       // one mbarrier per stage
   uint32_t *const rlo = (uint32_t *)(smem_dyn + P.WL.rlo);         // ADD_SELF only: first staged entry / insert position / bug column per row
   uint32_t *const rins = (uint32_t *)(smem_dyn + P.WL.rins);
   uint32_t *const rbug = (uint32_t *)(smem_dyn + P.WL.rbug);
-  // staged kept edges {neighbour id, full-graph slot} (+ row), CSR order: per-warp scratch in global memory.  A warp reuses its few KB
-  // for every subgraph, so the region stays in L2; keeping it out of shared memory is worth ~10 more resident warps per SM.
+  // staged kept edges {sub id, full-graph slot} (+ row), CSR order: per-warp scratch in global memory.  A warp reuses its few KB
+  // for every subgraph, so the region stays in L2.
   uint2 *const sc_ent = (uint2 *)(P.w_scratch + (size_t)blockIdx.x * P.w_scratch_stride);
   unsigned short *const sc_row = (unsigned short *)(sc_ent + P.w_ecap);
-  const uint2 *const hb = (const uint2 *)hk;
   const uint4 *const ind4 = (const uint4 *)P.indices;
   const int lane = threadIdx.x;
   const uint32_t FULL = 0xffffffffu;
-  const uint32_t lt = lanemask_lt(), le = lanemask_le();
-  const uint32_t nbuckets = (uint32_t)P.w_hbuckets;
-  const int hshift = P.w_hshift;
+  const uint32_t lt = lanemask_lt();
   const uint32_t ecap = (uint32_t)P.w_ecap;
   const bool ext = !ADD_SELF && !P.fixed_mode;                     // PS.cpp:401: slot `e` is tested whenever no self edge is inserted
   const uint32_t E = P.num_edges;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < WARP_NST; j++) mbar_init(bars + j, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t ph = 0;                                                  // bit j = parity the next wait on stage j expects
 
   // The header of a subgraph (ticket -> root, rows reserved -> table extent) is a chain of dependent global round trips; it is fetched
   // one subgraph ahead, each link issued where the previous one has had a whole phase to arrive.
@@ -356,14 +370,11 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       const uint32_t s = P.indptr[t];
       rs[n_below] = make_uint2(s, P.indptr[t + 1] - s);
     }
-    const int n = (int)run + 1;                         // == node_ptr[p+1] - node_ptr[p]
+    const int n = (int)run + 1;                         // == node_ptr[p+1] - node_ptr[p]; the root is node n_below
 
-    // ---------------- B: Bloom filter + exact table, chunk prefix ----------------
-#pragma unroll 1
-    for (uint32_t i = lane; i < nbuckets / 2; i += 32) reinterpret_cast<uint4 *>(hk)[i] = make_uint4(NONE32, NONE32, NONE32, NONE32);
+    // ---------------- B: Bloom filter, chunk prefix ----------------
 #pragma unroll
     for (int j = 0; j < NF; j++) fw[32 * j + lane] = 0u;
-    if (lane == 0) ovf[0] = 0;
     __syncwarp();
     uint32_t total = 0;                                 // chunks of the subgraph
 #pragma unroll 1
@@ -374,11 +385,6 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
         const uint32_t v = nodes[i];
         const uint32_t h = bloom_hash(v);
         atomicOr(&fw[bloom_word_index<NF>(h)], bloom_bits(h, bloom_hash2(v)));
-        const uint32_t b = h >> hshift;
-        if (atomicCAS(&hk[2 * b], NONE32, v) != NONE32 && atomicCAS(&hk[2 * b + 1], NONE32, v) != NONE32) {
-          const uint32_t q = atomicAdd(&ovf[0], 1u);
-          if (q < WARP_OVF_CAP) ovf[1 + q] = v;
-        }
         uint2 r = rs[i];
         if (ext && r.x + r.y < E) { r.y += 1; rs[i] = r; }                                       // the PS.cpp:401 slot joins the row
         ch = r.y ? (((r.x + r.y + (WARP_CS - 1)) >> WARP_CSH) - (r.x >> WARP_CSH)) : 1u;          // aligned chunks; every row owns >= 1
@@ -395,41 +401,59 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     for (int j = 0; j < NF; j++) f[j] = fw[32 * j + lane];
     p_next = __shfl_sync(FULL, (int)tk_next, 0);
     if (p_next < P.num_subg) { t_next = P.roots[p_next]; node_base_next = P.node_ptr[p_next]; cut_next = P.w_cut[p_next]; }    // consumed after the scan
-    const uint32_t novf = ovf[0];
-    const uint32_t *const ovl = ovf + 1;
-    bool bail = novf > WARP_OVF_CAP;
+    bool bail = total >= (1u << WARP_CBITS);
+    uint32_t topstep = 0;                               // bisections over cp[0..n-1] / nodes[0..n-1]: largest power of two <= n - 1
+    if (n > 1) topstep = 1u << (31 - __clz(n - 1));
 
-    // ---------------- C: one pass over the rows in chunk space ----------------
+    // ---------------- C: one pass over the rows in chunk space, the rows staged in shared memory by TMA ----------------
     uint32_t cnt = 0, qn = 0;
     if (!bail) {
-      int rbase = 0;                                    // cp[rbase] <= first chunk of the window <= cp[rbase+1]
-      const uint32_t step = 32u * WARP_U, room = 32u * (WARP_U + 1) * WARP_CS;      // what a stage can keep at most (incl. the queue's tail)
-      ScanStage SA;
-#if WARP_DB
-      ScanStage SB;
-      scan_load(SA, 0u, total, rbase, n, lane, le, cp, rs, ind4);
-#endif
+      const uint32_t nstages = (total + WARP_K - 1) / WARP_K;
+      const uint32_t room = 32u * (WARP_U * WARP_CS + 1);          // what a group of windows can keep at most (incl. the queue's tail)
+      int rb = 0;                                                   // row that owns the first chunk of the next stage to issue
+      uint32_t issued = 0;
+      for (; issued < nstages && issued < WARP_NST; issued++)
+        issue_stage(issued * WARP_K, min(total, (issued + 1) * WARP_K), rb, n, total, lane, cp, rs, ind4, (E - 1u) >> WARP_CSH, stage + (issued % WARP_NST) * WARP_K, bars + (issued % WARP_NST));
+      uint32_t i = 0;
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < total; c0 += step) {
-        if (cnt + room > ecap) { bail = true; break; }
-#if WARP_DB
-        if (c0 + step < total) scan_load(SB, c0 + step, total, rbase, n, lane, le, cp, rs, ind4);      // in flight while SA is processed
-#else
-        scan_load(SA, c0, total, rbase, n, lane, le, cp, rs, ind4);
-#endif
-        uint32_t any[WARP_U];                           // all Bloom tests of the stage first: 4 * WARP_U independent SHFLs in flight
+      for (; i < nstages && !bail; i++) {
+        const uint32_t st = i % WARP_NST, c0 = i * WARP_K, hi_c = min(total, c0 + WARP_K);
+        mbar_wait(bars + st, (ph >> st) & 1u);
+        ph ^= 1u << st;
+        const uint4 *const buf = stage + st * WARP_K;
+#pragma unroll 1
+        for (uint32_t w0 = 0; c0 + w0 < hi_c; w0 += 32u * WARP_U) {
+          if (cnt + room > ecap) { bail = true; break; }
+          uint4 q[WARP_U];
+          uint32_t cc[WARP_U], v[WARP_U][WARP_CS];
 #pragma unroll
-        for (int u = 0; u < WARP_U; u++)
-          any[u] = (bloom_test<NF>(f, SA.q[u].x) | bloom_test<NF>(f, SA.q[u].y) | bloom_test<NF>(f, SA.q[u].z) | bloom_test<NF>(f, SA.q[u].w)) & 1u;
+          for (int u = 0; u < WARP_U; u++) {
+            const uint32_t ci = w0 + 32u * u + lane;
+            cc[u] = c0 + ci;
+            q[u] = buf[ci];                             // (chunks beyond hi_c hold stale data: masked below)
+          }
 #pragma unroll
-        for (int u = 0; u < WARP_U; u++)
-          scan_window<ADD_SELF, NF>(any[u], SA.q[u], SA.code[u], cq_keys, cq_code, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
-#if WARP_DB
+          for (int u = 0; u < WARP_U; u++) {            // all Bloom tests of the group first: 4 * WARP_U independent SHFLs in flight
+            const uint32_t ok = cc[u] < hi_c ? 1u : 0u;
+            v[u][0] = bloom_test<NF>(f, q[u].x) & ok; v[u][1] = bloom_test<NF>(f, q[u].y) & ok;
+            v[u][2] = bloom_test<NF>(f, q[u].z) & ok; v[u][3] = bloom_test<NF>(f, q[u].w) & ok;
+          }
 #pragma unroll
-        for (int u = 0; u < WARP_U; u++) { SA.q[u] = SB.q[u]; SA.code[u] = SB.code[u]; }
-#endif
+          for (int u = 0; u < WARP_U; u++)
+            scan_window<ADD_SELF>(v[u][0], v[u][1], v[u][2], v[u][3], q[u], cc[u] << WARP_CSH, cq, qn, nodes, cp, n, topstep, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+        }
+        __syncwarp();                                   // every lane is done reading the buffer before TMA refills it
+        if (!bail && issued < nstages) {
+          issue_stage(issued * WARP_K, min(total, (issued + 1) * WARP_K), rb, n, total, lane, cp, rs, ind4, (E - 1u) >> WARP_CSH, stage + st * WARP_K, bars + st);
+          issued++;
+        }
       }
-      if (!bail && qn) { __syncwarp(); drain_batch<ADD_SELF>(cq_keys, cq_code, 0u, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt); }
+      if (bail) {                                       // copies still in flight must land before the buffers are reused
+        for (; i < issued; i++) { const uint32_t st = i % WARP_NST; mbar_wait(bars + st, (ph >> st) & 1u); ph ^= 1u << st; }
+      } else if (qn) {
+        __syncwarp();
+        drain_batch<ADD_SELF>(cq, qn, nodes, cp, n, topstep, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+      }
     }
     __syncwarp();
     if (p_next < P.num_subg) { off_next = P.ppr_ptr[t_next]; row_end_next = P.ppr_ptr[t_next + 1]; }      // consumed before the emit
@@ -451,10 +475,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
             uint32_t bsub = NONE32;
             if (present && !P.fixed_mode) {             // no insertion => slot e is tested too (:401)
               const uint32_t e = rs[i].x + rs[i].y;
-              if (e < E) {
-                const uint32_t nb = __ldg(P.indices + e);
-                if (probe2(hb, hshift, ovl, novf, nb)) bsub = sub_of(nodes, n, nb);
-              }
+              if (e < E) bsub = find_sub(nodes, n, topstep, __ldg(P.indices + e));
             }
             rins[i] = present ? NONE32 : ((w >> 14) & 0x3fffu); rbug[i] = bsub;
             c_i = k_i + (present ? 0u : 1u) + (bsub != NONE32 ? 1u : 0u);
@@ -496,7 +517,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     }
     if (lane == 0) {
       P.edge_span[p] = make_int2((int)edge_base, (int)(edge_base + m)); P.num_target[p] = 1;
-      P.target[p] = (int)(node_base + sub_of(nodes, n, t));
+      P.target[p] = (int)(node_base + n_below);
     }
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) P.row_span[node_base + i] = make_int2((int)(edge_base + cp[i]), (int)(edge_base + cp[i + 1]));
@@ -507,9 +528,9 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       long long pos = edge_base + g;
       if (ADD_SELF) {
         const uint32_t row = __ldcg(sc_row + g);
-        pos = edge_base + cp[row] + (g - rlo[row]) + ((rins[row] != NONE32 && ent.x > nodes[row]) ? 1 : 0);
+        pos = edge_base + cp[row] + (g - rlo[row]) + ((rins[row] != NONE32 && ent.x > row) ? 1 : 0);
       }
-      P.indices_out[pos] = (int)(node_base + sub_of(nodes, n, ent.x));
+      P.indices_out[pos] = (int)(node_base + ent.x);
       P.orig_edge[pos] = ent.y;                                                                   // :422
     }
     if (ADD_SELF) {

@@ -30,6 +30,11 @@ class BatchInfo(C.Structure):
                 ("has_drnl", C.c_int32), ("rand_draws", C.c_int64)]
 
 
+class LinearBranch(C.Structure):
+    """shadow_linear_branch"""
+    _fields_ = [(n, C.c_void_p) for n in ("X", "W", "bias", "scale", "offset", "Z", "out", "mean", "rstd")]
+
+
 METHOD = {"khop": 0, "ppr": 1, "ppr_st": 2, "nodeIID": 3}
 AUG = {"hops": 1, "pprs": 2, "drnls": 4}
 RNG_GLIBC, RNG_PHILOX = 0, 1
@@ -50,7 +55,7 @@ SYMBOLS = [
     "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32",
     "shadow_gat_fwd_f32", "shadow_gat_bwd_f32", "shadow_segment_pool_fwd_f32", "shadow_segment_pool_bwd_f32",
     "shadow_adam_clip_step_f32", "shadow_gemm_tf32x3_f32", "shadow_gemm_tf32x3_pair_f32",
-    "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32",
+    "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32", "shadow_linear_tc_f32",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -102,6 +107,7 @@ lib.shadow_gemm_tf32x3_pair_f32.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _i32
 lib.shadow_linear_umma_fwd_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_dgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_wgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]
+lib.shadow_linear_tc_f32.argtypes = [C.POINTER(LinearBranch), _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
 lib.shadow_adam_clip_step_f32.argtypes = [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]
 
 

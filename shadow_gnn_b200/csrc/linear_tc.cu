@@ -1,0 +1,344 @@
+// linear_tc.cu -- the dense Linear of the shaDow layers (shaDow/layers.py:329-338,421,451-452,474-483) on the 5th-generation tensor
+// cores, hand-written for sm_100a: TMA-staged operands, tcgen05.mma with the accumulator in TMEM, fused epilogue out of tcgen05.ld.
+//
+//     Z   = X W^T + b                                  X [M, K]  W [N, K]  (both K-major, fp32)         N <= 256
+//     out = [out +] norm_feat(act(Z))                  norm_feat over the N features of a row, learned scale / offset
+//
+// One CTA owns 128 rows and ALL N (<= 256) columns: its fp32 accumulator is 128 lanes x N columns of TMEM (256 of the 512 columns), so the
+// row statistics of norm_feat never leave the SM.  The reference is fp32 (1e-3 layer budget over 5 layers), so every product is an
+// error-compensated 3xTF32 sum: each fp32 operand tile that TMA lands in shared memory (128B-swizzled, K-major) is split IN PLACE into
+// hi = the value with its low 13 mantissa bits cleared (exactly what a TF32 tensor core reads) and lo = x - hi (exact in fp32) in a second
+// tile at the same offsets, and three tcgen05.mma.kind::tf32 run per 8-wide k-step:  hi*lo + lo*hi + hi*hi  (small terms first).
+//
+// Warp roles (192 threads):  warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocation + MMA issue (one elected lane),
+// warps 2-5 = split the landed tiles (the "transform" stage), then the epilogue: each thread owns one accumulator row (TMEM lane),
+// three passes over its N columns (sum -> mean, squared deviations -> rstd, normalise + store), bias / activation applied on the fly.
+// Pipeline: 2 stages x (A hi/lo 2 x 16 KB + B hi/lo 2 x 32 KB) = 192 KB of shared memory; mbarriers full (TMA -> transform),
+// ready (transform -> MMA), empty (tcgen05.commit -> producer), acc (last commit -> epilogue).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/shadow_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;          // rows per CTA = TMEM lanes
+constexpr int BLOCK_N = 256;          // columns per CTA = TMEM columns (fp32)
+constexpr int BLOCK_K = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;             // tf32: 32 bytes per MMA k-step
+constexpr int NSTAGES = 2;
+constexpr int A_TILE = BLOCK_M * BLOCK_K * 4;      // 16 KB
+constexpr int B_TILE = BLOCK_N * BLOCK_K * 4;      // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + 3 * BLOCK_N * 4 /*bias, scale, offset*/;
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused: 1) << 16 | SBO (8 rows x 128 B
+// = 1024 B) >> 4 << 32 | version 1 << 46 | layout 2 (SWIZZLE_128B) << 61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 << 17, M >> 4 << 24
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {      // arrives on `bar` once every MMA issued so far has completed (implies fence::before_thread_sync)
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+enum { ACT_RELU = 0, ACT_I = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_LRELU = 4 };
+template <int ACT>
+__device__ __forceinline__ float act_f(float z) {
+  if (ACT == ACT_RELU) return z > 0.f ? z : 0.f;
+  if (ACT == ACT_ELU) return z > 0.f ? z : expm1f(z);
+  if (ACT == ACT_TANH) return tanhf(z);
+  if (ACT == ACT_LRELU) return z > 0.f ? z : 0.2f * z;
+  return z;
+}
+
+// One launch = up to two products of the same shape (the self and the neighbour branch of a GraphSAGE layer, layers.py:474-483; blockIdx.y).
+struct LinearBranch {
+  const float *bias, *scale, *offset;      // [N] each (bias may be NULL; scale / offset only with norm_feat)
+  float *Z, *out, *mean, *rstd;            // Z [M, ldz] pre-activation (saved for backward; may be NULL), out [M, ldo], mean / rstd [M] (NULL without norm)
+};
+struct LinearParams {
+  LinearBranch br[2];
+  int ldz, ldo, M, N, K, act, do_norm;
+  int out_mode;                            // 0: out = o   1: out += o (one branch per launch)   2: red.global.add (both branches into one zeroed buffer)
+};
+
+__device__ __forceinline__ void store_out4(float *p, const float4 v, const int mode) {
+  if (mode == 0) *reinterpret_cast<float4 *>(p) = v;
+  else if (mode == 1) { float4 o = *reinterpret_cast<const float4 *>(p); o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w; *reinterpret_cast<float4 *>(p) = o; }
+  else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int ACT, bool NORM>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_x1,
+                 const __grid_constant__ CUtensorMap map_w1, const LinearParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B atoms are 1024-byte aligned
+  uint64_t *bars = (uint64_t *)(smem + NSTAGES * STAGE_BYTES);
+  uint64_t *full = bars, *ready = bars + NSTAGES, *empty = bars + 2 * NSTAGES, *acc = bars + 3 * NSTAGES;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 3 * NSTAGES + 1);
+  float *vecs = (float *)(bars + 3 * NSTAGES + 2);                 // bias / scale / offset of this branch (3 x BLOCK_N floats)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int num_kb = (P.K + BLOCK_K - 1) / BLOCK_K;
+  const CUtensorMap *map_x = blockIdx.y ? &map_x1 : &map_x0, *map_w = blockIdx.y ? &map_w1 : &map_w0;
+  const LinearBranch B = P.br[blockIdx.y];
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_w) : "memory");
+    for (int s = 0; s < NSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                   // TMEM: 256 columns x 128 lanes of fp32 accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BLOCK_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < BLOCK_N; i += NUM_THREADS) {
+    const bool in = i < P.N;
+    vecs[i] = (in && B.bias) ? B.bias[i] : 0.f;
+    vecs[BLOCK_N + i] = (in && NORM) ? B.scale[i] : 1.f;
+    vecs[2 * BLOCK_N + i] = (in && NORM) ? B.offset[i] : 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % NSTAGES;
+        mbar_wait(&empty[s], ((kb / NSTAGES) & 1) ^ 1);
+        unsigned char *st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], A_TILE + B_TILE);
+        tma_load_2d(st, map_x, &full[s], kb * BLOCK_K, m0);                       // A hi  [128 rows][32 k]
+        tma_load_2d(st + 2 * A_TILE, map_w, &full[s], kb * BLOCK_K, 0);           // B hi  [256 rows][32 k]
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(BLOCK_M, BLOCK_N);
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % NSTAGES;
+        mbar_wait(&ready[s], (kb / NSTAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_TILE, b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+          const uint32_t ko = k * UMMA_K * 4;          // byte offset of the k-step inside the 128-byte swizzle row
+          umma_tf32(tmem_base, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, (kb | k) ? 1u : 0u);
+          umma_tf32(tmem_base, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+          umma_tf32(tmem_base, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+        }
+        umma_commit(&empty[s]);                        // the stage's shared memory is free once these MMAs have read it
+      }
+      umma_commit(acc);                                // accumulator complete
+    }
+  } else {
+    // ===== transform warps (2..5): split every landed tile into hi / lo in place =====
+    const int t = threadIdx.x - 64;                    // 0..127
+    for (int kb = 0; kb < num_kb; kb++) {
+      const int s = kb % NSTAGES;
+      mbar_wait(&full[s], (kb / NSTAGES) & 1);
+      float4 *a_hi = (float4 *)(smem + s * STAGE_BYTES), *a_lo = a_hi + A_TILE / 16, *b_hi = a_hi + 2 * A_TILE / 16, *b_lo = b_hi + B_TILE / 16;
+#pragma unroll 4
+      for (int i = t; i < A_TILE / 16; i += 128) {
+        const float4 v = a_hi[i];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        a_hi[i] = h; a_lo[i] = l;
+      }
+#pragma unroll 4
+      for (int i = t; i < B_TILE / 16; i += 128) {
+        const float4 v = b_hi[i];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        b_hi[i] = h; b_lo[i] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&ready[s]);
+    }
+
+    // ===== epilogue: thread <-> accumulator row (TMEM lane); a warp may only touch lanes 32 * (warp % 4) .. + 31 =====
+    mbar_wait(acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int N = P.N;
+    const bool live = row < P.M;
+    const float *vb = vecs, *vs = vecs + BLOCK_N, *vo = vecs + 2 * BLOCK_N;
+    float mean = 0.f, rstd = 1.f;
+    uint32_t r[32];
+    if (NORM) {
+      float s1 = 0.f;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        tmem_ld32(taddr + c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (c0 + j < N) s1 += act_f<ACT>(__uint_as_float(r[j]) + vb[c0 + j]);
+      }
+      mean = s1 / (float)N;
+      float s2 = 0.f;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        tmem_ld32(taddr + c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (c0 + j < N) { const float d = act_f<ACT>(__uint_as_float(r[j]) + vb[c0 + j]) - mean; s2 += d * d; }
+      }
+      rstd = rsqrtf(s2 / (float)N + 1e-9f);
+      if (live && B.mean) { B.mean[row] = mean; B.rstd[row] = rstd; }
+    }
+    for (int c0 = 0; c0 < N; c0 += 32) {               // N is a multiple of 4: whole float4 groups
+      tmem_ld32(taddr + c0, r);
+      if (live) {
+        float *zrow = B.Z ? B.Z + (size_t)row * P.ldz + c0 : nullptr;
+        float *orow = B.out + (size_t)row * P.ldo + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (c0 + j < N) {
+            float z[4], o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              z[q] = __uint_as_float(r[j + q]) + vb[c0 + j + q];
+              o[q] = act_f<ACT>(z[q]);
+              if (NORM) o[q] = (o[q] - mean) * vs[c0 + j + q] * rstd + vo[c0 + j + q];
+            }
+            if (zrow) *reinterpret_cast<float4 *>(zrow + j) = make_float4(z[0], z[1], z[2], z[3]);
+            store_out4(orow + j, make_float4(o[0], o[1], o[2], o[3]), P.out_mode);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BLOCK_N) : "memory");
+  }
+}
+
+// ---- host: TMA descriptors through the driver entry point (no -lcuda link dependency) ----
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+// 2-D fp32 tensor [rows, cols], row stride ld floats; box = [BLOCK_K cols, box_rows rows]; 128-byte swizzle; out-of-bounds reads give 0
+int make_map(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld, int box_rows) {
+  encode_tiled_fn enc = get_encode();
+  if (!enc) FAIL(SHADOW_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FAIL(SHADOW_EINVAL, "cuTensorMapEncodeTiled failed (%d): base %p rows %lld cols %lld ld %lld", (int)r, (const void *)base, rows, cols, ld);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbranch, int64_t ldx, int64_t ldw, int64_t ldz, int64_t ldo, int32_t M,
+                                    int32_t N, int32_t K, int32_t act, int32_t do_norm, int32_t out_mode, void *cuda_stream) {
+  if (M <= 0) return 0;
+  if (!br || nbranch < 1 || nbranch > 2) FAIL(SHADOW_EINVAL, "linear_tc: 1 or 2 branches");
+  if (N < 8 || N > BLOCK_N || (N & 3) || K < 1) FAIL(SHADOW_EINVAL, "linear_tc: N must be a multiple of 4 in [8, %d] (got %d), K >= 1", BLOCK_N, N);
+  if ((ldx & 3) || (ldw & 3) || (ldz & 3) || (ldo & 3)) FAIL(SHADOW_EINVAL, "linear_tc: leading dimensions must be multiples of 4 floats");
+  if (out_mode < 0 || out_mode > 2) FAIL(SHADOW_EINVAL, "linear_tc: out_mode");
+  CUtensorMap mx[2], mw[2];
+  LinearParams P;
+  for (int b = 0; b < 2; b++) {
+    const shadow_linear_branch &s = br[b < nbranch ? b : 0];
+    if (!s.X || !s.W || !s.out) FAIL(SHADOW_EINVAL, "linear_tc: X / W / out is NULL");
+    if (((uintptr_t)s.X & 15) || ((uintptr_t)s.W & 15) || ((uintptr_t)s.out & 15) || ((uintptr_t)s.Z & 15)) FAIL(SHADOW_EINVAL, "linear_tc: X / W / Z / out must be 16-byte aligned");
+    if (do_norm && (!s.scale || !s.offset)) FAIL(SHADOW_EINVAL, "linear_tc: norm_feat needs scale and offset");
+    int rc = make_map(&mx[b], s.X, M, K, ldx, BLOCK_M);
+    if (rc) return rc;
+    rc = make_map(&mw[b], s.W, N, K, ldw, BLOCK_N);
+    if (rc) return rc;
+    P.br[b].bias = s.bias; P.br[b].scale = s.scale; P.br[b].offset = s.offset; P.br[b].Z = s.Z; P.br[b].out = s.out;
+    P.br[b].mean = do_norm ? s.mean : nullptr; P.br[b].rstd = do_norm ? s.rstd : nullptr;
+  }
+  P.ldz = (int)ldz; P.ldo = (int)ldo; P.M = M; P.N = N; P.K = K; P.act = act; P.do_norm = do_norm; P.out_mode = out_mode;
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LinearParams);
+  static const kern_t kerns[5][2] = {{linear_tc_kernel<0, false>, linear_tc_kernel<0, true>}, {linear_tc_kernel<1, false>, linear_tc_kernel<1, true>},
+                                     {linear_tc_kernel<2, false>, linear_tc_kernel<2, true>}, {linear_tc_kernel<3, false>, linear_tc_kernel<3, true>},
+                                     {linear_tc_kernel<4, false>, linear_tc_kernel<4, true>}};
+  if (act < 0 || act > 4) FAIL(SHADOW_EINVAL, "linear_tc: unknown activation id %d", act);
+  static bool attr_set[5][2] = {};
+  const kern_t kern = kerns[act][do_norm ? 1 : 0];
+  if (!attr_set[act][do_norm ? 1 : 0]) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_set[act][do_norm ? 1 : 0] = true; }
+  kern<<<dim3((M + BLOCK_M - 1) / BLOCK_M, nbranch), NUM_THREADS, SMEM_BYTES, (cudaStream_t)cuda_stream>>>(mx[0], mw[0], mx[1], mw[1], P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -7,7 +7,7 @@ import os
 
 import torch
 
-from ._lib import lib, check
+from ._lib import lib, check, LinearBranch
 
 ACT_ID = {"relu": 0, "I": 1, "elu": 2, "tanh": 3, "leakyrelu": 4}
 
@@ -191,14 +191,18 @@ def _grad_of(p):
     return p.grad
 
 
-# The dense Linear runs on the tensor cores.  SHADOW_LINEAR selects the implementation (all three are parity-tested):
-#   "tf32x3" (default) the warp-level mma.sync kernel of csrc/gemm.cu: error-compensated 3xTF32, fp32-accurate; 13.6-22.9 us per
+# The dense Linear runs on the tensor cores.  SHADOW_LINEAR selects the implementation (all are parity-tested):
+#   "tc"     (default) the hand-written tcgen05 kernel of csrc/linear_tc.cu: TMA-staged operands, tcgen05.mma.kind::tf32 (3xTF32, fp32-accurate)
+#            with the accumulator in TMEM, bias + activation + norm_feat fused into the tcgen05.ld epilogue, both GraphSAGE branches per
+#            launch; also the input-gradient product (on a transposed copy of the weight).  Weight gradients, and shapes that miss its
+#            alignment rules (e.g. the 47-class classifier), take the warp-level kernel below
+#   "tf32x3" the warp-level mma.sync kernel of csrc/gemm.cu: error-compensated 3xTF32, fp32-accurate; 13.6-22.9 us per
 #            4,832 x 256 x {100,256} product inside the captured step (the fp32 SIMT library GEMM: 13.8-26.5 us)
 #   "umma"   the tcgen05 / TMEM / TMA kernel assembled from CUTLASS templates (csrc/gemm_umma.cu, fp32 emulated with 9 bf16 products);
 #            shapes that miss the 16-byte TMA alignment (e.g. the 47-class classifier) take the kernel above.  Correct, but its
 #            load -> transform -> MMA -> epilogue pipeline is latency-bound at K = 256 with one tile per SM (24.8-32.7 us): not the default
 #   "cublas" the fp32 SIMT library GEMM (the former path, kept for A/B timing)
-_LINEAR = os.environ.get("SHADOW_LINEAR", "tf32x3")
+_LINEAR = os.environ.get("SHADOW_LINEAR", "tc")
 _TC_LINEAR = _LINEAR != "cublas"
 _SPLITK = 16
 
@@ -276,7 +280,35 @@ def _accum_wgrad(w, dZ, x):
 
 
 def _pair_ok(*ts):
-    return _LINEAR == "tf32x3" and all(t.is_contiguous() and t.dtype == torch.float32 for t in ts)
+    return _LINEAR in ("tf32x3", "tc") and all(t.is_contiguous() and t.dtype == torch.float32 for t in ts)
+
+
+def _tc_ok(N, K, *ts):
+    """alignment rules of csrc/linear_tc.cu (TMA descriptors, 128-bit epilogue stores)"""
+    return _LINEAR == "tc" and 8 <= N <= 256 and N % 4 == 0 and K % 4 == 0 and K >= 4 and \
+        all(t is None or (t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() % 16 == 0) for t in ts)
+
+
+def _linear_tc(branches, M, N, K, act, do_norm, out_mode):
+    """branches: 1 or 2 tuples (X, W, bias, scale, offset, Z, out, mean, rstd) of the same shape -> one launch of shadow_linear_tc_f32"""
+    arr = (LinearBranch * 2)()
+    for i, b in enumerate(branches):
+        arr[i] = LinearBranch(*[None if t is None else t.data_ptr() for t in b])
+    x, w, out, Z = branches[0][0], branches[0][1], branches[0][6], branches[0][5]
+    check(lib.shadow_linear_tc_f32(arr, len(branches), x.stride(0), w.stride(0), Z.stride(0) if Z is not None else N, out.stride(0), M, N, K, act,
+                                   int(do_norm), out_mode, _stream(x)))
+
+
+def _dgrad_tc_pair(dZs, ws):
+    """[dZ W for each pair] on the tcgen05 kernel: the product reduces over the Linear's OUTPUT features, so the K-major B operand is W^T"""
+    M, N_out = dZs[0].shape
+    K_in = ws[0].shape[1]
+    wts = [w.detach().t().contiguous() for w in ws]
+    outs = [torch.empty((M, K_in), dtype=torch.float32, device=dZs[0].device) for _ in dZs]
+    if not _tc_ok(K_in, N_out, *dZs, *wts, *outs):
+        return None
+    _linear_tc([(dz, wt, None, None, None, None, o, None, None) for dz, wt, o in zip(dZs, wts, outs)], M, K_in, N_out, ACT_ID["I"], False, 0)
+    return outs
 
 
 def _linear_fwd_pair(x0, w0, b0, x1, w1, b1):
@@ -346,8 +378,19 @@ class _LinearActNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, lin_w, lin_b, scale, offset, idx, act, do_norm):
         x = _req(x.contiguous(), torch.float32, "linear input")
-        Z = _linear_fwd(x, lin_w, lin_b)
-        out, mean, rstd = _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm)
+        M, K = x.shape
+        N = lin_w.shape[0]
+        w = lin_w.detach()
+        if M > 0 and _tc_ok(N, K, x, w):
+            Z = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            out = torch.empty_like(Z)
+            mean = torch.empty(M, dtype=torch.float32, device=x.device)
+            rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+            _linear_tc([(x, w, lin_b.detach() if lin_b is not None else None, scale.detach()[idx] if do_norm else None,
+                         offset.detach()[idx] if do_norm else None, Z, out, mean, rstd)], M, N, K, act, do_norm, 0)
+        else:
+            Z = _linear_fwd(x, lin_w, lin_b)
+            out, mean, rstd = _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm)
         ctx.save_for_backward(x, Z, mean, rstd)
         ctx.p = (lin_w, lin_b, scale, offset, idx, act, do_norm)
         return out
@@ -358,7 +401,10 @@ class _LinearActNorm(torch.autograd.Function):
         lin_w, lin_b, scale, offset, idx, act, do_norm = ctx.p
         dZ = _act_norm_bwd_raw(dOut.contiguous(), Z, scale, offset, lin_b, idx, mean, rstd, act, do_norm)
         _accum_wgrad(lin_w, dZ, x)
-        dX = _linear_dgrad(dZ, lin_w) if ctx.needs_input_grad[0] else None
+        dX = None
+        if ctx.needs_input_grad[0]:
+            r = _dgrad_tc_pair([dZ], [lin_w]) if _LINEAR == "tc" and dZ.shape[0] > 0 else None
+            dX = r[0] if r is not None else _linear_dgrad(dZ, lin_w)
         return dX, None, None, None, None, None, None, None
 
 
@@ -376,9 +422,21 @@ class _SageLayer(torch.autograd.Function):
         x = _req(x.contiguous(), torch.float32, "sage input")
         agg = torch.empty_like(x)
         check(lib.shadow_spmm_csr_fwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(x), _p(agg), adj.n, x.shape[1], 0.0, _stream(x)))
-        Zs, Zn = _linear_fwd_pair(x, ws, bs, agg, wn, bn)
-        out, mean_s, rstd_s = _act_norm_fwd_raw(Zs, scale, offset, 0, act, do_norm)
-        _, mean_n, rstd_n = _act_norm_fwd_raw(Zn, scale, offset, 1, act, do_norm, out=out, accumulate=True)
+        M, K = x.shape
+        N = ws.shape[0]
+        w0, w1 = ws.detach(), wn.detach()
+        if M > 0 and ws.shape == wn.shape and _tc_ok(N, K, x, agg, w0, w1):     # both branches in one tcgen05 launch, epilogue fused
+            Zs = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            Zn = torch.empty_like(Zs)
+            out = torch.zeros_like(Zs)
+            mean_s, rstd_s, mean_n, rstd_n = (torch.empty(M, dtype=torch.float32, device=x.device) for _ in range(4))
+            sc, of = scale.detach(), offset.detach()
+            _linear_tc([(x, w0, bs.detach(), sc[0] if do_norm else None, of[0] if do_norm else None, Zs, out, mean_s, rstd_s),
+                        (agg, w1, bn.detach(), sc[1] if do_norm else None, of[1] if do_norm else None, Zn, out, mean_n, rstd_n)], M, N, K, act, do_norm, 2)
+        else:
+            Zs, Zn = _linear_fwd_pair(x, ws, bs, agg, wn, bn)
+            out, mean_s, rstd_s = _act_norm_fwd_raw(Zs, scale, offset, 0, act, do_norm)
+            _, mean_n, rstd_n = _act_norm_fwd_raw(Zn, scale, offset, 1, act, do_norm, out=out, accumulate=True)
         ctx.save_for_backward(x, agg, Zs, Zn, mean_s, rstd_s, mean_n, rstd_n)
         ctx.p = (adj, ws, bs, wn, bn, scale, offset, act, do_norm)
         return out
@@ -393,7 +451,8 @@ class _SageLayer(torch.autograd.Function):
         _accum_wgrad_pair(ws, dZs, x, wn, dZn, agg)
         if not ctx.needs_input_grad[0]:
             return (None,) * 10
-        dX, dAgg = _linear_dgrad_pair(dZs, ws, dZn, wn)
+        r = _dgrad_tc_pair([dZs, dZn], [ws, wn]) if _LINEAR == "tc" and ws.shape == wn.shape and dZs.shape[0] > 0 else None
+        dX, dAgg = r if r is not None else _linear_dgrad_pair(dZs, ws, dZn, wn)
         check(lib.shadow_spmm_csr_bwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(dAgg), _p(dX), adj.n, dX.shape[1], _stream(dX)))
         return (dX,) + (None,) * 9
 
@@ -471,8 +530,9 @@ class FlatAdamClip:
     def __init__(self, params, lr, max_norm=5.0, betas=(0.9, 0.999), eps=1e-8):
         self.params = [p for p in params]
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        # every parameter starts on a 16-byte boundary (TMA descriptors of csrc/linear_tc.cu); the padding floats stay 0 in all four buffers
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
@@ -480,7 +540,7 @@ class FlatAdamClip:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             p.grad = self.grad[off:off + k].view_as(p)
-            off += k
+            off += (k + 3) // 4 * 4
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -367,3 +367,54 @@ def test_tensor_core_linear_pair_launch_matches_single_launches():
             assert ((got.double() - want).abs() / (d.double().abs().t() @ x.double().abs())).max().item() < 2e-5
     finally:
         ops._LINEAR = old
+
+
+@pytest.mark.parametrize("M,N,K,act,norm,nbranch,mode", [(128, 256, 32, "I", False, 1, 0), (4832, 256, 256, "relu", True, 2, 2), (4832, 256, 100, "elu", True, 1, 1),
+                                                         (1000, 64, 256, "tanh", True, 1, 0), (77, 48, 36, "leakyrelu", True, 2, 2), (300, 256, 256, "I", False, 2, 0)])
+def test_hand_written_tcgen05_linear_with_fused_epilogue_matches_fp64(M, N, K, act, norm, nbranch, mode):
+    """csrc/linear_tc.cu (shadow_linear_tc_f32): Z = X W^T + b, out = norm_feat(act(Z)) (layers.py:329-338,474-483) against fp64 torch:
+    pre-activation, output in all three output modes (store / add / atomic add of two branches), saved mean and rstd.  Tolerance: 2e-5
+    relative to the tensor's max (3xTF32 = fp32-level accuracy; the layer budget is 1e-3)."""
+    import torch.nn.functional as Fn
+    from shadow_gnn_b200 import ops
+    torch.manual_seed(1)
+    dev = torch.device("cuda")
+    f = {"relu": torch.relu, "I": lambda v: v, "elu": Fn.elu, "tanh": torch.tanh, "leakyrelu": lambda v: Fn.leaky_relu(v, 0.2)}[act]
+    X = [torch.randn(M, K, device=dev) for _ in range(nbranch)]
+    W = [torch.randn(N, K, device=dev) / K ** 0.5 for _ in range(nbranch)]
+    b = [torch.randn(N, device=dev) for _ in range(nbranch)]
+    sc = [torch.rand(N, device=dev) + 0.5 for _ in range(nbranch)]
+    of = [torch.randn(N, device=dev) for _ in range(nbranch)]
+    Zt = [torch.empty(M, N, device=dev) for _ in range(nbranch)]
+    mean = [torch.empty(M, device=dev) for _ in range(nbranch)]
+    rstd = [torch.empty(M, device=dev) for _ in range(nbranch)]
+    base = torch.randn(M, N, device=dev) if mode == 1 else torch.zeros(M, N, device=dev)
+    out0 = base.clone()
+    outs = [out0] * nbranch if mode == 2 else [out0] + [torch.empty(M, N, device=dev) for _ in range(nbranch - 1)]
+    assert ops._tc_ok(N, K, *X, *W, *Zt, *outs)
+    ops._linear_tc([(X[i], W[i], b[i], sc[i] if norm else None, of[i] if norm else None, Zt[i], outs[i], mean[i], rstd[i]) for i in range(nbranch)],
+                   M, N, K, ops.ACT_ID[act], norm, mode)
+    torch.cuda.synchronize()
+    rel = lambda a, w: float((a.double() - w).abs().max() / (w.abs().max() + 1e-12))
+    total = base.double().clone()
+    for i in range(nbranch):
+        z = X[i].double() @ W[i].double().t() + b[i].double()
+        o = f(z)
+        if norm:
+            m, v = o.mean(1, keepdim=True), o.var(1, unbiased=False, keepdim=True) + 1e-9
+            assert rel(mean[i], m[:, 0]) < 2e-5 and rel(rstd[i], torch.rsqrt(v)[:, 0]) < 2e-5
+            o = (o - m) * sc[i].double() * torch.rsqrt(v) + of[i].double()
+        assert rel(Zt[i], z) < 2e-5
+        if mode == 2:
+            total += o
+        else:
+            assert rel(outs[i], o + (base.double() if (mode == 1 and i == 0) else 0)) < 2e-5
+    if mode == 2:
+        assert rel(out0, total) < 2e-5
+
+
+def test_tcgen05_linear_rejects_misaligned_shapes():
+    from shadow_gnn_b200 import ops
+    x = torch.randn(64, 256, device="cuda")
+    assert not ops._tc_ok(47, 256, x) and not ops._tc_ok(256, 30, x) and not ops._tc_ok(512, 256, x)
+    assert not ops._tc_ok(256, 256, x[:, 1:])        # not contiguous / not 16-byte aligned
