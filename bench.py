@@ -54,9 +54,19 @@ def parse():
     ap.add_argument("--superbatch", type=int, default=65536)
     ap.add_argument("--superbatch-train", type=int, default=4096)
     ap.add_argument("--graph", default="S-products")
+    ap.add_argument("--arch", default="sage", choices=["sage", "gat", "gcn", "gin"], help="aggregator of the 5-layer model (BASELINE configs[2]: sage; configs[3]: gat, --batch 64)")
+    ap.add_argument("--batch", type=int, default=32, help="targets per step and GPU")
+    ap.add_argument("--no-clustered", action="store_true", help="skip the secondary measurement on the clustered stand-in S-products-c")
     ap.add_argument("--cpu-sample", type=int, default=4000, help="roots of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    TRAIN_CFG["batch"] = a.batch
+    if a.arch == "gat":          # config_train/products/vanilla/gat_5_ppr.yml (BASELINE configs[3])
+        TRAIN_CFG.update(dropout=0.35, dropedge=0.1, lr=0.001)
+        ARCH.update(aggr="gat", heads=4)
+    elif a.arch != "sage":
+        ARCH.update(aggr=a.arch)
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -107,9 +117,9 @@ class ClockSampler:
 def build_graph(name, device):
     """S-products etc. on the GPU (setup, untimed); returns int32-viewed CUDA tensors + int64 degrees."""
     import torch
-    from shadow_gnn_b200.synth import PRESETS, powerlaw_graph_torch
+    from shadow_gnn_b200.synth import PRESETS, CLUSTERED, powerlaw_graph_torch
     N, nnz, dmax, F, C, ntrain, seed = PRESETS[name]
-    indptr64, indices = powerlaw_graph_torch(N, nnz, seed, dmax, device)
+    indptr64, indices = powerlaw_graph_torch(N, nnz, seed, dmax, device, community=CLUSTERED.get(name))
     train = torch.from_numpy(np.random.default_rng(seed).permutation(N)[:ntrain].astype(np.int64))
     return dict(N=N, F=F, C=C, seed=seed, indptr64=indptr64, indptr=indptr64.to(torch.int32), indices=indices, train=train)
 
@@ -236,8 +246,16 @@ def host_graph(args):
 TRAIN_CFG = dict(batch=32, layers=5, dim=256, dropout=0.4, dropedge=0.05, lr=0.002)          # config_train/products/vanilla/sage_5_ppr.yml
 ARCH = dict(num_layers=5, num_cls_layers=1, heads=1, branch_sharing=False, dim=256, act="relu", layer_norm="norm_feat",
             feature_augment_ops="sum", aggr="sage", residue="none", pooling="center", loss="softmax", ensemble_act="leakyrelu")
-WORKLOAD = ("{g} 5-layer GraphSAGE-256, PPR(k=150,eps=1e-5) sampler, batch 32 per GPU, dropout 0.4, dropedge 0.05, Adam lr 0.002, clip 5: "
-            "sample + block-diagonal batch + feature gather + forward + backward + optimizer step")
+
+
+class _Workload:
+    def format(self, g):
+        name = {"sage": "GraphSAGE", "gat": "GAT (4 heads)", "gcn": "GCN", "gin": "GIN"}[ARCH["aggr"]]
+        return (f"{g} 5-layer {name}-256, PPR(k=150,eps=1e-5) sampler, batch {TRAIN_CFG['batch']} per GPU, dropout {TRAIN_CFG['dropout']}, "
+                f"dropedge {TRAIN_CFG['dropedge']}, Adam lr {TRAIN_CFG['lr']}, clip 5: sample + block-diagonal batch + feature gather + forward + backward + optimizer step")
+
+
+WORKLOAD = _Workload()
 
 
 def run_reference(args):
@@ -292,20 +310,22 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class Ctx:
-    def __init__(self, args):
+    def __init__(self, args, graph=None, feat=None):
         import torch
         import torch.distributed as dist
         self.rank, self.world, self.local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
         assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU: there is no CPU fallback"
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
-        if self.world > 1:
+        if self.world > 1 and not dist.is_initialized():
             dist.init_process_group("nccl", device_id=self.dev)
         torch.manual_seed(1234); np.random.seed(1234)
-        log("building graph")
-        self.g = build_graph(args.graph, self.dev)
+        self.graph_name = graph or args.graph
+        log("building graph", self.graph_name)
+        self.g = build_graph(self.graph_name, self.dev)
         self.N, self.F, self.C = self.g["N"], self.g["F"], self.g["C"]
-        self.feat = torch.randn(self.N, self.F, device=self.dev, generator=torch.Generator(device=self.dev).manual_seed(self.g["seed"] + 100))
+        self.feat = feat if feat is not None else \
+            torch.randn(self.N, self.F, device=self.dev, generator=torch.Generator(device=self.dev).manual_seed(self.g["seed"] + 100))
         self.deg = torch.diff(self.g["indptr64"])
         # every rank takes its share of the epoch's target order (independent units: no data-path collective in the sampler)
         from shadow_gnn_b200.parallel import partition_targets
@@ -443,7 +463,7 @@ def train_phase(ctx, steps, warmup):
     adjs = {m: (ctx.g["indptr"], ctx.g["indices"]) for m in range(3)}
     # the timed region must contain sampling whatever --steps is: at least 4 super-batch refills (sampler + gather + canonical CSR) fall inside it
     sb_train = max(B, min(args.superbatch_train, B * max(1, steps // 4)))
-    mb = MB.MinibatchShallowExtractor(args.graph, None, adjs, {0: share, 1: share[:B], 2: share[:B]}, cfg, set(), None, ctx.feat, labels, F, True, 1,
+    mb = MB.MinibatchShallowExtractor(ctx.graph_name, None, adjs, {0: share, 1: share[:B], 2: share[:B]}, cfg, set(), None, ctx.feat, labels, F, True, 1,
                                       seed_cpp=1, num_subg_per_batch=sb_train)
     model = DeepGNN(F, F, C, 0, ARCH, [], 1, dict(dropout=TRAIN_CFG["dropout"], dropedge=TRAIN_CFG["dropedge"], lr=TRAIN_CFG["lr"], ensemble_dropout="none"),
                     "node").to(dev)
@@ -451,7 +471,7 @@ def train_phase(ctx, steps, warmup):
     log("train phase: model ready; PPR push + first super-batch next")
     mb.epoch_start_reset(0, MB.TRAIN)
     mb.shuffle_entity(MB.TRAIN)
-    trainer = None if args.eager else GraphedTrainer(model, mb, row_cap=B * (PPR_K + 1), edge_cap=B * (PPR_K + 1) * 16)
+    trainer = None if args.eager else GraphedTrainer(model, mb, row_cap=B * (PPR_K + 1), edge_cap=B * (PPR_K + 1) * 64)
 
     def roll():
         if mb.is_end_epoch(MB.TRAIN):
@@ -494,7 +514,12 @@ def train_phase(ctx, steps, warmup):
         a = mb.idx_entity_evaluated[MB.TRAIN]
         if a + B <= mb.label_epoch[MB.TRAIN].numel():           # H2D: this step's labels (consumed by the step's loss); the step's target ids
             mb.label_epoch[MB.TRAIN][a:a + B].copy_(lab_epoch_host[a:a + B], non_blocking=True)   # travel with the epoch's target list (uploaded when it is shuffled)
+        if os.environ.get("BENCH_DEBUG"):
+            torch.cuda.synchronize(); td0 = time.perf_counter()
         loss, n = one_step()
+        if os.environ.get("BENCH_DEBUG"):
+            td1 = time.perf_counter(); torch.cuda.synchronize(); td2 = time.perf_counter()
+            if i % 10 == 0: log(f"e2e step {i}: host {1e3 * (td1 - td0):.3f} ms, +gpu drain {1e3 * (td2 - td1):.3f} ms, sampler calls {mb.num_sampler_calls}")
         loss_host.copy_(loss.reshape(1), non_blocking=True)                   # D2H: the step's loss
         torch.cuda.synchronize()
         ne2e += n
@@ -508,6 +533,27 @@ def train_phase(ctx, steps, warmup):
                 superbatch=sb_train, refills_in_timed_region=int(refills),
                 e2e={"value": ne_all / e2e_all, "unit": "samples/s", "h2d_bytes_per_step": B * 8 + B * 4, "d2h_bytes_per_step": 4,
                      "note": "labels from pinned host memory each step, loss read back each step; the epoch's target ids are uploaded once per epoch (4 B per target)"})
+
+
+def run_clustered(ctx, args):
+    """second named workload: the same sizes with community structure (a PPR scope keeps tens of percent of the slots it scans and
+    induces thousands of edges, like real co-purchase graphs; the uniform stand-in keeps 3 %)"""
+    import torch
+    try:
+        feat = ctx.feat
+        ctx.g = None
+        torch.cuda.empty_cache()
+        ctx2 = Ctx(args, graph="S-products-c", feat=feat)
+        s2 = sampler_phase(ctx2, 6, 4)
+        torch.cuda.empty_cache()
+        t2 = train_phase(ctx2, min(args.steps, 100), min(args.warmup, 5))
+        return {"workload": WORKLOAD.format(g="S-products-c") + " (planted partition: communities of 192 nodes, 75 % of the edges inside)",
+                "train": {k: t2[k] for k in ("value", "unit", "ms_per_step", "graph_steps", "eager_steps", "e2e")},
+                "sampler": {k: s2[k] for k in ("value", "unit", "ms_per_step", "steps", "superbatch", "avg_nodes_per_subgraph", "avg_edges_per_subgraph",
+                                               "redo_last_launch", "e2e")},
+                "roofline": s2["roofline"], "roofline_gather": s2["roofline_gather"]}
+    except Exception as e:      # noqa: the secondary workload never breaks the contract line
+        return {"workload": "S-products-c", "error": repr(e)[:300]}
 
 
 def run_ours(args):
@@ -564,6 +610,8 @@ def run_ours(args):
                                             "sample": f"{rs['n']} roots (500 per call), incl. list->numpy, block-diagonal collation, feature gather"}
             except Exception as e:      # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": line["unit"], "cores": 0, "kind": "unavailable", "sample": repr(e)[:200]}
+        if world == 1 and args.task == "full" and args.graph == "S-products" and not args.no_clustered:
+            line["workload_clustered"] = run_clustered(ctx, args)
         print(json.dumps(line), flush=True)
     if ctx.world > 1:
         torch.distributed.destroy_process_group()

@@ -210,9 +210,15 @@ int shadow_spmm_csr_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t
 typedef struct shadow_linear_branch {
   const float *X, *W, *bias, *scale, *offset;
   float *Z, *out, *mean, *rstd;
+  const float *W_lo;   /* NULL: W is the fp32 weight, split inside the kernel.  Else W = its TF32 head and W_lo = the exact remainder
+                          (shadow_tf32_split_f32 / shadow_tf32_split_transpose_f32, refreshed once per optimizer step) */
 } shadow_linear_branch;
 int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbranch, int64_t ldx, int64_t ldw, int64_t ldz, int64_t ldo, int32_t M,
                          int32_t N, int32_t K, int32_t act, int32_t do_norm, int32_t out_mode, void *cuda_stream);
+/* hi = src with the low 13 mantissa bits cleared (what a TF32 tensor core reads), lo = src - hi (exact in fp32) */
+int shadow_tf32_split_f32(const float *src, int64_t n, float *hi, float *lo, void *cuda_stream);
+/* the same for the TRANSPOSE of every 2-D weight inside one flat buffer: table_dev[e] = {src offset, rows, cols, dst offset} (int64, device) */
+int shadow_tf32_split_transpose_f32(const float *src, const int64_t *table_dev, int32_t num_entries, float *t_hi, float *t_lo, void *cuda_stream);
 /* act + norm_feat (layers.py:329-338; F_ACT layers.py:26-39): act ids 0 relu, 1 I, 2 elu, 3 tanh, 4 leakyrelu(0.2) */
 int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float *scale, const float *offset, float *out, int32_t ldo,
                             float *mean, float *rstd, int32_t n, int32_t D, int32_t act, int32_t do_norm, int32_t accumulate,
@@ -220,6 +226,13 @@ int shadow_act_norm_fwd_f32(const float *Z, int32_t ldz, const float *scale, con
 int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const float *Z, int32_t ldz, const float *scale, const float *mean,
                             const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, float *dbias, int32_t n,
                             int32_t D, int32_t act, int32_t do_norm, void *cuda_stream);   /* dscale/doffset/dbias (column sums of dZ, may be NULL) are ACCUMULATED */
+/* the same backward for one or two branches that share dOut (GraphSAGE: out = norm0(act(Z0)) + norm1(act(Z1)), layers.py:474-483; Z1 NULL = one
+ * branch).  Column sums are reduced in two deterministic stages through `scratch` (>= 2 * SMs * branches * 3 * D floats): no atomics. D <= 256. */
+int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
+                                 const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
+                                 float *dZ0, float *dZ1, int32_t lddz, float *dscale0, float *doffset0, float *dbias0, float *dscale1,
+                                 float *doffset1, float *dbias1, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
+                                 int64_t scratch_floats, void *cuda_stream);
 /* GAT._aggregate_attention for all heads (layers.py:560-582): a_self/a_neigh [n,heads] already through LeakyReLU(0.2) */
 int shadow_gat_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
                        const float *a_neigh, const float *H, float *out, float *rowmax, float *denom, int32_t n, int32_t heads,

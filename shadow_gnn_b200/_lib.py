@@ -32,7 +32,7 @@ class BatchInfo(C.Structure):
 
 class LinearBranch(C.Structure):
     """shadow_linear_branch"""
-    _fields_ = [(n, C.c_void_p) for n in ("X", "W", "bias", "scale", "offset", "Z", "out", "mean", "rstd")]
+    _fields_ = [(n, C.c_void_p) for n in ("X", "W", "bias", "scale", "offset", "Z", "out", "mean", "rstd", "W_lo")]
 
 
 METHOD = {"khop": 0, "ppr": 1, "ppr_st": 2, "nodeIID": 3}
@@ -52,10 +52,10 @@ SYMBOLS = [
     "shadow_sampler_sample", "shadow_sampler_batch_info", "shadow_sampler_batch_field_dev",
     "shadow_sampler_batch_field_host", "shadow_sampler_last_redo_count", "shadow_gather_rows_f32",
     "shadow_edge_vals_fill", "shadow_edge_vals_dropedge", "shadow_edge_vals_row_normalize", "shadow_edge_vals_sym_normalize",
-    "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32",
+    "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32", "shadow_act_norm_bwd_pair_f32",
     "shadow_gat_fwd_f32", "shadow_gat_bwd_f32", "shadow_segment_pool_fwd_f32", "shadow_segment_pool_bwd_f32",
     "shadow_adam_clip_step_f32", "shadow_gemm_tf32x3_f32", "shadow_gemm_tf32x3_pair_f32",
-    "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32", "shadow_linear_tc_f32",
+    "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32", "shadow_linear_tc_f32", "shadow_tf32_split_f32", "shadow_tf32_split_transpose_f32",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -107,6 +107,9 @@ lib.shadow_gemm_tf32x3_pair_f32.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _i32
 lib.shadow_linear_umma_fwd_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_dgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_wgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]
+lib.shadow_act_norm_bwd_pair_f32.argtypes = [_vp, _i32, _vp, _vp, _i32] + [_vp] * 8 + [_i32] + [_vp] * 6 + [_i32, _i32, _i32, _i32, _vp, _i64, _vp]
+lib.shadow_tf32_split_f32.argtypes = [_vp, _i64, _vp, _vp, _vp]
+lib.shadow_tf32_split_transpose_f32.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp]
 lib.shadow_linear_tc_f32.argtypes = [C.POINTER(LinearBranch), _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
 lib.shadow_adam_clip_step_f32.argtypes = [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]
 

@@ -373,6 +373,81 @@ __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_kernel(const float *
   }
 }
 
+// The same backward for up to TWO branches that share dOut (the self and the neighbour branch of a GraphSAGE layer: out = n0(act(Z0)) + n1(act(Z1)),
+// layers.py:474-483): dOut is read once, and the column sums (dscale, doffset, dbias per branch) are reduced in two deterministic stages --
+// every CTA writes its partial sums to `partials[cta][branch][3][D]`, colsum_finish_kernel adds them up in CTA order.  No atomics.
+struct AnbPair {
+  const float *Z[2], *scale[2], *mean[2], *rstd[2];
+  float *dZ[2], *dscale[2], *doffset[2], *dbias[2];
+};
+template <int NPL, int NB>
+__global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_pair_kernel(const float *__restrict__ dOut, int ldo, const AnbPair A, int ldz, int lddz, int n, int D, int act,
+                                                                        int do_norm, float *__restrict__ partials) {
+  extern __shared__ float sh[];               // [warps][NB][3][D]
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  float ps[NB][NPL], po[NB][NPL], pb[NB][NPL];
+#pragma unroll
+  for (int b = 0; b < NB; b++)
+#pragma unroll
+    for (int k = 0; k < NPL; k++) { ps[b][k] = 0.f; po[b][k] = 0.f; pb[b][k] = 0.f; }
+  for (int i = blockIdx.x * wpb + warp; i < n; i += gridDim.x * wpb) {
+    float g[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; g[k] = (f < D) ? dOut[(size_t)i * ldo + f] : 0.f; }
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      float a[NPL], z[NPL];
+#pragma unroll
+      for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; z[k] = (f < D) ? A.Z[b][(size_t)i * ldz + f] : 0.f; a[k] = act_f(z[k], act); }
+      if (do_norm) {
+        const float mean = A.mean[b][i], rstd = A.rstd[b][i];
+        float s1 = 0.f, s2 = 0.f, xh[NPL], dxh[NPL];
+#pragma unroll
+        for (int k = 0; k < NPL; k++) {
+          const int f = lane + 32 * k;
+          xh[k] = (f < D) ? (a[k] - mean) * rstd : 0.f; dxh[k] = (f < D) ? g[k] * A.scale[b][f] : 0.f;
+          s1 += dxh[k]; s2 += dxh[k] * xh[k];
+          ps[b][k] += g[k] * xh[k]; po[b][k] += g[k];
+        }
+        s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+        for (int k = 0; k < NPL; k++) {
+          const int f = lane + 32 * k;
+          if (f < D) { const float dz = rstd * (dxh[k] - s1 - xh[k] * s2) * act_df(z[k], a[k], act); A.dZ[b][(size_t)i * lddz + f] = dz; pb[b][k] += dz; }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) { const float dz = g[k] * act_df(z[k], a[k], act); A.dZ[b][(size_t)i * lddz + f] = dz; pb[b][k] += dz; } }
+      }
+    }
+  }
+  float *mine = sh + (size_t)warp * NB * 3 * D;
+#pragma unroll
+  for (int b = 0; b < NB; b++)
+#pragma unroll
+    for (int k = 0; k < NPL; k++) {
+      const int f = lane + 32 * k;
+      if (f < D) { mine[(b * 3 + 0) * D + f] = ps[b][k]; mine[(b * 3 + 1) * D + f] = po[b][k]; mine[(b * 3 + 2) * D + f] = pb[b][k]; }
+    }
+  __syncthreads();
+  for (int f = threadIdx.x; f < NB * 3 * D; f += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < wpb; w++) v += sh[(size_t)w * NB * 3 * D + f];
+    partials[(size_t)blockIdx.x * NB * 3 * D + f] = v;
+  }
+}
+// column c of [NB][3][D]: sum of the CTAs' partials in CTA order, ADDED to its destination (each destination has exactly one writer)
+__global__ void colsum_finish_kernel(const float *__restrict__ partials, int nparts, int D, int nb, const AnbPair A, int do_norm) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, cols = nb * 3 * D;
+  if (c >= cols) return;
+  float v = 0.f;
+#pragma unroll 8
+  for (int p = 0; p < nparts; p++) v += partials[(size_t)p * cols + c];
+  const int b = c / (3 * D), kind = (c / D) % 3, f = c % D;
+  float *dst = kind == 0 ? (do_norm ? A.dscale[b] : nullptr) : (kind == 1 ? (do_norm ? A.doffset[b] : nullptr) : A.dbias[b]);
+  if (dst) dst[f] += v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // GAT attention aggregation (layers.py:560-582), all heads in one launch, warp per (row, head):
 //   e_ij = a_self[i,k] + a_neigh[j,k];  u_ij = exp(e_ij - max_j e_ij) * A_ij;  out[i,k,:] = sum_j u_ij h[j,k,:] / clamp(sum_j u_ij, 1e-10)
@@ -604,6 +679,36 @@ extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const flo
   if (D <= 32) LAUNCH_BWD(1); else if (D <= 64) LAUNCH_BWD(2); else if (D <= 128) LAUNCH_BWD(4); else if (D <= 256) LAUNCH_BWD(8);
   else if (D <= 512) LAUNCH_BWD(16); else LAUNCH_BWD(32);
 #undef LAUNCH_BWD
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
+                                            const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
+                                            float *dZ0, float *dZ1, int32_t lddz, float *dscale0, float *doffset0, float *dbias0, float *dscale1,
+                                            float *doffset1, float *dbias1, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
+                                            int64_t scratch_floats, void *stream) {
+  if (n <= 0) return 0;
+  if (D > 256) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair: D=%d exceeds 256", D);
+  const int nb = Z1 ? 2 : 1;
+  AnbPair A;
+  A.Z[0] = Z0; A.Z[1] = Z1; A.scale[0] = scale0; A.scale[1] = scale1; A.mean[0] = mean0; A.mean[1] = mean1; A.rstd[0] = rstd0; A.rstd[1] = rstd1;
+  A.dZ[0] = dZ0; A.dZ[1] = dZ1; A.dscale[0] = dscale0; A.dscale[1] = dscale1; A.doffset[0] = doffset0; A.doffset[1] = doffset1; A.dbias[0] = dbias0; A.dbias[1] = dbias1;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = grid_for(n, WPB, 2 * sms);
+  if (!scratch || scratch_floats < (int64_t)grid * nb * 3 * D) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair: scratch needs %lld floats", (long long)grid * nb * 3 * D);
+  const size_t smem = (size_t)WPB * nb * 3 * D * sizeof(float);
+#define LAUNCH_PAIR(NPL, NB)                                                                                                                   \
+  do {                                                                                                                                         \
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(act_norm_bwd_pair_kernel<NPL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    act_norm_bwd_pair_kernel<NPL, NB><<<grid, LAYER_BLOCK, smem, ST(stream)>>>(dOut, ldo, A, ldz, lddz, n, D, act, do_norm, scratch);          \
+  } while (0)
+  if (nb == 2) { if (D <= 64) LAUNCH_PAIR(2, 2); else if (D <= 128) LAUNCH_PAIR(4, 2); else LAUNCH_PAIR(8, 2); }
+  else { if (D <= 64) LAUNCH_PAIR(2, 1); else if (D <= 128) LAUNCH_PAIR(4, 1); else LAUNCH_PAIR(8, 1); }
+#undef LAUNCH_PAIR
+  CUDA_TRY(cudaGetLastError());
+  const int cols = nb * 3 * D;
+  colsum_finish_kernel<<<(cols + 127) / 128, 128, 0, ST(stream)>>>(scratch, grid, D, nb, A, do_norm);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,7 @@
 // three passes over its N columns (sum -> mean, squared deviations -> rstd, normalise + store), bias / activation applied on the fly.
 // Pipeline: 2 stages x (A hi/lo 2 x 16 KB + B hi/lo 2 x 32 KB) = 192 KB of shared memory; mbarriers full (TMA -> transform),
 // ready (transform -> MMA), empty (tcgen05.commit -> producer), acc (last commit -> epilogue).
+#include <algorithm>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -25,14 +26,20 @@ namespace {
 
 constexpr int BLOCK_M = 128;          // rows per CTA = TMEM lanes
 constexpr int BLOCK_N = 256;          // columns per CTA = TMEM columns (fp32)
-constexpr int BLOCK_K = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+#ifndef LTC_BLOCK_K
+#define LTC_BLOCK_K 16
+#endif
+constexpr int BLOCK_K = LTC_BLOCK_K;  // fp32 elements per k-block = one swizzle row: 16 (64-byte swizzle, 4 stages of 48 KB) or 32 (128-byte swizzle, 2 stages of 96 KB)
 constexpr int UMMA_K = 8;             // tf32: 32 bytes per MMA k-step
-constexpr int NSTAGES = 2;
+constexpr int NSTAGES = BLOCK_K == 16 ? 4 : 2;
+static_assert(BLOCK_K == 16 || BLOCK_K == 32, "one swizzle row per k-block");
 constexpr int A_TILE = BLOCK_M * BLOCK_K * 4;      // 16 KB
 constexpr int B_TILE = BLOCK_N * BLOCK_K * 4;      // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
-constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + 3 * BLOCK_N * 4 /*bias, scale, offset*/;
-constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + 3 * BLOCK_N * 4 /*bias, scale, offset*/ + 2 * 2 * BLOCK_M * 4 /*row statistics of the two column halves*/;
+static_assert(NSTAGES * STAGE_BYTES >= 8 * 4 * 4096, "the epilogue stages its tiles in the pipeline buffers");
+constexpr int NUM_WORKERS = 256;      // transform + epilogue threads (warps 2..9: two warps per TMEM lane quadrant)
+constexpr int NUM_THREADS = 64 + NUM_WORKERS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -61,10 +68,18 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused: 1) << 16 | SBO (8 rows x 128 B
-// = 1024 B) >> 4 << 32 | version 1 << 46 | layout 2 (SWIZZLE_128B) << 61
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused: 1) << 16 | SBO (8 rows of one
+// swizzle row each: 1024 B or 512 B) >> 4 << 32 | version 1 << 46 | layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B) << 61
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t sbo = (8 * BLOCK_K * 4) >> 4, layout = BLOCK_K == 32 ? 2 : 4;
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 << 17, M >> 4 << 24
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
@@ -97,7 +112,7 @@ enum { ACT_RELU = 0, ACT_I = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_LRELU = 4 };
 template <int ACT>
 __device__ __forceinline__ float act_f(float z) {
   if (ACT == ACT_RELU) return z > 0.f ? z : 0.f;
-  if (ACT == ACT_ELU) return z > 0.f ? z : expm1f(z);
+  if (ACT == ACT_ELU) return z > 0.f ? z : __expf(z) - 1.f;          // absolute error ~1e-7 on a value in (-1, 0]
   if (ACT == ACT_TANH) return tanhf(z);
   if (ACT == ACT_LRELU) return z > 0.f ? z : 0.2f * z;
   return z;
@@ -111,35 +126,35 @@ struct LinearBranch {
 struct LinearParams {
   LinearBranch br[2];
   int ldz, ldo, M, N, K, act, do_norm;
+  int presplit;                            // the weights arrive as two planes (TF32 head, exact remainder): no in-kernel split of the B tiles
+  int debug;                               // SHADOW_LTC_DEBUG bits (timing experiments only): 1 skip the main loop, 2 skip the epilogue
   int out_mode;                            // 0: out = o   1: out += o (one branch per launch)   2: red.global.add (both branches into one zeroed buffer)
 };
-
-__device__ __forceinline__ void store_out4(float *p, const float4 v, const int mode) {
-  if (mode == 0) *reinterpret_cast<float4 *>(p) = v;
-  else if (mode == 1) { float4 o = *reinterpret_cast<const float4 *>(p); o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w; *reinterpret_cast<float4 *>(p) = o; }
-  else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 
 template <int ACT, bool NORM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_x1,
-                 const __grid_constant__ CUtensorMap map_w1, const LinearParams P) {
+                 const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_z0, const __grid_constant__ CUtensorMap map_o0,
+                 const __grid_constant__ CUtensorMap map_z1, const __grid_constant__ CUtensorMap map_o1, const __grid_constant__ CUtensorMap map_wl0,
+                 const __grid_constant__ CUtensorMap map_wl1, const LinearParams P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B atoms are 1024-byte aligned
   uint64_t *bars = (uint64_t *)(smem + NSTAGES * STAGE_BYTES);
   uint64_t *full = bars, *ready = bars + NSTAGES, *empty = bars + 2 * NSTAGES, *acc = bars + 3 * NSTAGES;
   uint32_t *tmem_slot = (uint32_t *)(bars + 3 * NSTAGES + 1);
   float *vecs = (float *)(bars + 3 * NSTAGES + 2);                 // bias / scale / offset of this branch (3 x BLOCK_N floats)
+  float *part = vecs + 3 * BLOCK_N;                                // [2 passes][2 column halves][BLOCK_M] partial row sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M;
-  const int num_kb = (P.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = (P.debug & 1) ? 0 : (P.K + BLOCK_K - 1) / BLOCK_K;
   const CUtensorMap *map_x = blockIdx.y ? &map_x1 : &map_x0, *map_w = blockIdx.y ? &map_w1 : &map_w0;
+  const CUtensorMap *map_z = blockIdx.y ? &map_z1 : &map_z0, *map_o = blockIdx.y ? &map_o1 : &map_o0, *map_wl = blockIdx.y ? &map_wl1 : &map_wl0;
   const LinearBranch B = P.br[blockIdx.y];
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(map_w) : "memory");
-    for (int s = 0; s < NSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], NUM_WORKERS); mbar_init(&empty[s], 1); }
     mbar_init(acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -165,9 +180,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
         const int s = kb % NSTAGES;
         mbar_wait(&empty[s], ((kb / NSTAGES) & 1) ^ 1);
         unsigned char *st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&full[s], A_TILE + B_TILE);
-        tma_load_2d(st, map_x, &full[s], kb * BLOCK_K, m0);                       // A hi  [128 rows][32 k]
-        tma_load_2d(st + 2 * A_TILE, map_w, &full[s], kb * BLOCK_K, 0);           // B hi  [256 rows][32 k]
+        mbar_expect_tx(&full[s], A_TILE + (P.presplit ? 2 : 1) * B_TILE);
+        tma_load_2d(st, map_x, &full[s], kb * BLOCK_K, m0);                       // A     [128 rows][BLOCK_K]
+        tma_load_2d(st + 2 * A_TILE, map_w, &full[s], kb * BLOCK_K, 0);           // B (hi) [256 rows][BLOCK_K]
+        if (P.presplit) tma_load_2d(st + 2 * A_TILE + B_TILE, map_wl, &full[s], kb * BLOCK_K, 0);      // B lo
       }
     }
   } else if (warp == 1) {
@@ -188,17 +204,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
         }
         umma_commit(&empty[s]);                        // the stage's shared memory is free once these MMAs have read it
       }
-      umma_commit(acc);                                // accumulator complete
+      if (num_kb) umma_commit(acc);                    // accumulator complete
     }
   } else {
     // ===== transform warps (2..5): split every landed tile into hi / lo in place =====
-    const int t = threadIdx.x - 64;                    // 0..127
+    const int t = threadIdx.x - 64;                    // 0..255
     for (int kb = 0; kb < num_kb; kb++) {
       const int s = kb % NSTAGES;
       mbar_wait(&full[s], (kb / NSTAGES) & 1);
       float4 *a_hi = (float4 *)(smem + s * STAGE_BYTES), *a_lo = a_hi + A_TILE / 16, *b_hi = a_hi + 2 * A_TILE / 16, *b_lo = b_hi + B_TILE / 16;
 #pragma unroll 4
-      for (int i = t; i < A_TILE / 16; i += 128) {
+      for (int i = t; i < A_TILE / 16; i += NUM_WORKERS) {
         const float4 v = a_hi[i];
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -206,8 +222,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
         l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
         a_hi[i] = h; a_lo[i] = l;
       }
+      if (!P.presplit)
 #pragma unroll 4
-      for (int i = t; i < B_TILE / 16; i += 128) {
+      for (int i = t; i < B_TILE / 16; i += NUM_WORKERS) {
         const float4 v = b_hi[i];
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -219,56 +236,77 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
       mbar_arrive(&ready[s]);
     }
 
-    // ===== epilogue: thread <-> accumulator row (TMEM lane); a warp may only touch lanes 32 * (warp % 4) .. + 31 =====
-    mbar_wait(acc, 0);
+    // ===== epilogue: thread <-> accumulator row (TMEM lane); a warp may only touch lanes 32 * (warp % 4) .. + 31.  Two warps share a lane
+    // quadrant: the 32-column blocks alternate between them (row statistics of norm_feat are combined through shared memory).  Every
+    // 32 x 32 block is written to a 128B-swizzled staging tile (the pipeline stages are free by now) and leaves through TMA: a plain store
+    // for Z, a store or a reduce-add for the output, so global memory sees whole 128-byte lines and out-of-range rows / columns are clipped
+    // by the tensor map. =====
+    if (num_kb) mbar_wait(acc, 0);
+    if (!(P.debug & 2)) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int quad = warp & 3;
-    const int row = m0 + quad * 32 + lane;
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int row_l = quad * 32 + lane;                // row inside the CTA tile
+    const int row = m0 + row_l;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int N = P.N;
-    const bool live = row < P.M;
     const float *vb = vecs, *vs = vecs + BLOCK_N, *vo = vecs + 2 * BLOCK_N;
     float mean = 0.f, rstd = 1.f;
     uint32_t r[32];
     if (NORM) {
       float s1 = 0.f;
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = half * 32; c0 < N; c0 += 64) {
         tmem_ld32(taddr + c0, r);
 #pragma unroll
         for (int j = 0; j < 32; j++)
           if (c0 + j < N) s1 += act_f<ACT>(__uint_as_float(r[j]) + vb[c0 + j]);
       }
-      mean = s1 / (float)N;
+      part[half * BLOCK_M + row_l] = s1;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      mean = (part[row_l] + part[BLOCK_M + row_l]) / (float)N;
       float s2 = 0.f;
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = half * 32; c0 < N; c0 += 64) {
         tmem_ld32(taddr + c0, r);
 #pragma unroll
         for (int j = 0; j < 32; j++)
           if (c0 + j < N) { const float d = act_f<ACT>(__uint_as_float(r[j]) + vb[c0 + j]) - mean; s2 += d * d; }
       }
-      rstd = rsqrtf(s2 / (float)N + 1e-9f);
-      if (live && B.mean) { B.mean[row] = mean; B.rstd[row] = rstd; }
+      part[2 * BLOCK_M + half * BLOCK_M + row_l] = s2;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      rstd = rsqrtf((part[2 * BLOCK_M + row_l] + part[3 * BLOCK_M + row_l]) / (float)N + 1e-9f);
+      if (half == 0 && row < P.M && B.mean) { B.mean[row] = mean; B.rstd[row] = rstd; }
     }
-    for (int c0 = 0; c0 < N; c0 += 32) {               // N is a multiple of 4: whole float4 groups
+    unsigned char *stage_w = smem + (size_t)(warp - 2) * (4 * 4096);       // this warp: {Z, out} x 2 buffers of 32 rows x 128 bytes
+    const uint32_t sw = (uint32_t)(lane & 7);                               // 128-byte swizzle: 16-byte chunk q of row l lives at chunk q ^ (l % 8)
+    int it = 0;
+    for (int c0 = half * 32; c0 < N; c0 += 64, it++) {
       tmem_ld32(taddr + c0, r);
-      if (live) {
-        float *zrow = B.Z ? B.Z + (size_t)row * P.ldz + c0 : nullptr;
-        float *orow = B.out + (size_t)row * P.ldo + c0;
+      unsigned char *zb = stage_w + (size_t)(it & 1) * 8192, *ob = zb + 4096;
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the stores that last read this buffer pair are done
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (c0 + j < N) {
-            float z[4], o[4];
+      for (int q = 0; q < 8; q++) {
+        float z[4], o[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              z[q] = __uint_as_float(r[j + q]) + vb[c0 + j + q];
-              o[q] = act_f<ACT>(z[q]);
-              if (NORM) o[q] = (o[q] - mean) * vs[c0 + j + q] * rstd + vo[c0 + j + q];
-            }
-            if (zrow) *reinterpret_cast<float4 *>(zrow + j) = make_float4(z[0], z[1], z[2], z[3]);
-            store_out4(orow + j, make_float4(o[0], o[1], o[2], o[3]), P.out_mode);
-          }
+        for (int e = 0; e < 4; e++) {
+          const int j = 4 * q + e;
+          z[e] = __uint_as_float(r[j]) + vb[c0 + j];
+          o[e] = act_f<ACT>(z[e]);
+          if (NORM) o[e] = (o[e] - mean) * vs[c0 + j] * rstd + vo[c0 + j];
         }
+        const uint32_t off = (uint32_t)lane * 128u + ((((uint32_t)q) ^ sw) << 4);
+        if (B.Z) *reinterpret_cast<float4 *>(zb + off) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4 *>(ob + off) = make_float4(o[0], o[1], o[2], o[3]);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to TMA
+      __syncwarp();
+      if (lane == 0) {
+        if (B.Z) tma_store_2d(map_z, zb, c0, m0 + quad * 32);
+        if (P.out_mode == 0) tma_store_2d(map_o, ob, c0, m0 + quad * 32);
+        else tma_reduce_add_2d(map_o, ob, c0, m0 + quad * 32);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until TMA has read it; writes complete
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -276,6 +314,34 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BLOCK_N) : "memory");
+  }
+}
+
+// ---- the weights' two TF32 planes, refreshed once per optimizer step instead of once per tile and CTA ----
+__global__ void tf32_split_kernel(const float *__restrict__ src, long long n, float *__restrict__ hi, float *__restrict__ lo) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = src[i], h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h; lo[i] = v - h;
+  }
+}
+// table[e] = {src offset, rows, cols, dst offset}: dst[c][r] = src[r][c] for every 2-D weight, split on the way (the input-gradient product
+// reduces over the Linear's output features, so its K-major B operand is W^T)
+__global__ void tf32_split_transpose_kernel(const float *__restrict__ src, const long long *__restrict__ table, float *__restrict__ t_hi, float *__restrict__ t_lo) {
+  __shared__ float tile[32][33];
+  const long long so = table[4 * blockIdx.y], rows = table[4 * blockIdx.y + 1], cols = table[4 * blockIdx.y + 2], dof = table[4 * blockIdx.y + 3];
+  const long long tr = (rows + 31) / 32, tc = (cols + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (long long tid = blockIdx.x; tid < tr * tc; tid += gridDim.x) {
+    const long long r0 = (tid / tc) * 32, c0 = (tid % tc) * 32;
+    for (int k = ty; k < 32; k += 8) tile[k][tx] = (r0 + k < rows && c0 + tx < cols) ? src[so + (r0 + k) * cols + c0 + tx] : 0.f;
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      if (c0 + k < cols && r0 + tx < rows) {
+        const float v = tile[tx][k], h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        t_hi[dof + (c0 + k) * rows + r0 + tx] = h; t_lo[dof + (c0 + k) * rows + r0 + tx] = v - h;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -293,14 +359,14 @@ encode_tiled_fn get_encode() {
   return fn;
 }
 // 2-D fp32 tensor [rows, cols], row stride ld floats; box = [BLOCK_K cols, box_rows rows]; 128-byte swizzle; out-of-bounds reads give 0
-int make_map(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld, int box_rows) {
+int make_map(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld, int box_rows, int box_cols = BLOCK_K) {
   encode_tiled_fn enc = get_encode();
   if (!enc) FAIL(SHADOW_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) FAIL(SHADOW_EINVAL, "cuTensorMapEncodeTiled failed (%d): base %p rows %lld cols %lld ld %lld", (int)r, (const void *)base, rows, cols, ld);
   return 0;
@@ -315,7 +381,8 @@ extern "C" int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbra
   if (N < 8 || N > BLOCK_N || (N & 3) || K < 1) FAIL(SHADOW_EINVAL, "linear_tc: N must be a multiple of 4 in [8, %d] (got %d), K >= 1", BLOCK_N, N);
   if ((ldx & 3) || (ldw & 3) || (ldz & 3) || (ldo & 3)) FAIL(SHADOW_EINVAL, "linear_tc: leading dimensions must be multiples of 4 floats");
   if (out_mode < 0 || out_mode > 2) FAIL(SHADOW_EINVAL, "linear_tc: out_mode");
-  CUtensorMap mx[2], mw[2];
+  CUtensorMap mx[2], mw[2], mz[2], mo[2], mwl[2];
+  const bool presplit = br[0].W_lo != nullptr;
   LinearParams P;
   for (int b = 0; b < 2; b++) {
     const shadow_linear_branch &s = br[b < nbranch ? b : 0];
@@ -326,11 +393,20 @@ extern "C" int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbra
     if (rc) return rc;
     rc = make_map(&mw[b], s.W, N, K, ldw, BLOCK_N);
     if (rc) return rc;
+    if ((s.W_lo != nullptr) != presplit || ((uintptr_t)s.W_lo & 15)) FAIL(SHADOW_EINVAL, "linear_tc: W_lo must be given for all branches or none, 16-byte aligned");
+    rc = make_map(&mwl[b], presplit ? s.W_lo : s.W, N, K, ldw, BLOCK_N);
+    if (rc) return rc;
+    rc = make_map(&mo[b], s.out, M, N, ldo, 32, 32);                           // epilogue tiles: 32 rows x 32 columns, 128-byte swizzle
+    if (rc) return rc;
+    rc = make_map(&mz[b], s.Z ? s.Z : s.out, M, N, s.Z ? ldz : ldo, 32, 32);
+    if (rc) return rc;
     P.br[b].bias = s.bias; P.br[b].scale = s.scale; P.br[b].offset = s.offset; P.br[b].Z = s.Z; P.br[b].out = s.out;
     P.br[b].mean = do_norm ? s.mean : nullptr; P.br[b].rstd = do_norm ? s.rstd : nullptr;
   }
-  P.ldz = (int)ldz; P.ldo = (int)ldo; P.M = M; P.N = N; P.K = K; P.act = act; P.do_norm = do_norm; P.out_mode = out_mode;
-  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LinearParams);
+  P.ldz = (int)ldz; P.ldo = (int)ldo; P.M = M; P.N = N; P.K = K; P.act = act; P.do_norm = do_norm; P.out_mode = out_mode; P.presplit = presplit ? 1 : 0;
+  { const char *e = getenv("SHADOW_LTC_DEBUG"); P.debug = e ? atoi(e) : 0; }
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                         const CUtensorMap, const CUtensorMap, const CUtensorMap, const LinearParams);
   static const kern_t kerns[5][2] = {{linear_tc_kernel<0, false>, linear_tc_kernel<0, true>}, {linear_tc_kernel<1, false>, linear_tc_kernel<1, true>},
                                      {linear_tc_kernel<2, false>, linear_tc_kernel<2, true>}, {linear_tc_kernel<3, false>, linear_tc_kernel<3, true>},
                                      {linear_tc_kernel<4, false>, linear_tc_kernel<4, true>}};
@@ -338,7 +414,22 @@ extern "C" int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbra
   static bool attr_set[5][2] = {};
   const kern_t kern = kerns[act][do_norm ? 1 : 0];
   if (!attr_set[act][do_norm ? 1 : 0]) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_set[act][do_norm ? 1 : 0] = true; }
-  kern<<<dim3((M + BLOCK_M - 1) / BLOCK_M, nbranch), NUM_THREADS, SMEM_BYTES, (cudaStream_t)cuda_stream>>>(mx[0], mw[0], mx[1], mw[1], P);
+  kern<<<dim3((M + BLOCK_M - 1) / BLOCK_M, nbranch), NUM_THREADS, SMEM_BYTES, (cudaStream_t)cuda_stream>>>(mx[0], mw[0], mx[1], mw[1], mz[0], mo[0], mz[1], mo[1], mwl[0], mwl[1], P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int shadow_tf32_split_f32(const float *src, int64_t n, float *hi, float *lo, void *cuda_stream) {
+  if (n <= 0) return 0;
+  if (!src || !hi || !lo) FAIL(SHADOW_EINVAL, "tf32_split: NULL argument");
+  tf32_split_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 1184), 256, 0, (cudaStream_t)cuda_stream>>>(src, n, hi, lo);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int shadow_tf32_split_transpose_f32(const float *src, const int64_t *table_dev, int32_t num_entries, float *t_hi, float *t_lo, void *cuda_stream) {
+  if (num_entries <= 0) return 0;
+  if (!src || !table_dev || !t_hi || !t_lo) FAIL(SHADOW_EINVAL, "tf32_split_transpose: NULL argument");
+  tf32_split_transpose_kernel<<<dim3(64, num_entries), 256, 0, (cudaStream_t)cuda_stream>>>(src, (const long long *)table_dev, t_hi, t_lo);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -117,6 +117,8 @@ class DeepGNN(nn.Module):
             self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
             if self._world > 1:        # replicas must start from the same weights whatever each rank's RNG state was
                 dist.broadcast(self.optimizer.flat, src=0)
+            if self.optimizer.planes is not None:      # weights restored from a checkpoint later on: the TF32 planes follow
+                self.register_load_state_dict_post_hook(lambda module, incompatible: module.optimizer.planes.mark_stale())
         return self.optimizer
 
     # ---- models.py:209-237 ----

@@ -4,6 +4,7 @@ Every op here fails loudly without the CUDA library / a CUDA tensor: there is no
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -289,11 +290,56 @@ def _tc_ok(N, K, *ts):
         all(t is None or (t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() % 16 == 0) for t in ts)
 
 
-def _linear_tc(branches, M, N, K, act, do_norm, out_mode):
-    """branches: 1 or 2 tuples (X, W, bias, scale, offset, Z, out, mean, rstd) of the same shape -> one launch of shadow_linear_tc_f32"""
+class WeightPlanes:
+    """The two TF32 planes (head = what a TF32 tensor core reads, exact fp32 remainder) of every parameter of one flat buffer, and of the
+    TRANSPOSE of every 2-D parameter, kept in step with the weights by their owner (FlatAdamClip refreshes them right after each optimizer
+    step: 2 launches per step instead of a split of every weight tile in every CTA of every Linear launch).
+    Weights changed behind the owner's back (checkpoint restore, manual edits) must be followed by `mark_stale()`; DeepGNN does that from
+    a load_state_dict hook."""
+    _owners = []
+
+    def __init__(self, flat, params, offsets):
+        self.flat, self.n = flat, flat.numel()
+        self.hi, self.lo, self.t_hi, self.t_lo = (torch.zeros_like(flat) for _ in range(4))
+        rows = [(offsets[id(p)], p.shape[0], p.shape[1], offsets[id(p)]) for p in params if p.dim() == 2]
+        self.table = torch.tensor(rows if rows else [(0, 0, 0, 0)], dtype=torch.int64, device=flat.device)
+        self.ntab = len(rows)
+        self.fresh = False
+        WeightPlanes._owners = [r for r in WeightPlanes._owners if r() is not None and r().flat.data_ptr() != flat.data_ptr()] + [weakref.ref(self)]
+
+    def mark_stale(self):
+        self.fresh = False
+
+    def refresh(self):
+        check(lib.shadow_tf32_split_f32(_p(self.flat), self.n, _p(self.hi), _p(self.lo), _stream(self.flat)))
+        check(lib.shadow_tf32_split_transpose_f32(_p(self.flat), _p(self.table), self.ntab, _p(self.t_hi), _p(self.t_lo), _stream(self.flat)))
+        self.fresh = True
+
+    @staticmethod
+    def of(w, transposed=False):
+        """(hi, lo) planes of the weight `w` (a view into a registered flat buffer) or of its transpose; None when `w` is not registered"""
+        if os.environ.get("SHADOW_LTC_PRESPLIT", "1") == "0":
+            return None
+        for r in WeightPlanes._owners:
+            o = r()
+            if o is None:
+                continue
+            off = (w.data_ptr() - o.flat.data_ptr()) // 4
+            if 0 <= off < o.n and w.is_contiguous() and w.device == o.flat.device:
+                if not o.fresh:
+                    o.refresh()
+                a, b = (o.t_hi, o.t_lo) if transposed else (o.hi, o.lo)
+                shape = (w.shape[1], w.shape[0]) if transposed else tuple(w.shape)
+                return a[off:off + w.numel()].view(shape), b[off:off + w.numel()].view(shape)
+        return None
+
+
+def _linear_tc(branches, M, N, K, act, do_norm, out_mode, w_lo=None):
+    """branches: 1 or 2 tuples (X, W, bias, scale, offset, Z, out, mean, rstd) of the same shape -> one launch of shadow_linear_tc_f32;
+    w_lo: the weights' remainder planes when W holds their TF32 heads (WeightPlanes)"""
     arr = (LinearBranch * 2)()
     for i, b in enumerate(branches):
-        arr[i] = LinearBranch(*[None if t is None else t.data_ptr() for t in b])
+        arr[i] = LinearBranch(*[None if t is None else t.data_ptr() for t in b], None if w_lo is None else w_lo[i].data_ptr())
     x, w, out, Z = branches[0][0], branches[0][1], branches[0][6], branches[0][5]
     check(lib.shadow_linear_tc_f32(arr, len(branches), x.stride(0), w.stride(0), Z.stride(0) if Z is not None else N, out.stride(0), M, N, K, act,
                                    int(do_norm), out_mode, _stream(x)))
@@ -303,11 +349,15 @@ def _dgrad_tc_pair(dZs, ws):
     """[dZ W for each pair] on the tcgen05 kernel: the product reduces over the Linear's OUTPUT features, so the K-major B operand is W^T"""
     M, N_out = dZs[0].shape
     K_in = ws[0].shape[1]
-    wts = [w.detach().t().contiguous() for w in ws]
+    planes = [WeightPlanes.of(w.detach(), transposed=True) for w in ws]
+    if all(pl is not None for pl in planes):
+        wts, w_lo = [pl[0] for pl in planes], [pl[1] for pl in planes]
+    else:
+        wts, w_lo = [w.detach().t().contiguous() for w in ws], None
     outs = [torch.empty((M, K_in), dtype=torch.float32, device=dZs[0].device) for _ in dZs]
-    if not _tc_ok(K_in, N_out, *dZs, *wts, *outs):
+    if not _tc_ok(K_in, N_out, *dZs, *wts, *outs) or (w_lo is not None and not _tc_ok(K_in, N_out, *w_lo)):
         return None
-    _linear_tc([(dz, wt, None, None, None, None, o, None, None) for dz, wt, o in zip(dZs, wts, outs)], M, K_in, N_out, ACT_ID["I"], False, 0)
+    _linear_tc([(dz, wt, None, None, None, None, o, None, None) for dz, wt, o in zip(dZs, wts, outs)], M, K_in, N_out, ACT_ID["I"], False, 0, w_lo)
     return outs
 
 
@@ -371,6 +421,32 @@ def _act_norm_bwd_raw(dOut, Z, scale, offset, bias, idx, mean, rstd, act, do_nor
     return dZ
 
 
+_ANB_SCRATCH = {}
+
+
+def _act_norm_bwd_pair(dOut, Zs, scale, offset, biases, idxs, means, rstds, act, do_norm):
+    """dZ of one or two branches that share dOut (csrc/layers.cu: act_norm_bwd_pair_kernel + colsum_finish_kernel, deterministic);
+    dscale[idx] / doffset[idx] / dbias are accumulated straight into the parameters' .grad"""
+    n, D = Zs[0].shape
+    dev = dOut.device
+    key = (dev.index, D)
+    if key not in _ANB_SCRATCH:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        _ANB_SCRATCH[key] = torch.empty(2 * sms * 2 * 3 * D, dtype=torch.float32, device=dev)
+    scratch = _ANB_SCRATCH[key]
+    dZs = [torch.empty_like(Z) for Z in Zs]
+    nb = len(Zs)
+    sc = [scale.detach()[i] if do_norm else None for i in idxs]
+    ds = [_grad_of(scale)[i] if do_norm else None for i in idxs]
+    do = [_grad_of(offset)[i] if do_norm else None for i in idxs]
+    db = [_grad_of(b) if b is not None else None for b in biases]
+    g = lambda lst, i: _p(lst[i]) if i < nb else None
+    check(lib.shadow_act_norm_bwd_pair_f32(_p(dOut), D, g(Zs, 0), g(Zs, 1), D, g(sc, 0), g(sc, 1), g(means, 0), g(rstds, 0), g(means, 1), g(rstds, 1),
+                                           g(dZs, 0), g(dZs, 1), D, g(ds, 0), g(do, 0), g(db, 0), g(ds, 1), g(do, 1), g(db, 1), n, D, act, int(do_norm),
+                                           _p(scratch), scratch.numel(), _stream(dOut)))
+    return dZs
+
+
 class _LinearActNorm(torch.autograd.Function):
     """out = norm_feat_idx(act(x W^T + b)) with ONE fused backward kernel; parameter gradients (W, b, scale[idx], offset[idx]) are
     accumulated in place into `.grad` (the flat bucket of FlatAdamClip), so autograd launches no bias-sum / select / accumulate kernels"""
@@ -386,8 +462,9 @@ class _LinearActNorm(torch.autograd.Function):
             out = torch.empty_like(Z)
             mean = torch.empty(M, dtype=torch.float32, device=x.device)
             rstd = torch.empty(M, dtype=torch.float32, device=x.device)
-            _linear_tc([(x, w, lin_b.detach() if lin_b is not None else None, scale.detach()[idx] if do_norm else None,
-                         offset.detach()[idx] if do_norm else None, Z, out, mean, rstd)], M, N, K, act, do_norm, 0)
+            pl = WeightPlanes.of(w)
+            _linear_tc([(x, pl[0] if pl else w, lin_b.detach() if lin_b is not None else None, scale.detach()[idx] if do_norm else None,
+                         offset.detach()[idx] if do_norm else None, Z, out, mean, rstd)], M, N, K, act, do_norm, 0, [pl[1]] if pl else None)
         else:
             Z = _linear_fwd(x, lin_w, lin_b)
             out, mean, rstd = _act_norm_fwd_raw(Z, scale, offset, idx, act, do_norm)
@@ -399,7 +476,10 @@ class _LinearActNorm(torch.autograd.Function):
     def backward(ctx, dOut):
         x, Z, mean, rstd = ctx.saved_tensors
         lin_w, lin_b, scale, offset, idx, act, do_norm = ctx.p
-        dZ = _act_norm_bwd_raw(dOut.contiguous(), Z, scale, offset, lin_b, idx, mean, rstd, act, do_norm)
+        if Z.shape[1] <= 256 and Z.shape[0] > 0:
+            dZ = _act_norm_bwd_pair(dOut.contiguous(), [Z], scale, offset, [lin_b], [idx], [mean], [rstd], act, do_norm)[0]
+        else:
+            dZ = _act_norm_bwd_raw(dOut.contiguous(), Z, scale, offset, lin_b, idx, mean, rstd, act, do_norm)
         _accum_wgrad(lin_w, dZ, x)
         dX = None
         if ctx.needs_input_grad[0]:
@@ -431,8 +511,11 @@ class _SageLayer(torch.autograd.Function):
             out = torch.zeros_like(Zs)
             mean_s, rstd_s, mean_n, rstd_n = (torch.empty(M, dtype=torch.float32, device=x.device) for _ in range(4))
             sc, of = scale.detach(), offset.detach()
-            _linear_tc([(x, w0, bs.detach(), sc[0] if do_norm else None, of[0] if do_norm else None, Zs, out, mean_s, rstd_s),
-                        (agg, w1, bn.detach(), sc[1] if do_norm else None, of[1] if do_norm else None, Zn, out, mean_n, rstd_n)], M, N, K, act, do_norm, 2)
+            p0, p1 = WeightPlanes.of(w0), WeightPlanes.of(w1)
+            pre = p0 is not None and p1 is not None
+            _linear_tc([(x, p0[0] if pre else w0, bs.detach(), sc[0] if do_norm else None, of[0] if do_norm else None, Zs, out, mean_s, rstd_s),
+                        (agg, p1[0] if pre else w1, bn.detach(), sc[1] if do_norm else None, of[1] if do_norm else None, Zn, out, mean_n, rstd_n)],
+                       M, N, K, act, do_norm, 2, [p0[1], p1[1]] if pre else None)
         else:
             Zs, Zn = _linear_fwd_pair(x, ws, bs, agg, wn, bn)
             out, mean_s, rstd_s = _act_norm_fwd_raw(Zs, scale, offset, 0, act, do_norm)
@@ -446,8 +529,11 @@ class _SageLayer(torch.autograd.Function):
         x, agg, Zs, Zn, mean_s, rstd_s, mean_n, rstd_n = ctx.saved_tensors
         adj, ws, bs, wn, bn, scale, offset, act, do_norm = ctx.p
         dOut = dOut.contiguous()
-        dZs = _act_norm_bwd_raw(dOut, Zs, scale, offset, bs, 0, mean_s, rstd_s, act, do_norm)
-        dZn = _act_norm_bwd_raw(dOut, Zn, scale, offset, bn, 1, mean_n, rstd_n, act, do_norm)
+        if Zs.shape[1] <= 256 and Zs.shape[0] > 0:       # both branches in one launch: dOut is read once, column sums without atomics
+            dZs, dZn = _act_norm_bwd_pair(dOut, [Zs, Zn], scale, offset, [bs, bn], [0, 1], [mean_s, mean_n], [rstd_s, rstd_n], act, do_norm)
+        else:
+            dZs = _act_norm_bwd_raw(dOut, Zs, scale, offset, bs, 0, mean_s, rstd_s, act, do_norm)
+            dZn = _act_norm_bwd_raw(dOut, Zn, scale, offset, bn, 1, mean_n, rstd_n, act, do_norm)
         _accum_wgrad_pair(ws, dZs, x, wn, dZn, agg)
         if not ctx.needs_input_grad[0]:
             return (None,) * 10
@@ -535,14 +621,17 @@ class FlatAdamClip:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
+        self.offsets = {}                                    # id(parameter) -> first float of the parameter in the flat buffers
         for p in self.params:
             k = p.numel()
+            self.offsets[id(p)] = off
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             p.grad = self.grad[off:off + k].view_as(p)
             off += (k + 3) // 4 * 4
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.planes = WeightPlanes(self.flat, self.params, self.offsets) if self.flat.is_cuda and _LINEAR == "tc" else None
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
@@ -554,6 +643,8 @@ class FlatAdamClip:
         check(lib.shadow_adam_clip_step_f32(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.flat.numel(), grad_scale,
                                             self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps, _p(self.step_dev), _p(self.sqnorm),
                                             _stream(self.flat)))
+        if self.planes is not None:
+            self.planes.refresh()
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_dev, "lr": self.lr}

@@ -17,13 +17,19 @@ def world_info():
 
 
 def partition_targets(targets, rank, world, batch_size=1):
-    """Strided slice of the epoch's target order, truncated so that every rank owns the same number of whole batches
-    (all ranks must run the same number of steps, or the all-reduce would hang)."""
+    """Strided slice of the epoch's target order.  Every rank must run the same number of steps (or the all-reduce would hang), so the
+    slices are PADDED to the same whole number of batches by wrapping around to the head of the rank's own slice: no
+    target is dropped, at most `batch_size * world - 1` are seen twice in an epoch."""
     targets = np.asarray(targets)
-    per_rank = (targets.size // world // batch_size) * batch_size
-    if per_rank == 0:
-        per_rank = targets.size // world
-    return targets[rank::world][:per_rank]
+    if targets.size == 0 or world <= 1:
+        return targets                                                   # one rank: the reference's own epoch (short last batch, minibatch.py:252-262)
+    mine = targets[rank::world]
+    longest = -(-targets.size // world)                                  # ceil: the longest strided slice
+    per_rank = -(-longest // batch_size) * batch_size
+    if mine.size == 0:                                                   # fewer targets than ranks: borrow from the global order
+        mine = targets[:1]
+    reps = -(-per_rank // mine.size)
+    return np.concatenate([mine] * reps)[:per_rank] if mine.size < per_rank else mine[:per_rank]
 
 
 def allreduce_flat_gradients(flat_grad):
@@ -32,3 +38,19 @@ def allreduce_flat_gradients(flat_grad):
     if world > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
     return 1.0 / world
+
+
+def allreduce_two_buckets(flat_grad, split, side_stream):
+    """inside a stream capture: the tail bucket flat_grad[split:] (the layers whose backward is already done) is reduced on `side_stream`
+    while the rest of the backward pass runs on the current stream; returns nothing -- finish with `join_buckets`"""
+    cur = torch.cuda.current_stream()
+    side_stream.wait_stream(cur)
+    with torch.cuda.stream(side_stream):
+        dist.all_reduce(flat_grad[split:], op=dist.ReduceOp.SUM)
+
+
+def join_buckets(flat_grad, split, side_stream):
+    """the head bucket on the current stream, then wait for the tail bucket"""
+    if split > 0:
+        dist.all_reduce(flat_grad[:split], op=dist.ReduceOp.SUM)
+    torch.cuda.current_stream().wait_stream(side_stream)

@@ -12,7 +12,11 @@ PRESETS = {
     "S-arxiv":    (169_343,     2_320_000,    13_161, 128, 40,   90_941, 0),
     "S-products": (2_449_029, 123_700_000,    17_481, 100, 47,  196_615, 1),
     "S-papers":   (111_059_956, 3_230_000_000, 100_000, 128, 172, 1_207_179, 2),
+    # the same sizes with COMMUNITY structure (planted partition, see clustered_graph_torch): a PPR scope then induces thousands of edges
+    "S-products-c": (2_449_029, 123_700_000,  17_481, 100, 47,  196_615, 1),
+    "S-papers-8":   (13_882_495,  403_750_000, 100_000, 128, 172,   150_897, 2),      # one eighth of S-papers (per-GPU share of an 8-GPU box)
 }
+CLUSTERED = {"S-products-c": (192, 0.75)}        # name -> (community size, probability that an edge stays inside its community)
 
 
 def _coo_to_csr_sym(src, dst, n):
@@ -48,9 +52,12 @@ def powerlaw_graph(n, nnz_target, seed, dmax=None, tail=False):
     return _coo_to_csr_sym(src, dst, n)
 
 
-def powerlaw_graph_torch(n, nnz_target, seed, dmax, device):
+def powerlaw_graph_torch(n, nnz_target, seed, dmax, device, community=None):
     """Same recipe on the GPU with torch ops (setup only, not part of any timed region):
-    the S-products graph (124 M edges) takes seconds instead of a minute of host sorting."""
+    the S-products graph (124 M edges) takes seconds instead of a minute of host sorting.
+    community = (size, p_in): planted partition -- nodes [j * size, (j + 1) * size) form a community and an edge's second endpoint is
+    drawn inside the first endpoint's community with probability p_in, uniformly otherwise.  Real co-purchase / citation graphs are
+    clustered like this; the uniform recipe is not (a 141-node PPR scope keeps 3 % of the slots it scans there, 20-60 % here)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -63,6 +70,12 @@ def powerlaw_graph_torch(n, nnz_target, seed, dmax, device):
     deg = torch.clamp(torch.floor(raw * c) + 1, max=dmax).long()
     src = torch.repeat_interleave(torch.arange(n, device=device), deg)
     dst = torch.randint(0, n, (src.numel(),), generator=g, device=device)
+    if community is not None:
+        size, p_in = community
+        inside = torch.rand(src.numel(), generator=g, device=device) < p_in
+        local = torch.div(src, size, rounding_mode="floor") * size + torch.randint(0, size, (src.numel(),), generator=g, device=device)
+        dst = torch.where(inside, local.clamp_max(n - 1), dst)
+        del inside, local
     keep = src != dst
     src, dst = src[keep], dst[keep]
     key = torch.cat([src * n + dst, dst * n + src])

@@ -7,13 +7,15 @@ Dropout uses torch's graph-safe Philox state; dropedge reads its stream position
 (csrc/layers.cu: dropedge_kernel), so every replay drops different edges.  Batches that do not fit the captured capacity (the short
 batch at the end of an epoch, an unusually large scope) run through the eager `DeepGNN.step`.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
 
 from .minibatch import TRAIN
 from .ops import DeviceCSR
-from .parallel import allreduce_flat_gradients
+from .parallel import allreduce_flat_gradients, allreduce_two_buckets, join_buckets
 
 
 class GraphedTrainer:
@@ -43,15 +45,51 @@ class GraphedTrainer:
             self.world = torch.distributed.get_world_size()
         self.graph_bwd = None
         self.eager_steps = self.graph_steps = 0
+        # data parallel: the gradient exchange and the optimizer live INSIDE the captured step.  The flat gradient buffer is cut in two
+        # at the first parameter of conv layer `_split_layer`: the tail bucket (that layer and everything behind it: later layers, pooling,
+        # classifier) is all-reduced on a side stream as soon as the layer's input gradient exists, i.e. while the earlier layers are
+        # still in their backward pass; only the head bucket's exchange is exposed.  SHADOW_DP_GRAPH=0 keeps the exchange outside the graph.
+        self.dp_in_graph = self.world > 1 and os.environ.get("SHADOW_DP_GRAPH", "1") != "0"
+        self._side = None
+        self._split = 0
+        self._split_layer = None
 
     # ------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd(self, exchange=False):
         m = self.model
         adj = DeviceCSR(self.span, self.col, 0, self.val, row_ord=self.rowptr)
+        handle = None
+        if exchange and self._split > 0:
+            opt = m.optimizer
+
+            def fire(module, inputs, output):                # the split layer's OUTPUT gradient exists <=> every later layer's backward is done
+                output[0].register_hook(lambda g: allreduce_two_buckets(opt.grad, self._split, self._side))
+            handle = self._split_prev.register_forward_hook(fire)
         preds, _ = m(self.mode, [self.feat], [adj], [self.target], self.sizes, [{}], m.dropedge)
+        if handle is not None:
+            handle.remove()
         loss = m._loss(preds, self.label)
         loss.backward()
+        if exchange:
+            opt = m.optimizer
+            if self._split > 0:
+                join_buckets(opt.grad, self._split, self._side)
+            else:
+                allreduce_flat_gradients(opt.grad)
         self.loss.copy_(loss.detach())
+
+    def _plan_buckets(self, opt):
+        """tail bucket = conv layers [L - L//2 ..) + pooling + classifier (about the second half of the parameters, whose gradients are
+        complete after the first ~half of the backward pass)"""
+        convs = list(self.model.conv_layers[0])
+        if len(convs) < 2:
+            return
+        k = len(convs) - max(1, len(convs) // 2)             # first layer of the tail bucket
+        first = next(iter(convs[k].parameters()), None)
+        if first is None or id(first) not in opt.offsets:
+            return
+        self._split, self._split_prev = opt.offsets[id(first)], convs[k - 1]
+        self._side = torch.cuda.Stream()
 
     def _capture(self):
         m = self.model
@@ -66,13 +104,18 @@ class GraphedTrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         opt.zero_grad()
+        if self.dp_in_graph:
+            self._plan_buckets(opt)
+            torch.distributed.all_reduce(torch.zeros(8, device=opt.grad.device))      # the communicator exists before the capture starts
+            torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             opt.grad.zero_()
-            self._fwd_bwd()
-            if self.world == 1:
-                opt.step(1.0)
-        # with several ranks the gradient all-reduce sits between the captured fwd/bwd and the (eager, 3-launch) optimizer step
+            self._fwd_bwd(exchange=self.dp_in_graph)
+            if self.world == 1 or self.dp_in_graph:
+                opt.step(1.0 / self.world)
+        # SHADOW_DP_GRAPH=0: the gradient all-reduce sits between the captured fwd/bwd and the (eager, 4-launch) optimizer step
 
     def _load_static(self, sb, bs):
         a = sb.cursor
@@ -106,7 +149,7 @@ class GraphedTrainer:
                 if self.graph is None:
                     self._capture()
                 self.graph.replay()
-                if self.world > 1:
+                if self.world > 1 and not self.dp_in_graph:
                     opt = self.model.optimizer
                     opt.step(allreduce_flat_gradients(opt.grad))
                 self.graph_steps += 1

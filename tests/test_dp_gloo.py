@@ -49,8 +49,12 @@ def test_dp2_equals_dp1(tmp_path):
 
 
 def test_partition_targets_equal_whole_batches():
+    """every rank gets the same whole number of batches; the tail of the epoch is padded by wrap-around, never dropped"""
     t = np.arange(1000)
     parts = [partition_targets(t, r, 8, batch_size=32) for r in range(8)]
-    assert len({p.size for p in parts}) == 1 and parts[0].size % 32 == 0 and parts[0].size == 96
-    assert len(set(np.concatenate(parts).tolist())) == 8 * 96
-    assert partition_targets(t, 0, 1, 32).size == 992
+    assert len({p.size for p in parts}) == 1 and parts[0].size % 32 == 0 and parts[0].size == 128
+    assert set(np.concatenate(parts).tolist()) == set(range(1000))              # nothing dropped
+    for r, p in enumerate(parts):
+        assert set(p.tolist()) == set(t[r::8].tolist())                          # padding comes from the rank's own slice
+    assert partition_targets(t, 0, 1, 32).size == 1000                           # one rank: the reference's epoch, short last batch included
+    assert partition_targets(np.arange(3), 5, 8, 2).size == 2                    # fewer targets than ranks

@@ -418,3 +418,53 @@ def test_tcgen05_linear_rejects_misaligned_shapes():
     x = torch.randn(64, 256, device="cuda")
     assert not ops._tc_ok(47, 256, x) and not ops._tc_ok(256, 30, x) and not ops._tc_ok(512, 256, x)
     assert not ops._tc_ok(256, 256, x[:, 1:])        # not contiguous / not 16-byte aligned
+
+
+def test_presplit_weight_planes_equal_in_kernel_split_and_follow_checkpoints(monkeypatch):
+    """the TF32 planes of the weights that FlatAdamClip refreshes after every optimizer step (ops.WeightPlanes; read by csrc/linear_tc.cu instead
+    of splitting every weight tile in every CTA) give bit-identical training to the in-kernel split, and a load_state_dict after the optimizer
+    exists is followed by the planes (stale planes would silently compute with the old weights)"""
+    from shadow_gnn_b200 import minibatch as MB, ops
+    from shadow_gnn_b200.models import DeepGNN
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(2000, 12, 9)
+    N = indptr.size - 1
+    torch.manual_seed(0)
+    label = torch.randint(0, 4, (N,))
+    feat = torch.randn(N, 16)
+    train = np.arange(0, 256, dtype=np.int64)
+    cfg = {"batch_size": 32, "configs": [{"method": "ppr", "k": [20], "threshold": [0.0], "epsilon": [1e-4]}]}
+    arch = dict(num_layers=3, num_cls_layers=1, heads=1, branch_sharing=False, dim=32, act="relu", layer_norm="norm_feat", feature_augment_ops="sum",
+                aggr="sage", residue="none", pooling="center", loss="softmax", ensemble_act="leakyrelu")
+    runs = []
+    for presplit in ("1", "0"):
+        monkeypatch.setenv("SHADOW_LTC_PRESPLIT", presplit)
+        torch.manual_seed(1); np.random.seed(1)
+        mb = MB.MinibatchShallowExtractor("toy", None, {m: (indptr, indices) for m in range(3)}, {0: train, 1: train[:64], 2: train[:64]}, cfg, set(), None,
+                                          feat, label, 16, True, 1, seed_cpp=1, num_subg_per_batch=128)
+        model = DeepGNN(16, 16, 4, 0, arch, [], 1, dict(dropout=0.0, dropedge=0.0, lr=0.01, ensemble_dropout="none"), "node").cuda()
+        mb.epoch_start_reset(0, MB.TRAIN); mb.shuffle_entity(MB.TRAIN)
+        losses = []
+        while not mb.is_end_epoch(MB.TRAIN):
+            losses.append(model.step(MB.TRAIN, "running", mb.one_batch(MB.TRAIN))["loss"].detach().clone())
+        runs.append((torch.stack(losses), [p.detach().clone() for p in model.parameters()], model, mb))
+    # the two forward passes are bit-identical; spmm backward and the weight-gradient split accumulate with fp32 atomics (order varies run to
+    # run), so losses after the first step and the parameters agree to rounding
+    assert torch.equal(runs[0][0][0], runs[1][0][0])
+    assert torch.allclose(runs[0][0], runs[1][0], rtol=1e-4, atol=1e-6)
+    for a, b in zip(runs[0][1], runs[1][1]):
+        close(a, b.cpu(), "parameters: pre-split planes vs in-kernel split")
+    # checkpoint restore with live planes: the forward pass must see the restored weights
+    monkeypatch.setenv("SHADOW_LTC_PRESPLIT", "1")
+    model, mb = runs[0][2], runs[0][3]
+    assert model.optimizer.planes is not None and model.optimizer.planes.fresh
+    mb.epoch_start_reset(0, MB.VALID); mb.shuffle_entity(MB.VALID)
+    b = mb.one_batch(MB.VALID)
+    before = model.step(MB.VALID, "running", b)["preds"].clone()
+    sd = {k: (v * 0.5 if v.dim() == 2 else v.clone()) for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)
+    assert not model.optimizer.planes.fresh
+    after = model.step(MB.VALID, "running", b)["preds"]
+    monkeypatch.setenv("SHADOW_LTC_PRESPLIT", "0")
+    want = model.step(MB.VALID, "running", b)["preds"]
+    assert torch.equal(after, want) and not torch.equal(after, before)
