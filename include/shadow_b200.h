@@ -215,6 +215,13 @@ typedef struct shadow_linear_branch {
 } shadow_linear_branch;
 int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbranch, int64_t ldx, int64_t ldw, int64_t ldz, int64_t ldo, int32_t M,
                          int32_t N, int32_t K, int32_t act, int32_t do_norm, int32_t out_mode, void *cuda_stream);
+/* Weight gradient on the same tensor-core path:  grad[N_out, K_in] += dZ[M, N_out]^T X[M, K_in]  for one or two (dZ, X, grad) triples
+ * (dZ1 NULL = one).  The batch is cut into 128-row slices, every slice's partial product goes to scratch (shadow_wgrad_tc_scratch_floats
+ * floats per triple) and a second kernel adds the slices in slice order: deterministic.  Row-major contiguous operands (ld = N_out / K_in),
+ * N_out and K_in multiples of 4 in [8, 256], 16-byte aligned pointers. */
+int64_t shadow_wgrad_tc_scratch_floats(int32_t M, int32_t N_out, int32_t K_in);
+int shadow_wgrad_tc_f32(const float *dZ0, const float *X0, float *grad0, float *scratch0, const float *dZ1, const float *X1, float *grad1,
+                        float *scratch1, int32_t M, int32_t N_out, int32_t K_in, void *cuda_stream);
 /* hi = src with the low 13 mantissa bits cleared (what a TF32 tensor core reads), lo = src - hi (exact in fp32) */
 int shadow_tf32_split_f32(const float *src, int64_t n, float *hi, float *lo, void *cuda_stream);
 /* the same for the TRANSPOSE of every 2-D weight inside one flat buffer: table_dev[e] = {src offset, rows, cols, dst offset} (int64, device) */

@@ -217,32 +217,68 @@ __global__ void __launch_bounds__(LAYER_BLOCK) spmm_fwd_scalar_kernel(const int2
     }
   }
 }
-// backward: dX[c,:] += val[p] * dY[i,:] with 128-bit vector reductions (red.global.add.v4.f32, sm_90+)
+// backward: dX[c,:] += val[p] * dY[i,:] with 128-bit vector reductions (red.global.add.v4.f32, sm_90+).  The dY row lives in registers
+// (F <= 256: two float4 per lane); a row longer than 32 edges (the root's ~140 in-scope neighbours) is not walked by one warp: it is queued
+// and all warps of the CTA take 32-edge pieces of it afterwards -- the kernel's duration used to be that one warp's serial walk.
 template <bool VEC>
 __global__ void __launch_bounds__(LAYER_BLOCK) spmm_bwd_kernel(const int2 *__restrict__ row_span, const int *__restrict__ col, int col_off,
                                                                const float *__restrict__ val, const float *__restrict__ dY, float *__restrict__ dX,
                                                                int n, int F) {
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
-    const int2 sp = row_span[i];
-    if (VEC) {
-      const int F4 = F >> 2;
-      for (int p0 = sp.x; p0 < sp.y; p0 += 32) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  __shared__ int long_rows[LAYER_BLOCK / 32];
+  __shared__ int n_long;
+  if (VEC) {
+    const int F4 = F >> 2;
+    const bool small = F4 <= 64;
+    auto walk = [&](const int i, const int p_lo, const int p_hi) {      // edges [p_lo, p_hi) of row i
+      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+      if (small) {
+        if (lane < F4) g0 = reinterpret_cast<const float4 *>(dY + (size_t)i * F)[lane];
+        if (lane + 32 < F4) g1 = reinterpret_cast<const float4 *>(dY + (size_t)i * F)[lane + 32];
+      }
+      for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
         const int pl = p0 + lane;
-        const int c_l = pl < sp.y ? col[pl] - col_off : 0;
-        const float w_l = pl < sp.y ? (val ? val[pl] : 1.f) : 0.f;
-        const int cnt = min(32, sp.y - p0);
+        const int c_l = pl < p_hi ? col[pl] - col_off : 0;
+        const float w_l = pl < p_hi ? (val ? val[pl] : 1.f) : 0.f;
+        const int cnt = min(32, p_hi - p0);
         for (int u = 0; u < cnt; u++) {                        // shuffles outside the feature loop: every lane takes part
           const int c = __shfl_sync(0xffffffffu, c_l, u);
           const float w = __shfl_sync(0xffffffffu, w_l, u);
           if (w == 0.f) continue;
-          for (int f = lane; f < F4; f += 32) {
-            const float4 g = reinterpret_cast<const float4 *>(dY + (size_t)i * F)[f];
-            atomicAdd(reinterpret_cast<float4 *>(dX + (size_t)c * F) + f, make_float4(w * g.x, w * g.y, w * g.z, w * g.w));
+          float4 *dst = reinterpret_cast<float4 *>(dX + (size_t)c * F);
+          if (small) {
+            if (lane < F4) atomicAdd(dst + lane, make_float4(w * g0.x, w * g0.y, w * g0.z, w * g0.w));
+            if (lane + 32 < F4) atomicAdd(dst + lane + 32, make_float4(w * g1.x, w * g1.y, w * g1.z, w * g1.w));
+          } else {
+            for (int f = lane; f < F4; f += 32) {
+              const float4 g = reinterpret_cast<const float4 *>(dY + (size_t)i * F)[f];
+              atomicAdd(dst + f, make_float4(w * g.x, w * g.y, w * g.z, w * g.w));
+            }
           }
         }
       }
-    } else {
+    };
+    for (int base = blockIdx.x * wpb; base < n; base += gridDim.x * wpb) {
+      if (threadIdx.x == 0) n_long = 0;
+      __syncthreads();
+      const int i = base + warp;
+      if (i < n) {
+        const int2 sp = row_span[i];
+        if (sp.y - sp.x > 32) { if (lane == 0) long_rows[atomicAdd(&n_long, 1)] = i; }
+        else walk(i, sp.x, sp.y);
+      }
+      __syncthreads();
+      const int nl = n_long;
+      for (int r = 0; r < nl; r++) {
+        const int il = long_rows[r];
+        const int2 sp = row_span[il];
+        for (int p = sp.x + 32 * warp; p < sp.y; p += 32 * wpb) walk(il, p, min(p + 32, sp.y));
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int i = blockIdx.x * wpb + warp; i < n; i += gridDim.x * wpb) {
+      const int2 sp = row_span[i];
       for (int f = lane; f < F; f += 32) {
         const float g = dY[(size_t)i * F + f];
         for (int p = sp.x; p < sp.y; p++) {
@@ -380,44 +416,95 @@ struct AnbPair {
   const float *Z[2], *scale[2], *mean[2], *rstd[2];
   float *dZ[2], *dscale[2], *doffset[2], *dbias[2];
 };
-template <int NPL, int NB>
-__global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_pair_kernel(const float *__restrict__ dOut, int ldo, const AnbPair A, int ldz, int lddz, int n, int D, int act,
-                                                                        int do_norm, float *__restrict__ partials) {
+template <int ACT>
+__device__ __forceinline__ float act_ft(float z) {
+  if (ACT == ACT_RELU) return z > 0.f ? z : 0.f;
+  if (ACT == ACT_ELU) return z > 0.f ? z : expm1f(z);
+  if (ACT == ACT_TANH) return tanhf(z);
+  if (ACT == ACT_LRELU) return z > 0.f ? z : 0.2f * z;
+  return z;
+}
+template <int ACT>
+__device__ __forceinline__ float act_dft(float z, float a) {
+  if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (ACT == ACT_ELU) return z > 0.f ? 1.f : a + 1.f;
+  if (ACT == ACT_TANH) return 1.f - a * a;
+  if (ACT == ACT_LRELU) return z > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+// NV float4 per lane (D <= 128 * NV, D % 4 == 0): lane l owns features 4 * (l + 32 v) .. + 3
+template <int NV, int NB, int ACT, bool NORM>
+__global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_pair_kernel(const float *__restrict__ dOut, int ldo, const AnbPair A, int ldz, int lddz, int n, int D,
+                                                                        float *__restrict__ partials) {
   extern __shared__ float sh[];               // [warps][NB][3][D]
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  float ps[NB][NPL], po[NB][NPL], pb[NB][NPL];
+  float ps[NB][NV][4], po[NB][NV][4], pb[NB][NV][4], sc[NB][NV][4];
+  bool on[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) on[v] = 4 * (lane + 32 * v) < D;
 #pragma unroll
   for (int b = 0; b < NB; b++)
 #pragma unroll
-    for (int k = 0; k < NPL; k++) { ps[b][k] = 0.f; po[b][k] = 0.f; pb[b][k] = 0.f; }
-  for (int i = blockIdx.x * wpb + warp; i < n; i += gridDim.x * wpb) {
-    float g[NPL];
+    for (int v = 0; v < NV; v++) {
+      float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (NORM && on[v]) s4 = reinterpret_cast<const float4 *>(A.scale[b])[lane + 32 * v];
+      sc[b][v][0] = s4.x; sc[b][v][1] = s4.y; sc[b][v][2] = s4.z; sc[b][v][3] = s4.w;
 #pragma unroll
-    for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; g[k] = (f < D) ? dOut[(size_t)i * ldo + f] : 0.f; }
+      for (int e = 0; e < 4; e++) { ps[b][v][e] = 0.f; po[b][v][e] = 0.f; pb[b][v][e] = 0.f; }
+    }
+  for (int i = blockIdx.x * wpb + warp; i < n; i += gridDim.x * wpb) {
+    float g[NV][4];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on[v]) g4 = reinterpret_cast<const float4 *>(dOut + (size_t)i * ldo)[lane + 32 * v];
+      g[v][0] = g4.x; g[v][1] = g4.y; g[v][2] = g4.z; g[v][3] = g4.w;
+    }
+    float4 z4[NB][NV];
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+#pragma unroll
+      for (int v = 0; v < NV; v++) z4[b][v] = on[v] ? reinterpret_cast<const float4 *>(A.Z[b] + (size_t)i * ldz)[lane + 32 * v] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-      float a[NPL], z[NPL];
+      float z[NV][4], a[NV][4], dz[NV][4];
 #pragma unroll
-      for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; z[k] = (f < D) ? A.Z[b][(size_t)i * ldz + f] : 0.f; a[k] = act_f(z[k], act); }
-      if (do_norm) {
+      for (int v = 0; v < NV; v++) {
+        z[v][0] = z4[b][v].x; z[v][1] = z4[b][v].y; z[v][2] = z4[b][v].z; z[v][3] = z4[b][v].w;
+#pragma unroll
+        for (int e = 0; e < 4; e++) a[v][e] = act_ft<ACT>(z[v][e]);
+      }
+      if (NORM) {
         const float mean = A.mean[b][i], rstd = A.rstd[b][i];
-        float s1 = 0.f, s2 = 0.f, xh[NPL], dxh[NPL];
+        float s1 = 0.f, s2 = 0.f, xh[NV][4], dxh[NV][4];
 #pragma unroll
-        for (int k = 0; k < NPL; k++) {
-          const int f = lane + 32 * k;
-          xh[k] = (f < D) ? (a[k] - mean) * rstd : 0.f; dxh[k] = (f < D) ? g[k] * A.scale[b][f] : 0.f;
-          s1 += dxh[k]; s2 += dxh[k] * xh[k];
-          ps[b][k] += g[k] * xh[k]; po[b][k] += g[k];
-        }
-        s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
+        for (int v = 0; v < NV; v++)
 #pragma unroll
-        for (int k = 0; k < NPL; k++) {
-          const int f = lane + 32 * k;
-          if (f < D) { const float dz = rstd * (dxh[k] - s1 - xh[k] * s2) * act_df(z[k], a[k], act); A.dZ[b][(size_t)i * lddz + f] = dz; pb[b][k] += dz; }
-        }
+          for (int e = 0; e < 4; e++) {
+            xh[v][e] = on[v] ? (a[v][e] - mean) * rstd : 0.f; dxh[v][e] = g[v][e] * sc[b][v][e];
+            s1 += dxh[v][e]; s2 += dxh[v][e] * xh[v][e];
+            ps[b][v][e] += g[v][e] * xh[v][e]; po[b][v][e] += g[v][e];
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        s1 /= (float)D; s2 /= (float)D;
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) dz[v][e] = rstd * (dxh[v][e] - s1 - xh[v][e] * s2) * act_dft<ACT>(z[v][e], a[v][e]);
       } else {
 #pragma unroll
-        for (int k = 0; k < NPL; k++) { const int f = lane + 32 * k; if (f < D) { const float dz = g[k] * act_df(z[k], a[k], act); A.dZ[b][(size_t)i * lddz + f] = dz; pb[b][k] += dz; } }
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) dz[v][e] = g[v][e] * act_dft<ACT>(z[v][e], a[v][e]);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        if (on[v]) {
+          reinterpret_cast<float4 *>(A.dZ[b] + (size_t)i * lddz)[lane + 32 * v] = make_float4(dz[v][0], dz[v][1], dz[v][2], dz[v][3]);
+#pragma unroll
+          for (int e = 0; e < 4; e++) pb[b][v][e] += dz[v][e];
+        }
       }
     }
   }
@@ -425,10 +512,13 @@ __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_pair_kernel(const fl
 #pragma unroll
   for (int b = 0; b < NB; b++)
 #pragma unroll
-    for (int k = 0; k < NPL; k++) {
-      const int f = lane + 32 * k;
-      if (f < D) { mine[(b * 3 + 0) * D + f] = ps[b][k]; mine[(b * 3 + 1) * D + f] = po[b][k]; mine[(b * 3 + 2) * D + f] = pb[b][k]; }
-    }
+    for (int v = 0; v < NV; v++)
+      if (on[v]) {
+        const int f4 = lane + 32 * v;
+        reinterpret_cast<float4 *>(mine + (b * 3 + 0) * D)[f4] = make_float4(ps[b][v][0], ps[b][v][1], ps[b][v][2], ps[b][v][3]);
+        reinterpret_cast<float4 *>(mine + (b * 3 + 1) * D)[f4] = make_float4(po[b][v][0], po[b][v][1], po[b][v][2], po[b][v][3]);
+        reinterpret_cast<float4 *>(mine + (b * 3 + 2) * D)[f4] = make_float4(pb[b][v][0], pb[b][v][1], pb[b][v][2], pb[b][v][3]);
+      }
   __syncthreads();
   for (int f = threadIdx.x; f < NB * 3 * D; f += blockDim.x) {
     float v = 0.f;
@@ -436,16 +526,26 @@ __global__ void __launch_bounds__(LAYER_BLOCK) act_norm_bwd_pair_kernel(const fl
     partials[(size_t)blockIdx.x * NB * 3 * D + f] = v;
   }
 }
-// column c of [NB][3][D]: sum of the CTAs' partials in CTA order, ADDED to its destination (each destination has exactly one writer)
-__global__ void colsum_finish_kernel(const float *__restrict__ partials, int nparts, int D, int nb, const AnbPair A, int do_norm) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, cols = nb * 3 * D;
-  if (c >= cols) return;
+// 32 columns of [NB][3][D] per CTA: 8 groups of threads each add every 8th CTA's partial, the groups are then summed in a fixed order, and the
+// total is ADDED to its destination (each destination has exactly one writer): deterministic
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float *__restrict__ partials, int nparts, int D, int nb, const AnbPair A, int do_norm) {
+  __shared__ float red[8][32];
+  const int cols = nb * 3 * D, c = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
   float v = 0.f;
-#pragma unroll 8
-  for (int p = 0; p < nparts; p++) v += partials[(size_t)p * cols + c];
-  const int b = c / (3 * D), kind = (c / D) % 3, f = c % D;
-  float *dst = kind == 0 ? (do_norm ? A.dscale[b] : nullptr) : (kind == 1 ? (do_norm ? A.doffset[b] : nullptr) : A.dbias[b]);
-  if (dst) dst[f] += v;
+  if (c < cols) {
+#pragma unroll 4
+    for (int p = grp; p < nparts; p += 8) v += partials[(size_t)p * cols + c];
+  }
+  red[grp][threadIdx.x & 31] = v;
+  __syncthreads();
+  if (grp == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += red[k][threadIdx.x];
+    const int b = c / (3 * D), kind = (c / D) % 3, f = c % D;
+    float *dst = kind == 0 ? (do_norm ? A.dscale[b] : nullptr) : (kind == 1 ? (do_norm ? A.doffset[b] : nullptr) : A.dbias[b]);
+    if (dst) dst[f] += t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -698,17 +798,31 @@ extern "C" int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, cons
   const int grid = grid_for(n, WPB, 2 * sms);
   if (!scratch || scratch_floats < (int64_t)grid * nb * 3 * D) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair: scratch needs %lld floats", (long long)grid * nb * 3 * D);
   const size_t smem = (size_t)WPB * nb * 3 * D * sizeof(float);
-#define LAUNCH_PAIR(NPL, NB)                                                                                                                   \
-  do {                                                                                                                                         \
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(act_norm_bwd_pair_kernel<NPL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    act_norm_bwd_pair_kernel<NPL, NB><<<grid, LAYER_BLOCK, smem, ST(stream)>>>(dOut, ldo, A, ldz, lddz, n, D, act, do_norm, scratch);          \
+  if ((D & 3) || (ldo & 3) || (ldz & 3) || (lddz & 3)) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair: D and the leading dimensions must be multiples of 4");
+#define LAUNCH_PAIR4(NV, NB, ACT, NORM)                                                                                                              \
+  do {                                                                                                                                               \
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(act_norm_bwd_pair_kernel<NV, NB, ACT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    act_norm_bwd_pair_kernel<NV, NB, ACT, NORM><<<grid, LAYER_BLOCK, smem, ST(stream)>>>(dOut, ldo, A, ldz, lddz, n, D, scratch);                    \
   } while (0)
-  if (nb == 2) { if (D <= 64) LAUNCH_PAIR(2, 2); else if (D <= 128) LAUNCH_PAIR(4, 2); else LAUNCH_PAIR(8, 2); }
-  else { if (D <= 64) LAUNCH_PAIR(2, 1); else if (D <= 128) LAUNCH_PAIR(4, 1); else LAUNCH_PAIR(8, 1); }
-#undef LAUNCH_PAIR
+#define LAUNCH_PAIR3(NV, NB, ACT) do { if (do_norm) LAUNCH_PAIR4(NV, NB, ACT, true); else LAUNCH_PAIR4(NV, NB, ACT, false); } while (0)
+#define LAUNCH_PAIR2(NV, NB)                                                                                                                          \
+  do {                                                                                                                                               \
+    switch (act) {                                                                                                                                   \
+      case ACT_RELU: LAUNCH_PAIR3(NV, NB, ACT_RELU); break;                                                                                          \
+      case ACT_ELU: LAUNCH_PAIR3(NV, NB, ACT_ELU); break;                                                                                            \
+      case ACT_TANH: LAUNCH_PAIR3(NV, NB, ACT_TANH); break;                                                                                          \
+      case ACT_LRELU: LAUNCH_PAIR3(NV, NB, ACT_LRELU); break;                                                                                        \
+      default: LAUNCH_PAIR3(NV, NB, ACT_I); break;                                                                                                   \
+    }                                                                                                                                                \
+  } while (0)
+  if (nb == 2) { if (D <= 128) LAUNCH_PAIR2(1, 2); else LAUNCH_PAIR2(2, 2); }
+  else { if (D <= 128) LAUNCH_PAIR2(1, 1); else LAUNCH_PAIR2(2, 1); }
+#undef LAUNCH_PAIR2
+#undef LAUNCH_PAIR3
+#undef LAUNCH_PAIR4
   CUDA_TRY(cudaGetLastError());
   const int cols = nb * 3 * D;
-  colsum_finish_kernel<<<(cols + 127) / 128, 128, 0, ST(stream)>>>(scratch, grid, D, nb, A, do_norm);
+  colsum_finish_kernel<<<(cols + 31) / 32, 256, 0, ST(stream)>>>(scratch, grid, D, nb, A, do_norm);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -317,6 +317,177 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
   }
 }
 
+// ================================================================================================================================
+// Weight gradient  dW[n, k] = sum_m dZ[m, n] X[m, k]  (shaDow/layers.py:421,451-452 backward): the reduction runs over the ROWS of both
+// operands, so neither is K-major in memory.  TMA lands 16 rows of dZ and of X as they are ([16][256], no swizzle); the worker warps
+// transpose them while they split them: thread t reads column t of the 16 rows and writes row t of the K-major, 64B-swizzled hi / lo tiles
+// (the swizzle makes those 64-byte row writes conflict-free).  The batch is cut into slices of 128 rows, one CTA per slice and branch; a CTA
+// holds the whole [N_out <= 256, K_in <= 256] partial gradient in TMEM (two 128-lane accumulators = all 512 columns) and writes it with TMA
+// to partial[slice]; wgrad_finish_kernel adds the slices up in slice order into the gradient: deterministic, no atomics.
+// ================================================================================================================================
+constexpr int WG_ROWS = 128;                         // rows of the batch per CTA
+constexpr int WG_BK = 16;                            // rows per k-block
+constexpr int WG_RAW = WG_BK * 256 * 4;              // one raw tile: 16 KB
+constexpr int WG_OP = 256 * WG_BK * 4;               // one operand plane ([256 rows][16] K-major): 16 KB
+constexpr int WG_STAGES = 2;
+constexpr int WG_STAGE_BYTES = 2 * WG_RAW + 4 * WG_OP;          // raw dZ, raw X, A hi, A lo, B hi, B lo = 96 KB
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 128;
+
+struct WgradParams {
+  int M, N_out, K_in;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {      // K-major, 64-byte rows, 8-row groups of 512 bytes
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz0, const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_dz1,
+                const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1,
+                const WgradParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = (uint64_t *)(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t *full = bars, *ready = bars + WG_STAGES, *empty = bars + 2 * WG_STAGES, *acc = bars + 3 * WG_STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 3 * WG_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x, m0 = slice * WG_ROWS;
+  const CUtensorMap *map_dz = blockIdx.y ? &map_dz1 : &map_dz0, *map_x = blockIdx.y ? &map_x1 : &map_x0, *map_p = blockIdx.y ? &map_p1 : &map_p0;
+  const int num_kb = WG_ROWS / WG_BK;
+  const int halves = P.N_out > 128 ? 2 : 1;
+  const int n_mma = (P.K_in + 15) & ~15;             // MMA N: the gradient's columns
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_dz) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_x) : "memory");
+    for (int s = 0; s < WG_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], NUM_WORKERS); mbar_init(&empty[s], 1); }
+    mbar_init(acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                   // all of TMEM: two 128-lane x 256-column fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % WG_STAGES;
+        mbar_wait(&empty[s], ((kb / WG_STAGES) & 1) ^ 1);
+        unsigned char *st = smem + s * WG_STAGE_BYTES;
+        mbar_expect_tx(&full[s], 2 * WG_RAW);
+        tma_load_2d(st, map_dz, &full[s], 0, m0 + kb * WG_BK);                   // [16 rows][256 columns of dZ], out-of-range = 0
+        tma_load_2d(st + WG_RAW, map_x, &full[s], 0, m0 + kb * WG_BK);           // [16 rows][256 columns of X]
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, n_mma);
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % WG_STAGES;
+        mbar_wait(&ready[s], (kb / WG_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + s * WG_STAGE_BYTES + 2 * WG_RAW), a_lo = a_hi + WG_OP, b_hi = a_lo + WG_OP, b_lo = b_hi + WG_OP;
+        for (int h = 0; h < halves; h++) {
+          const uint32_t ah = a_hi + h * (WG_OP / 2), al = a_lo + h * (WG_OP / 2), d = tmem_base + h * 256;
+#pragma unroll
+          for (int k = 0; k < WG_BK / UMMA_K; k++) {
+            const uint32_t ko = k * UMMA_K * 4;
+            umma_tf32(d, umma_desc_sw64(ah + ko), umma_desc_sw64(b_lo + ko), idesc, (kb | k) ? 1u : 0u);
+            umma_tf32(d, umma_desc_sw64(al + ko), umma_desc_sw64(b_hi + ko), idesc, 1u);
+            umma_tf32(d, umma_desc_sw64(ah + ko), umma_desc_sw64(b_hi + ko), idesc, 1u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc);
+    }
+  } else {
+    // ===== transposing transform: thread t owns column t of both raw tiles =====
+    const int t = threadIdx.x - 64;                    // 0..255
+    const uint32_t row_off = (uint32_t)(t >> 3) * 512u + (uint32_t)(t & 7) * 64u, sw = (uint32_t)(t >> 1) & 3u;
+    for (int kb = 0; kb < num_kb; kb++) {
+      const int s = kb % WG_STAGES;
+      mbar_wait(&full[s], (kb / WG_STAGES) & 1);
+      unsigned char *st = smem + s * WG_STAGE_BYTES;
+#pragma unroll
+      for (int op = 0; op < 2; op++) {
+        const float *raw = reinterpret_cast<const float *>(st + op * WG_RAW);
+        unsigned char *hi = st + 2 * WG_RAW + op * 2 * WG_OP, *lo = hi + WG_OP;
+        float v[WG_BK];
+#pragma unroll
+        for (int m = 0; m < WG_BK; m++) v[m] = raw[m * 256 + t];
+#pragma unroll
+        for (int q = 0; q < WG_BK / 4; q++) {
+          float4 h4, l4;
+          h4.x = __uint_as_float(__float_as_uint(v[4 * q]) & 0xFFFFE000u); h4.y = __uint_as_float(__float_as_uint(v[4 * q + 1]) & 0xFFFFE000u);
+          h4.z = __uint_as_float(__float_as_uint(v[4 * q + 2]) & 0xFFFFE000u); h4.w = __uint_as_float(__float_as_uint(v[4 * q + 3]) & 0xFFFFE000u);
+          l4.x = v[4 * q] - h4.x; l4.y = v[4 * q + 1] - h4.y; l4.z = v[4 * q + 2] - h4.z; l4.w = v[4 * q + 3] - h4.w;
+          const uint32_t off = row_off + ((((uint32_t)q) ^ sw) << 4);
+          *reinterpret_cast<float4 *>(hi + off) = h4;
+          *reinterpret_cast<float4 *>(lo + off) = l4;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&ready[s]);
+    }
+    // ===== epilogue: partial[slice][n][k] out of TMEM through swizzled staging tiles and TMA =====
+    mbar_wait(acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    unsigned char *stage_w = smem + (size_t)(warp - 2) * (2 * 4096);
+    const uint32_t sw7 = (uint32_t)(lane & 7);
+    uint32_t r[32];
+    int it = 0;
+    for (int h = 0; h < halves; h++) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + h * 256;
+      for (int c0 = half * 32; c0 < P.K_in; c0 += 64, it++) {
+        tmem_ld32(taddr + c0, r);
+        unsigned char *ob = stage_w + (size_t)(it & 1) * 4096;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          *reinterpret_cast<float4 *>(ob + (uint32_t)lane * 128u + ((((uint32_t)q) ^ sw7) << 4)) =
+              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(map_p, ob, c0, h * 128 + quad * 32, slice);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// grad[i] += sum over the slices, in slice order (grad is W.grad: the optimizer's flat gradient bucket)
+__global__ void wgrad_finish_kernel(const float4 *__restrict__ part0, const float4 *__restrict__ part1, float4 *__restrict__ g0, float4 *__restrict__ g1, int n4,
+                                    int slices) {
+  const float4 *part = blockIdx.y ? part1 : part0;
+  float4 *g = blockIdx.y ? g1 : g0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 a = g[i];
+#pragma unroll 8
+    for (int s = 0; s < slices; s++) { const float4 v = part[(size_t)s * n4 + i]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    g[i] = a;
+  }
+}
+
 // ---- the weights' two TF32 planes, refreshed once per optimizer step instead of once per tile and CTA ----
 __global__ void tf32_split_kernel(const float *__restrict__ src, long long n, float *__restrict__ hi, float *__restrict__ lo) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -430,6 +601,68 @@ extern "C" int shadow_tf32_split_transpose_f32(const float *src, const int64_t *
   if (num_entries <= 0) return 0;
   if (!src || !table_dev || !t_hi || !t_lo) FAIL(SHADOW_EINVAL, "tf32_split_transpose: NULL argument");
   tf32_split_transpose_kernel<<<dim3(64, num_entries), 256, 0, (cudaStream_t)cuda_stream>>>(src, (const long long *)table_dev, t_hi, t_lo);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+int make_map_raw(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld) {      // box = [256 columns, 16 rows], no swizzle
+  encode_tiled_fn enc = get_encode();
+  if (!enc) FAIL(SHADOW_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {256, (cuuint32_t)WG_BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FAIL(SHADOW_EINVAL, "cuTensorMapEncodeTiled (raw) failed (%d)", (int)r);
+  return 0;
+}
+int make_map_partial(CUtensorMap *map, const float *base, long long slices, long long n_out, long long k_in) {     // [slices][n_out][k_in], box 32 x 32 x 1, 128-byte swizzle
+  encode_tiled_fn enc = get_encode();
+  if (!enc) FAIL(SHADOW_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)k_in, (cuuint64_t)n_out, (cuuint64_t)slices};
+  cuuint64_t strides[2] = {(cuuint64_t)k_in * 4, (cuuint64_t)k_in * n_out * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FAIL(SHADOW_EINVAL, "cuTensorMapEncodeTiled (partial) failed (%d)", (int)r);
+  return 0;
+}
+}  // namespace
+
+extern "C" int64_t shadow_wgrad_tc_scratch_floats(int32_t M, int32_t N_out, int32_t K_in) {
+  return (int64_t)((M + WG_ROWS - 1) / WG_ROWS) * N_out * K_in;
+}
+extern "C" int shadow_wgrad_tc_f32(const float *dZ0, const float *X0, float *grad0, float *scratch0, const float *dZ1, const float *X1, float *grad1,
+                                   float *scratch1, int32_t M, int32_t N_out, int32_t K_in, void *cuda_stream) {
+  if (M <= 0) return 0;
+  const int nb = dZ1 ? 2 : 1;
+  if (N_out < 8 || N_out > 256 || K_in < 8 || K_in > 256 || (N_out & 3) || (K_in & 3)) FAIL(SHADOW_EINVAL, "wgrad_tc: N_out / K_in must be multiples of 4 in [8, 256]");
+  const float *dZ[2] = {dZ0, dZ1 ? dZ1 : dZ0}, *X[2] = {X0, X1 ? X1 : X0};
+  float *grad[2] = {grad0, grad1 ? grad1 : grad0}, *scr[2] = {scratch0, scratch1 ? scratch1 : scratch0};
+  const int slices = (M + WG_ROWS - 1) / WG_ROWS;
+  CUtensorMap mdz[2], mx[2], mp[2];
+  for (int b = 0; b < 2; b++) {
+    if (!dZ[b] || !X[b] || !grad[b] || !scr[b]) FAIL(SHADOW_EINVAL, "wgrad_tc: NULL argument");
+    if (((uintptr_t)dZ[b] | (uintptr_t)X[b] | (uintptr_t)grad[b] | (uintptr_t)scr[b]) & 15) FAIL(SHADOW_EINVAL, "wgrad_tc: pointers must be 16-byte aligned");
+    int rc = make_map_raw(&mdz[b], dZ[b], M, N_out, N_out);
+    if (rc) return rc;
+    rc = make_map_raw(&mx[b], X[b], M, K_in, K_in);
+    if (rc) return rc;
+    rc = make_map_partial(&mp[b], scr[b], slices, N_out, K_in);
+    if (rc) return rc;
+  }
+  WgradParams P;
+  P.M = M; P.N_out = N_out; P.K_in = K_in;
+  static bool attr_set = false;
+  if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM)); attr_set = true; }
+  wgrad_tc_kernel<<<dim3(slices, nb), NUM_THREADS, WG_SMEM, (cudaStream_t)cuda_stream>>>(mdz[0], mx[0], mdz[1], mx[1], mp[0], mp[1], P);
+  CUDA_TRY(cudaGetLastError());
+  const int n4 = N_out * K_in / 4;
+  wgrad_finish_kernel<<<dim3((n4 + 255) / 256, nb), 256, 0, (cudaStream_t)cuda_stream>>>((const float4 *)scr[0], (const float4 *)scr[1], (float4 *)grad[0], (float4 *)grad[1],
+                                                                                         n4, slices);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

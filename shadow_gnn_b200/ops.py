@@ -258,9 +258,38 @@ def _linear_dgrad(dZ, w):
     return gemm(dZ, w, b_kn=True)
 
 
+_WG_SCRATCH = {}
+
+
+def _wgrad_tc(ws, dZs, xs):
+    """W.grad += dZ^T x for one or two (W, dZ, x) triples of the same shape on the tcgen05 kernel (csrc/linear_tc.cu: wgrad_tc_kernel +
+    wgrad_finish_kernel: slices of 128 rows, summed in slice order -- deterministic).  False when the shapes miss its alignment rules."""
+    if _LINEAR != "tc" or os.environ.get("SHADOW_WGRAD_TC", "1") == "0":
+        return False
+    n, N_out = dZs[0].shape
+    K_in = xs[0].shape[1]
+    gs = [_grad_of(w) for w in ws]
+    ok = n > 0 and 8 <= N_out <= 256 and 8 <= K_in <= 256 and N_out % 4 == 0 and K_in % 4 == 0 and \
+        all(t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() % 16 == 0 for t in (*dZs, *xs, *gs)) and \
+        all(dz.shape == dZs[0].shape for dz in dZs) and all(x.shape == xs[0].shape for x in xs)
+    if not ok:
+        return False
+    need = int(lib.shadow_wgrad_tc_scratch_floats(n, N_out, K_in))
+    key = (dZs[0].device.index, N_out, K_in)
+    sc = _WG_SCRATCH.get(key)
+    if sc is None or sc[0].numel() < need:
+        sc = _WG_SCRATCH[key] = [torch.empty(need, dtype=torch.float32, device=dZs[0].device) for _ in range(2)]
+    two = len(ws) == 2
+    check(lib.shadow_wgrad_tc_f32(_p(dZs[0]), _p(xs[0]), _p(gs[0]), _p(sc[0]), _p(dZs[1]) if two else None, _p(xs[1]) if two else None,
+                                  _p(gs[1]) if two else None, _p(sc[1]) if two else None, n, N_out, K_in, _stream(dZs[0])))
+    return True
+
+
 def _accum_wgrad(w, dZ, x):
     """W.grad += dZ^T x.  The product is [D_out, n] x [n, D_in] with n ~ 4,800 and a 256 x 256 result: a handful of output tiles, so it is
     split along n (tcgen05 path: 16 batched slices + a sum; warp-MMA path: ~160 rows per CTA, fp32 atomics into the gradient)."""
+    if _wgrad_tc([w], [dZ], [x]):
+        return
     g = _grad_of(w)
     n = x.shape[0]
     if not _TC_LINEAR:
@@ -387,6 +416,8 @@ def _linear_dgrad_pair(dZ0, w0, dZ1, w1):
 
 
 def _accum_wgrad_pair(w0, dZ0, x0, w1, dZ1, x1):
+    if w0.shape == w1.shape and _wgrad_tc([w0, w1], [dZ0, dZ1], [x0, x1]):
+        return
     if _pair_ok(dZ0, dZ1, x0, x1) and dZ0.shape == dZ1.shape and x0.shape == x1.shape:
         g0, g1 = _grad_of(w0), _grad_of(w1)
         n, N_out, K_in = x0.shape[0], dZ0.shape[1], x0.shape[1]
@@ -476,7 +507,7 @@ class _LinearActNorm(torch.autograd.Function):
     def backward(ctx, dOut):
         x, Z, mean, rstd = ctx.saved_tensors
         lin_w, lin_b, scale, offset, idx, act, do_norm = ctx.p
-        if Z.shape[1] <= 256 and Z.shape[0] > 0:
+        if Z.shape[1] <= 256 and Z.shape[1] % 4 == 0 and Z.shape[0] > 0:
             dZ = _act_norm_bwd_pair(dOut.contiguous(), [Z], scale, offset, [lin_b], [idx], [mean], [rstd], act, do_norm)[0]
         else:
             dZ = _act_norm_bwd_raw(dOut.contiguous(), Z, scale, offset, lin_b, idx, mean, rstd, act, do_norm)
@@ -529,7 +560,7 @@ class _SageLayer(torch.autograd.Function):
         x, agg, Zs, Zn, mean_s, rstd_s, mean_n, rstd_n = ctx.saved_tensors
         adj, ws, bs, wn, bn, scale, offset, act, do_norm = ctx.p
         dOut = dOut.contiguous()
-        if Zs.shape[1] <= 256 and Zs.shape[0] > 0:       # both branches in one launch: dOut is read once, column sums without atomics
+        if Zs.shape[1] <= 256 and Zs.shape[1] % 4 == 0 and Zs.shape[0] > 0:       # both branches in one launch: dOut is read once, column sums without atomics
             dZs, dZn = _act_norm_bwd_pair(dOut, [Zs, Zn], scale, offset, [bs, bn], [0, 1], [mean_s, mean_n], [rstd_s, rstd_n], act, do_norm)
         else:
             dZs = _act_norm_bwd_raw(dOut, Zs, scale, offset, bs, 0, mean_s, rstd_s, act, do_norm)
