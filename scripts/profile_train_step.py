@@ -6,16 +6,16 @@ import bench
 from shadow_gnn_b200 import minibatch as MB
 from shadow_gnn_b200.models import DeepGNN
 from shadow_gnn_b200.train import GraphedTrainer
-sys.argv = ["bench.py", "--task", "train"]
+sys.argv = ["bench.py", "--task", "train"] + os.environ.get("BENCH_ARGS", "").split()
 args = bench.parse()
 ctx = bench.Ctx(args)
-dev, F, C, B = ctx.dev, ctx.F, ctx.C, 32
+dev, F, C, B = ctx.dev, ctx.F, ctx.C, args.batch
 labels = torch.from_numpy(np.random.default_rng(7).integers(0, C, ctx.N)).to(dev)
 share = ctx.share.numpy()[:8192]
 cfg = {"batch_size": B, "configs": [{"method": "ppr", "k": [150], "threshold": [0.0], "epsilon": [1e-5]}]}
 adjs = {m: (ctx.g["indptr"], ctx.g["indices"]) for m in range(3)}
 mb = MB.MinibatchShallowExtractor("g", None, adjs, {0: share, 1: share[:B], 2: share[:B]}, cfg, set(), None, ctx.feat, labels, F, True, 1, seed_cpp=1, num_subg_per_batch=4096)
-model = DeepGNN(F, F, C, 0, bench.ARCH, [], 1, dict(dropout=0.4, dropedge=0.05, lr=0.002, ensemble_dropout="none"), "node").to(dev)
+model = DeepGNN(F, F, C, 0, bench.ARCH, [], 1, dict(dropout=bench.TRAIN_CFG["dropout"], dropedge=bench.TRAIN_CFG["dropedge"], lr=bench.TRAIN_CFG["lr"], ensemble_dropout="none"), "node").to(dev)
 mb.epoch_start_reset(0, MB.TRAIN); mb.shuffle_entity(MB.TRAIN)
 for _ in range(5):
     model.step(MB.TRAIN, "running", mb.one_batch(MB.TRAIN))
@@ -33,7 +33,7 @@ print(f"total device time per step: {tot/10:.1f} us")
 for k, t, c in rows[:28]:
     print(f"{t/10:9.1f} us/step {c/10:6.1f}x {t/tot*100:5.1f}%  {k[:100]}")
 # graphed step timing + static-load overhead
-tr = GraphedTrainer(model, mb, row_cap=B * 151, edge_cap=B * 151 * 16)
+tr = GraphedTrainer(model, mb, row_cap=B * 151, edge_cap=B * 151 * 64)
 for _ in range(10): tr.step()
 torch.cuda.synchronize()
 t0 = time.perf_counter()

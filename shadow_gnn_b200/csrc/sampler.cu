@@ -55,8 +55,14 @@ struct DevBuf {
     if (need <= bytes) return 0;
     if (p) cudaFree(p);
     p = nullptr; bytes = 0;
-    size_t want = std::max(need, (size_t)256);
-    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+    // 25 % head room: batch sizes fluctuate by a few percent from call to call, and every cudaFree / cudaMalloc pair is a device-wide
+    // synchronisation (it used to drain the training pipeline for 4-13 ms whenever a super-batch set a new maximum)
+    size_t want = std::max(need + need / 4, (size_t)256);
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      want = std::max(need, (size_t)256);
+      if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+    }
     bytes = want;
     return 0;
   }

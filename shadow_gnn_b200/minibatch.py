@@ -14,6 +14,8 @@ from copy import deepcopy
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -60,6 +62,8 @@ class _SuperBatch:
     def __init__(self, dev_batch, feat, aug, num_roots):
         self.b = dev_batch
         self.node_ptr_host = dev_batch.node_ptr.cpu().numpy().astype(np.int64)
+        if dev_batch.has_csr:
+            dev_batch.row_span, dev_batch.indices_raw, dev_batch.target, dev_batch.orig_node      # views fetched while the sampler still points at this call
         self.feat, self.aug, self.num_roots = feat, aug, num_roots
         self.val = torch.empty(max(dev_batch.total_edges, 1), dtype=torch.float32, device=feat.device)
         self.cursor = 0
@@ -79,11 +83,15 @@ class _SuperBatch:
         aug = {k: v[lo:hi] for k, v in self.aug.items()}
         return adj, self.feat[lo:hi], target, sizes, aug, self.b.orig_node[lo:hi]
 
+    def prepare_canonical(self):
+        if not hasattr(self, "edge_ptr_host"):
+            self.edge_ptr_host = self.b.edge_ptr.cpu().numpy().astype(np.int64)        # runs the canonicalisation kernel once per super-batch
+            self.b.rowptr, self.b.indices                                              # views fetched while the sampler still points at this call
+
     def take_canonical(self, bs):
         """the same batch as contiguous slices of the CANONICAL CSR of the super-batch (for the CUDA-graph trainer, which copies
         them into static buffers): returns (rowptr slice [n+1], indices slice [e], first row, first edge, feat slice, target slice)"""
-        if not hasattr(self, "edge_ptr_host"):
-            self.edge_ptr_host = self.b.edge_ptr.cpu().numpy().astype(np.int64)        # runs the canonicalisation kernel once per super-batch
+        self.prepare_canonical()
         a, b = self.cursor, self.cursor + bs
         lo, hi = int(self.node_ptr_host[a]), int(self.node_ptr_host[b])
         e0, e1 = int(self.edge_ptr_host[a]), int(self.edge_ptr_host[b])
@@ -121,6 +129,7 @@ def drnl2onehot(drnl_i32, dim):
 
 class MinibatchShallowExtractor:
     FULL, SUBG = 0, 1
+    NUM_RING = 2            # result buffers of the sampler: a super-batch stays valid while the next one is sampled
 
     def __init__(self, name_data, dir_data, adjs, entity_set, sampler_config_ensemble, aug_feats, percent_per_epoch, feat_full, label_full,
                  dim_feat_raw: int, is_transductive: bool, parallelism: int, full_tensor_on_gpu: bool = True, bin_adj_files=None,
@@ -169,6 +178,7 @@ class MinibatchShallowExtractor:
         self.dim_1hot_hop, self.dim_1hot_ppr, self.dim_1hot_drnl = 5 + 2, 1, 25 + 1        # minibatch.py:246-248
         self.profiler = None
         self.num_sampler_calls = 0
+        self.prefetch_canonical = False      # GraphedTrainer: build the canonical CSR (and its host offsets) inside the sampler call
 
     # ------------------------------------------------------------------ epoch protocol (minibatch.py:252-343)
     def _get_cur_batch_size(self, mode):
@@ -235,10 +245,10 @@ class MinibatchShallowExtractor:
         elif self.bin_adj_files is not None and self.bin_adj_files.get(mode):
             f = self.bin_adj_files[mode]
             s = PS.ParallelSampler([], [], [], per_call, 1, True, True, [], len(cfgs), f["indptr"], f["indices"], f.get("data", ""), self.seed_cpp,
-                                   device=self.dev_torch.index, strict_reference_compat=self._compat, rng=self._rng)
+                                   device=self.dev_torch.index, strict_reference_compat=self._compat, rng=self._rng, num_ring=self.NUM_RING)
         else:
             s = PS.ParallelSampler(indptr, indices, [], per_call, 1, True, True, [], len(cfgs), "", "", "", self.seed_cpp,
-                                   device=self.dev_torch.index, strict_reference_compat=self._compat, rng=self._rng)
+                                   device=self.dev_torch.index, strict_reference_compat=self._compat, rng=self._rng, num_ring=self.NUM_RING)
         cpp_cfgs = []
         for c in cfgs:
             tf = lambda key: "true" if c.get(key, False) else "false"
@@ -266,7 +276,9 @@ class MinibatchShallowExtractor:
         self.is_stochastic_sampler[mode] = any(c["method"] in ("khop", "ppr_st") for c in cfgs)
 
     def par_graph_sample(self, mode):
-        """one sampler call -> one super-batch per ensemble branch, features gathered, aug one-hots built (minibatch.py:403-426,469-477)"""
+        """one sampler call -> one super-batch per ensemble branch, features gathered, aug one-hots built (minibatch.py:403-426,469-477).
+        Runs on the caller's stream.  (Moving it to a side stream so that queued training steps hide it was tried and dropped: the call is
+        ~0.35 ms for 160 roots once the result buffers stop being re-allocated, and the overlap did not pay for its hazards.)"""
         s = self.graph_sampler[mode]
         self.num_sampler_calls += 1
         augs = [set(self.aug_feats) & {"hops", "pprs", "drnls"} for _ in self.sampler_cfgs[mode]]
@@ -280,8 +292,11 @@ class MinibatchShallowExtractor:
                 aug["pprs"] = ppr2onehot(b.ppr, self.dim_1hot_ppr)
             if "drnls" in self.aug_feats:
                 aug["drnls"] = drnl2onehot(b.drnl, self.dim_1hot_drnl)
-            # the views must outlive the sampler's ring slot: keep one super-batch per branch in flight (num_ring = 2)
-            self.pool[mode][i].append(_SuperBatch(b, feat, aug, 1))
+            sb = _SuperBatch(b, feat, aug, 1)
+            if self.prefetch_canonical:
+                sb.prepare_canonical()
+            # the views must outlive the sampler's ring slot: one super-batch per branch is in flight, the ring holds NUM_RING
+            self.pool[mode][i].append(sb)
 
     def _front(self, mode, i, bs):
         """super-batch of branch i that holds the next `bs` subgraphs (sampling a new one when the pool is dry)"""

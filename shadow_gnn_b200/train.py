@@ -25,6 +25,7 @@ class GraphedTrainer:
         assert "sort" not in pools, "sort pooling has data-dependent shapes (repeat_interleave): use the eager DeepGNN.step"
         self._needs_sizes = pools != {"center"}
         self.model, self.mb, self.mode = model, minibatch, mode
+        minibatch.prefetch_canonical = True
         self.B = minibatch._cfg_ensemble["batch_size"]
         dev, Fd = minibatch.dev_torch, minibatch.feat_full.shape[1]
         self.row_cap, self.edge_cap = int(row_cap), int(edge_cap)
