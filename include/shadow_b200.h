@@ -248,6 +248,32 @@ int shadow_gat_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_
                        const float *a_neigh, const float *H, const float *out, const float *rowmax, const float *denom,
                        const float *dOut, float *dH, float *da_self, float *da_neigh, int32_t n, int32_t heads, int32_t d,
                        void *cuda_stream);
+/* The GAT layer between its two Linear products, all heads per launch (csrc/gat.cu; shaDow/layers.py:539-645).  Shapes: heads in {1,2,4,8},
+ * head width d in {16,32,64,128,256}, heads * d <= 256 (shadow_gat_supported); att / scale / offset are [2][heads * d].
+ *   logits    s_b[i,k] = sum_f att[b,k,f] h_b[i,k,f], a_b = LeakyReLU_0.2(s_b)       (b = 0 self, 1 neighbour)
+ *   agg       softmax-weighted neighbour sum of h_neigh per head (rowmax / denom saved), backward scatters into dHn / da_self / da_neigh (pre-zeroed)
+ *   headnorm  out = (norm_feat_{1,k}(h_self) + norm_feat_{0,k}(agg)) / 2 per head; mean / rstd are [2][n][heads]
+ *   pre_bwd   attention-logit backward + activation backward: dZ_b = (dh_b + ds_b att_b) act'(.), d att and d bias ACCUMULATED
+ * Column sums are reduced in two deterministic stages through `scratch` (shadow_gat_scratch_floats floats). */
+int shadow_gat_supported(int32_t heads, int32_t d);
+int64_t shadow_gat_scratch_floats(int32_t heads, int32_t d);
+int shadow_gat_logits_fwd_f32(const float *h_self, const float *h_neigh, const float *att, float *s_self, float *s_neigh, float *a_self, float *a_neigh,
+                              int32_t n, int32_t heads, int32_t d, void *cuda_stream);
+int shadow_gat_agg_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self, const float *a_neigh,
+                           const float *Hn, float *out, float *rowmax, float *denom, int32_t n, int32_t heads, int32_t d, void *cuda_stream);
+int shadow_gat_agg_bwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self, const float *a_neigh,
+                           const float *Hn, const float *out, const float *rowmax, const float *denom, const float *dOut, float *dHn, float *da_self,
+                           float *da_neigh, int32_t n, int32_t heads, int32_t d, void *cuda_stream);
+int shadow_gat_headnorm_fwd_f32(const float *h_self, const float *agg, const float *scale, const float *offset, float *out, float *mean, float *rstd,
+                                int32_t n, int32_t heads, int32_t d, int32_t do_norm, void *cuda_stream);
+int shadow_gat_headnorm_bwd_f32(const float *dOut, const float *h_self, const float *agg, const float *scale, const float *mean, const float *rstd,
+                                float *dh_self, float *dagg, float *dscale, float *doffset, int32_t n, int32_t heads, int32_t d, int32_t do_norm,
+                                float *scratch, int64_t scratch_floats, void *cuda_stream);
+int shadow_gat_pre_bwd_f32(const float *dh_self, const float *dh_neigh, const float *h_self, const float *h_neigh, const float *s_self, const float *s_neigh,
+                           const float *da_self, const float *da_neigh, const float *att, float *dZ_self, float *dZ_neigh, float *datt, float *dbias_self,
+                           float *dbias_neigh, int32_t n, int32_t heads, int32_t d, int32_t act, float *scratch, int64_t scratch_floats, void *cuda_stream);
+int shadow_colsum_finish_f32(const float *partials, int32_t nparts, int32_t D, float *d00, float *d01, float *d02, float *d10, float *d11, float *d12,
+                             void *cuda_stream);
 /* per-subgraph pooling (F.embedding_bag in ResPool, layers.py:168-184): mode 0 sum, 1 mean, 2 max; seg = node_ptr slice */
 int shadow_segment_pool_fwd_f32(const float *X, const int32_t *seg, int32_t seg_off, int32_t S, int32_t F, int32_t mode, float *out,
                                 int32_t *argmax, void *cuda_stream);

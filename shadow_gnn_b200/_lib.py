@@ -56,6 +56,8 @@ SYMBOLS = [
     "shadow_gat_fwd_f32", "shadow_gat_bwd_f32", "shadow_segment_pool_fwd_f32", "shadow_segment_pool_bwd_f32",
     "shadow_adam_clip_step_f32", "shadow_gemm_tf32x3_f32", "shadow_gemm_tf32x3_pair_f32",
     "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32", "shadow_linear_tc_f32", "shadow_tf32_split_f32", "shadow_tf32_split_transpose_f32", "shadow_wgrad_tc_f32", "shadow_wgrad_tc_scratch_floats",
+    "shadow_gat_supported", "shadow_gat_scratch_floats", "shadow_gat_logits_fwd_f32", "shadow_gat_agg_fwd_f32", "shadow_gat_agg_bwd_f32",
+    "shadow_gat_headnorm_fwd_f32", "shadow_gat_headnorm_bwd_f32", "shadow_gat_pre_bwd_f32", "shadow_colsum_finish_f32",
 ]
 
 if not os.path.exists(LIB_PATH):
@@ -108,6 +110,16 @@ lib.shadow_linear_umma_fwd_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _i64,
 lib.shadow_linear_umma_dgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]
 lib.shadow_linear_umma_wgrad_f32.argtypes = [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]
 lib.shadow_act_norm_bwd_pair_f32.argtypes = [_vp, _i32, _vp, _vp, _i32] + [_vp] * 8 + [_i32] + [_vp] * 6 + [_i32, _i32, _i32, _i32, _vp, _i64, _vp]
+lib.shadow_gat_supported.argtypes = [_i32, _i32]
+lib.shadow_gat_scratch_floats.argtypes = [_i32, _i32]
+lib.shadow_gat_scratch_floats.restype = _i64
+lib.shadow_gat_logits_fwd_f32.argtypes = [_vp] * 7 + [_i32, _i32, _i32, _vp]
+lib.shadow_gat_agg_fwd_f32.argtypes = [_vp, _vp, _i32] + [_vp] * 7 + [_i32, _i32, _i32, _vp]
+lib.shadow_gat_agg_bwd_f32.argtypes = [_vp, _vp, _i32] + [_vp] * 11 + [_i32, _i32, _i32, _vp]
+lib.shadow_gat_headnorm_fwd_f32.argtypes = [_vp] * 7 + [_i32, _i32, _i32, _i32, _vp]
+lib.shadow_gat_headnorm_bwd_f32.argtypes = [_vp] * 10 + [_i32, _i32, _i32, _i32, _vp, _i64, _vp]
+lib.shadow_gat_pre_bwd_f32.argtypes = [_vp] * 14 + [_i32, _i32, _i32, _i32, _vp, _i64, _vp]
+lib.shadow_colsum_finish_f32.argtypes = [_vp, _i32, _i32] + [_vp] * 7
 lib.shadow_wgrad_tc_scratch_floats.argtypes = [_i32, _i32, _i32]
 lib.shadow_wgrad_tc_scratch_floats.restype = _i64
 lib.shadow_wgrad_tc_f32.argtypes = [_vp] * 8 + [_i32, _i32, _i32, _vp]

@@ -29,10 +29,10 @@ SRCS="sampler.cu gather.cu ppr_push.cu layers.cu gemm.cu"
 SOBJ=_obj/sampler_$(basename "$OUT" .so).o          # variant builds (EXTRA) differ only in this object
 $NVCC $ARCH ${PTXAS_V:+-Xptxas -v} $EXTRA -c sampler.cu -o $SOBJ &
 pids="$pids $!"
-for f in gather ppr_push layers gemm linear_tc; do
+for f in gather ppr_push layers gemm linear_tc gat; do
   $NVCC $ARCH ${PTXAS_V:+-Xptxas -v} -c $f.cu -o _obj/$f.o &
   pids="$pids $!"
 done
 for p in $pids; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a --shared -o $OUT $SOBJ _obj/gather.o _obj/ppr_push.o _obj/layers.o _obj/gemm.o _obj/linear_tc.o _obj/gemm_umma_0.o _obj/gemm_umma_1.o _obj/gemm_umma_2.o
+$NVCC -gencode arch=compute_100a,code=sm_100a --shared -o $OUT $SOBJ _obj/gather.o _obj/ppr_push.o _obj/layers.o _obj/gemm.o _obj/linear_tc.o _obj/gat.o _obj/gemm_umma_0.o _obj/gemm_umma_1.o _obj/gemm_umma_2.o
 echo "built $(realpath $OUT)"

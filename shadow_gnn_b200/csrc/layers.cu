@@ -5,6 +5,8 @@
 // written to be captured in one CUDA graph per step.  Dense Linear layers stay on cuBLAS (torch.nn.functional.linear).
 #include <algorithm>
 
+#include <cstring>
+
 #include "common.cuh"
 
 #define LAYER_BLOCK 256
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(LAYER_BLOCK) gat_fwd_kernel(const int2 *__rest
     for (int p = sp.x + lane; p < sp.y; p += 32) mx = fmaxf(mx, as + a_neigh[(size_t)(col[p] - col_off) * heads + k]);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};       // d <= 128
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // d <= 256
     float den = 0.f;
     for (int p = sp.x; p < sp.y; p++) {
       const int j = col[p] - col_off;
@@ -596,7 +598,7 @@ __global__ void __launch_bounds__(LAYER_BLOCK) gat_bwd_kernel(const int2 *__rest
     const float as = a_self[(size_t)i * heads + k], mx = rowmax[w], den = denom[w];
     const bool clamped = den < 1e-10f;
     const float S = fmaxf(den, 1e-10f);
-    float g[4], go = 0.f;
+    float g[8], go = 0.f;
     int c = 0;
     for (int f = lane; f < d; f += 32, c++) { g[c] = dOut[(size_t)i * D + k * d + f]; go += g[c] * out[(size_t)i * D + k * d + f]; }
     go = warp_sum(go);
@@ -826,11 +828,23 @@ extern "C" int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, cons
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+// [parts][2][3][D] partial column sums -> dst[b][plane] += total (fixed order; NULL destinations are skipped).  Used by csrc/gat.cu.
+extern "C" int shadow_colsum_finish_f32(const float *partials, int32_t nparts, int32_t D, float *d00, float *d01, float *d02, float *d10, float *d11, float *d12,
+                                        void *stream) {
+  if (nparts <= 0 || D <= 0) return 0;
+  AnbPair A;
+  memset(&A, 0, sizeof(A));
+  A.dscale[0] = d00; A.doffset[0] = d01; A.dbias[0] = d02; A.dscale[1] = d10; A.doffset[1] = d11; A.dbias[1] = d12;
+  const int cols = 2 * 3 * D;
+  colsum_finish_kernel<<<(cols + 31) / 32, 256, 0, ST(stream)>>>(partials, nparts, D, 2, A, 1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 extern "C" int shadow_gat_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
                                   const float *a_neigh, const float *H, float *out, float *rowmax, float *denom, int32_t n, int32_t heads,
                                   int32_t d, void *stream) {
   if (n <= 0) return 0;
-  if (d > 128) FAIL(SHADOW_EINVAL, "gat: head dim %d exceeds 128", d);
+  if (d > 256) FAIL(SHADOW_EINVAL, "gat: head dim %d exceeds 256", d);
   gat_fwd_kernel<<<grid_for((long long)n * heads, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, a_self, a_neigh, H, out,
                                                                                              rowmax, denom, n, heads, d);
   CUDA_TRY(cudaGetLastError());
@@ -840,7 +854,7 @@ extern "C" int shadow_gat_bwd_f32(const int32_t *row_span, const int32_t *col, i
                                   const float *a_neigh, const float *H, const float *out, const float *rowmax, const float *denom,
                                   const float *dOut, float *dH, float *da_self, float *da_neigh, int32_t n, int32_t heads, int32_t d, void *stream) {
   if (n <= 0) return 0;
-  if (d > 128) FAIL(SHADOW_EINVAL, "gat: head dim %d exceeds 128", d);
+  if (d > 256) FAIL(SHADOW_EINVAL, "gat: head dim %d exceeds 256", d);
   gat_bwd_kernel<<<grid_for((long long)n * heads, WPB, 8192), LAYER_BLOCK, 0, ST(stream)>>>((const int2 *)row_span, col, col_off, val, a_self, a_neigh, H, out,
                                                                                              rowmax, denom, dOut, dH, da_self, da_neigh, n, heads, d);
   CUDA_TRY(cudaGetLastError());

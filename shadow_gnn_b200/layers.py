@@ -211,6 +211,11 @@ class GAT(shaDowLayer):
             adj.mask_only(dropedge, *_Dropedge.next(feat_in.device))
         feat_in = self.f_dropout(feat_in)
         N, H, d = feat_in.shape[0], self.mulhead, self.dim_slice
+        if feat_in.is_cuda and self.act_name in ops.ACT_ID and ops.gat_layer_supported(feat_in, self.f_lin[0].weight, H):
+            has_norm = self.norm == "norm_feat"       # (without norm_feat the scale / offset arguments are placeholders the kernels never read)
+            out = ops.gat_layer(feat_in, adj, self.f_lin[0], self.f_lin[1], self.attention, self.scale if has_norm else self.attention,
+                                self.offset if has_norm else self.attention, self.act_name, H, has_norm)
+            return out, adj, True, 0.0
         h_self = self.act(self.f_lin[0](feat_in))
         h_neigh = self.act(self.f_lin[1](feat_in))
         a_self = self.att_act((h_self.view(N, H, d) * self.attention[0]).sum(-1))

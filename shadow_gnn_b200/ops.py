@@ -607,6 +607,94 @@ class _GATAgg(torch.autograd.Function):
         return da_self, da_neigh, dH, None, None
 
 
+_GAT_SCRATCH = {}
+
+
+def gat_layer_supported(x, w, heads):
+    """shapes the fused GAT node covers (csrc/gat.cu + csrc/linear_tc.cu); everything else takes the composed path of layers.GAT"""
+    D, K = w.shape
+    return _LINEAR == "tc" and D % heads == 0 and bool(lib.shadow_gat_supported(heads, D // heads)) and x.dim() == 2 and x.shape[0] > 0 and \
+        _tc_ok(D, K, x, w.detach()) and _tc_ok(K, D) and os.environ.get("SHADOW_GAT_FUSED", "1") != "0"
+
+
+class _GATLayer(torch.autograd.Function):
+    """GAT layer body (layers.py:607-629 of the reference) as ONE autograd node:
+    fwd  both Linear + activation in one tcgen05 launch, attention logits, softmax aggregation of all heads, per-head norm_feat of both branches
+    bwd  the three mirrored kernels, the activation / logit backward with its column sums, both weight gradients in one launch, and the
+         input gradient dZ_self W_self + dZ_neigh W_neigh in one launch (both products reduce-add into the same tensor)"""
+
+    @staticmethod
+    def forward(ctx, x, adj, w0, b0, w1, b1, att, scale, offset, act, do_norm, heads):
+        x = _req(x.contiguous(), torch.float32, "gat input")
+        M, K = x.shape
+        D = w0.shape[0]
+        d = D // heads
+        dev = x.device
+        h_self = torch.empty((M, D), dtype=torch.float32, device=dev)
+        h_neigh = torch.empty_like(h_self)
+        p0, p1 = WeightPlanes.of(w0.detach()), WeightPlanes.of(w1.detach())
+        pre = p0 is not None and p1 is not None
+        _linear_tc([(x, p0[0] if pre else w0.detach(), b0.detach(), None, None, None, h_self, None, None),
+                    (x, p1[0] if pre else w1.detach(), b1.detach(), None, None, None, h_neigh, None, None)], M, D, K, act, False, 0, [p0[1], p1[1]] if pre else None)
+        s_self, s_neigh, a_self, a_neigh, rowmax, denom = (torch.empty((M, heads), dtype=torch.float32, device=dev) for _ in range(6))
+        attc = att.detach().contiguous()
+        check(lib.shadow_gat_logits_fwd_f32(_p(h_self), _p(h_neigh), _p(attc), _p(s_self), _p(s_neigh), _p(a_self), _p(a_neigh), M, heads, d, _stream(x)))
+        agg = torch.empty_like(h_self)
+        check(lib.shadow_gat_agg_fwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(a_self), _p(a_neigh), _p(h_neigh), _p(agg), _p(rowmax), _p(denom),
+                                         M, heads, d, _stream(x)))
+        out = torch.empty_like(h_self)
+        mean = torch.empty((2, M, heads), dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        sc, of = scale.detach().contiguous(), offset.detach().contiguous()
+        check(lib.shadow_gat_headnorm_fwd_f32(_p(h_self), _p(agg), _p(sc), _p(of), _p(out), _p(mean), _p(rstd), M, heads, d, int(do_norm), _stream(x)))
+        ctx.save_for_backward(x, h_self, h_neigh, s_self, s_neigh, a_self, a_neigh, agg, rowmax, denom, mean, rstd)
+        ctx.p = (adj, w0, b0, w1, b1, att, scale, offset, act, do_norm, heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        x, h_self, h_neigh, s_self, s_neigh, a_self, a_neigh, agg, rowmax, denom, mean, rstd = ctx.saved_tensors
+        adj, w0, b0, w1, b1, att, scale, offset, act, do_norm, heads = ctx.p
+        M, K = x.shape
+        D = w0.shape[0]
+        d = D // heads
+        dev = x.device
+        dOut = dOut.contiguous()
+        key = (dev.index, heads, d)
+        if key not in _GAT_SCRATCH:
+            _GAT_SCRATCH[key] = torch.empty(int(lib.shadow_gat_scratch_floats(heads, d)), dtype=torch.float32, device=dev)
+        scratch = _GAT_SCRATCH[key]
+        st = _stream(x)
+        dh_self, dagg = torch.empty_like(h_self), torch.empty_like(h_self)
+        assert scale.is_contiguous() and offset.is_contiguous() and att.is_contiguous()
+        check(lib.shadow_gat_headnorm_bwd_f32(_p(dOut), _p(h_self), _p(agg), _p(scale.detach()), _p(mean), _p(rstd), _p(dh_self), _p(dagg),
+                                              _p(_grad_of(scale)) if do_norm else None, _p(_grad_of(offset)) if do_norm else None, M, heads, d, int(do_norm),
+                                              _p(scratch), scratch.numel(), st))
+        dh_neigh = torch.zeros_like(h_self)
+        da_self = torch.zeros((M, heads), dtype=torch.float32, device=dev)
+        da_neigh = torch.zeros((M, heads), dtype=torch.float32, device=dev)
+        check(lib.shadow_gat_agg_bwd_f32(_p(adj.row_span), _p(adj.col), adj.col_off, _p(adj.val), _p(a_self), _p(a_neigh), _p(h_neigh), _p(agg), _p(rowmax), _p(denom),
+                                         _p(dagg), _p(dh_neigh), _p(da_self), _p(da_neigh), M, heads, d, st))
+        dZs, dZn = torch.empty_like(h_self), torch.empty_like(h_self)
+        check(lib.shadow_gat_pre_bwd_f32(_p(dh_self), _p(dh_neigh), _p(h_self), _p(h_neigh), _p(s_self), _p(s_neigh), _p(da_self), _p(da_neigh), _p(att.detach()),
+                                         _p(dZs), _p(dZn), _p(_grad_of(att)), _p(_grad_of(b0)), _p(_grad_of(b1)), M, heads, d, act, _p(scratch), scratch.numel(), st))
+        _accum_wgrad_pair(w0, dZs, x, w1, dZn, x)
+        dX = None
+        if ctx.needs_input_grad[0]:
+            dX = torch.zeros((M, K), dtype=torch.float32, device=dev)
+            planes = [WeightPlanes.of(w.detach(), transposed=True) for w in (w0, w1)]
+            if all(pl is not None for pl in planes):
+                wts, w_lo = [pl[0] for pl in planes], [pl[1] for pl in planes]
+            else:
+                wts, w_lo = [w.detach().t().contiguous() for w in (w0, w1)], None
+            _linear_tc([(dZs, wts[0], None, None, None, None, dX, None, None), (dZn, wts[1], None, None, None, None, dX, None, None)], M, K, D, ACT_ID["I"], False, 2, w_lo)
+        return (dX,) + (None,) * 11
+
+
+def gat_layer(x, adj, lin_self, lin_neigh, attention, scale, offset, act, heads, do_norm=True):
+    return _GATLayer.apply(x, adj, lin_self.weight, lin_self.bias, lin_neigh.weight, lin_neigh.bias, attention, scale, offset, ACT_ID[act], bool(do_norm), heads)
+
+
 def gat_aggregate(adj, a_self, a_neigh, H, heads):
     """GAT._aggregate_attention for all heads at once (layers.py:560-582)"""
     return _GATAgg.apply(a_self, a_neigh, H, adj, heads)

@@ -504,3 +504,34 @@ def test_tcgen05_weight_gradient_matches_fp64_and_is_deterministic(M, N_out, K_i
         incs.append([w.grad.clone() for w in W])
     for a, b in zip(*incs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("D,H,K,act", [(256, 4, 256, "relu"), (256, 4, 100, "elu"), (64, 4, 32, "relu"), (128, 1, 64, "tanh"), (256, 1, 128, "leakyrelu"), (256, 8, 256, "relu")])
+def test_fused_gat_layer_equals_composed_path(D, H, K, act, monkeypatch):
+    """the fused GAT node (csrc/gat.cu + the tcgen05 Linear: layers.py:607-629 in 4 forward / 6 backward launches) against the composed path
+    (separate Linear, logits, aggregation, per-head norm ops) that the reference goldens pin at small dims: output, input gradient and every
+    parameter gradient, on the golden batch (self edges, PS.cpp:401 bug edges) with some edges dropped"""
+    from shadow_gnn_b200 import layers as L
+    torch.manual_seed(3)
+    adj, _, _ = device_adj(True)
+    n = adj.n
+    x0 = torch.randn(n, K, device="cuda")
+    res = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("SHADOW_GAT_FUSED", fused)
+        torch.manual_seed(4)
+        layer = L.GAT(K, D, dropout=0.0, act=act, norm="norm_feat", mulhead=H).cuda()
+        with torch.no_grad():
+            layer.scale.uniform_(0.5, 1.5); layer.offset.normal_(); layer.attention.normal_()
+        a, _, _ = device_adj(True)
+        a.val = torch.ones(a.col.numel(), device="cuda")
+        a.val[::7] = 0.0                                   # dropped edges
+        a.normed = "gat"
+        x = x0.clone().requires_grad_(True)
+        out = layer((x, a, True, 0.0), None)[0]
+        (out * torch.linspace(0.5, 1.5, out.numel(), device="cuda").view_as(out)).sum().backward()
+        res.append((out.detach(), x.grad.detach(), {k: p.grad.detach().clone() for k, p in layer.named_parameters()}))
+    close(res[1][0], res[0][0].cpu(), "fused GAT output")
+    close(res[1][1], res[0][1].cpu(), "fused GAT input gradient")
+    for k in res[0][2]:
+        close(res[1][2][k], res[0][2][k].cpu(), f"fused GAT grad of {k}")
