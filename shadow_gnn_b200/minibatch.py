@@ -100,6 +100,30 @@ class _SuperBatch:
         return self.b.rowptr[lo:hi + 1], self.b.indices[e0:e1], lo, e0, self.feat[lo:hi], self.b.target[a * R:b * R]
 
 
+def negative_sampling(pos_edge, num_nodes, num_neg, device, max_rounds=8):
+    """torch_geometric.utils.negative_sampling as the reference calls it (minibatch.py:289-293), on the device: `num_neg` distinct node pairs
+    that are not in add_self_loops(to_undirected(pos_edge)).  Pairs are drawn uniformly from the N x N grid and rejected against the sorted
+    key list of the excluded pairs; fewer than `num_neg` come back only if the graph is (nearly) complete.  (The random stream is torch's,
+    not PyG's: the pairs differ from the reference's draw, their distribution and the exclusion rule do not.)"""
+    pos = torch.as_tensor(np.asarray(pos_edge).astype(np.int64), device=device).reshape(-1, 2)
+    N = int(num_nodes)
+    loops = torch.arange(N, device=device, dtype=torch.int64)
+    excluded = torch.unique(torch.cat([pos[:, 0] * N + pos[:, 1], pos[:, 1] * N + pos[:, 0], loops * N + loops]))
+    got = torch.empty(0, dtype=torch.int64, device=device)
+    for _ in range(max_rounds):
+        need = num_neg - got.numel()
+        if need <= 0:
+            break
+        cand = torch.randint(0, N * N, (int(need * 1.2) + 16,), device=device, dtype=torch.int64)
+        idx = torch.searchsorted(excluded, cand).clamp_(max=excluded.numel() - 1)
+        cand = cand[excluded[idx] != cand]
+        got = torch.cat([got, cand])
+        uniq, first = np.unique(got.cpu().numpy(), return_index=True)             # distinct pairs, draw order kept
+        got = got[torch.as_tensor(np.sort(first), device=device)]
+    got = got[:num_neg]
+    return torch.stack([torch.div(got, N, rounding_mode="floor"), got % N], 1).cpu().numpy()
+
+
 def hop2onehot(hop_i32, dim):
     """EntityEncoding.hop2onehot_vec (frontend/graph.py:134-147): column 0 = unreachable (0xFFFFFFFF, or >= 255), column h+1 = hop h
     for h <= dim-2; larger finite hops give an all-zero row"""
@@ -142,9 +166,14 @@ class MinibatchShallowExtractor:
         self.batch_num = -1
         self.batch_size = {TRAIN: 0, VALID: 0, TEST: 0}
         self.raw_entity_set = entity_set
-        if isinstance(entity_set[TRAIN], dict):
-            raise NotImplementedError("link-prediction entity sets (2 roots per subgraph) are not wired through the device minibatch yet")
-        self.prediction_task = "node"
+        if isinstance(entity_set[TRAIN], dict):            # link prediction: {"pos": [E,2] (, "neg": [E',2])} per mode (minibatch.py:183-189)
+            for v in entity_set.values():
+                assert set(v.keys()).issubset({"pos", "neg"}) and "pos" in v
+            assert label_full is None, "link prediction takes its labels from the edge sets"
+            self.prediction_task = "link"
+        else:
+            self.prediction_task = "node"
+        self.num_roots = 2 if self.prediction_task == "link" else 1          # size_root (minibatch.py:373): both end points root one subgraph
         self.entity_epoch = {m: None for m in (TRAIN, VALID, TEST)}
         self.label_epoch = {m: None for m in (TRAIN, VALID, TEST)}
         self.is_transductive = is_transductive
@@ -195,12 +224,34 @@ class MinibatchShallowExtractor:
             assert all(sum(sb.remaining for sb in q) == 0 for q in self.pool[mode])
 
     def shuffle_entity(self, mode):
+        if self.prediction_task == "link":
+            return self._shuffle_edges(mode)
         perm = np.random.permutation(self.raw_entity_set[mode].size)
         if self.percent_per_epoch[mode] < 1.0:
             perm = perm[:int(np.ceil(self.percent_per_epoch[mode] * perm.size))]
         self.entity_epoch[mode] = np.asarray(self.raw_entity_set[mode])[perm]
         self.label_epoch[mode] = self.label_full[torch.as_tensor(self.entity_epoch[mode].astype(np.int64), device=self.dev_torch)]
         self.graph_sampler[mode].shuffle_targets(self.entity_epoch[mode])
+
+    def _shuffle_edges(self, mode):
+        """link prediction epoch (minibatch.py:281-304): positives + as many negatives (given, or drawn among the node pairs that are neither
+        a positive edge in either direction nor a self loop), label 1 / 0, one permutation over both; the sampler gets the end points
+        flattened, two consecutive targets root one subgraph"""
+        es = self.raw_entity_set[mode]
+        pos = np.asarray(es["pos"]).astype(np.int64).reshape(-1, 2)
+        if "neg" in es:
+            neg = np.asarray(es["neg"]).astype(np.int64).reshape(-1, 2)
+        else:
+            indptr = self.adj[mode][0] if isinstance(self.adj[mode], (tuple, list)) else self.adj[mode].indptr
+            neg = negative_sampling(pos, int(len(indptr) - 1), pos.shape[0], self.dev_torch)
+        edge_set = np.concatenate([pos, neg], axis=0)
+        label = np.repeat([1, 0], [pos.shape[0], neg.shape[0]])[:, np.newaxis]
+        perm = np.random.permutation(edge_set.shape[0])
+        if self.percent_per_epoch[mode] < 1.0:
+            perm = perm[:int(np.ceil(self.percent_per_epoch[mode] * perm.size))]
+        self.entity_epoch[mode] = edge_set[perm]
+        self.label_epoch[mode] = torch.from_numpy(label[perm]).to(self.dev_torch)
+        self.graph_sampler[mode].shuffle_targets(self.entity_epoch[mode].reshape(-1))
 
     def epoch_start_reset(self, epoch, mode):
         self.batch_num = -1
@@ -252,7 +303,8 @@ class MinibatchShallowExtractor:
         cpp_cfgs = []
         for c in cfgs:
             tf = lambda key: "true" if c.get(key, False) else "false"
-            d = {"method": c["method"], "num_roots": "1", "add_self_edge": tf("add_self_edge"), "include_target_conn": tf("include_target_conn")}
+            d = {"method": c["method"], "num_roots": str(self.num_roots), "add_self_edge": tf("add_self_edge"),
+                 "include_target_conn": "false" if self.prediction_task == "link" else tf("include_target_conn")}      # minibatch.py:376-377
             if c["method"] == "khop":
                 d.update(depth=str(c["depth"]), budget=str(c["budget"]))
             elif c["method"] in ("ppr", "ppr_st"):
@@ -270,7 +322,9 @@ class MinibatchShallowExtractor:
                 os.makedirs(d, exist_ok=True)
                 suffix = f"{'transductive' if self.is_transductive else 'inductive'}_{MODE2STR[mode]}_{alpha}_{eps}_{k}.bin"      # samplers_cpp.py:135-170
                 fn, fs = f"{d}/neighs_{suffix}", f"{d}/scores_{suffix}"
-            s.preproc_ppr_approximate(np.asarray(self.raw_entity_set[mode]), k, alpha, eps, fn, fs)
+            # node task: the mode's targets; link task: every node can be an end point (minibatch.py:380-389)
+            prep = np.asarray(self.raw_entity_set[mode]) if self.prediction_task == "node" else np.arange(len(indptr) - 1)
+            s.preproc_ppr_approximate(prep, k, alpha, eps, fn, fs)
         self.graph_sampler[mode] = s
         self.sampler_cfgs[mode] = cpp_cfgs
         self.is_stochastic_sampler[mode] = any(c["method"] in ("khop", "ppr_st") for c in cfgs)
@@ -292,7 +346,7 @@ class MinibatchShallowExtractor:
                 aug["pprs"] = ppr2onehot(b.ppr, self.dim_1hot_ppr)
             if "drnls" in self.aug_feats:
                 aug["drnls"] = drnl2onehot(b.drnl, self.dim_1hot_drnl)
-            sb = _SuperBatch(b, feat, aug, 1)
+            sb = _SuperBatch(b, feat, aug, self.num_roots)
             if self.prefetch_canonical:
                 sb.prepare_canonical()
             # the views must outlive the sampler's ring slot: one super-batch per branch is in flight, the ring holds NUM_RING

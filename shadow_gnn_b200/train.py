@@ -21,6 +21,7 @@ from .parallel import allreduce_flat_gradients, allreduce_two_buckets, join_buck
 class GraphedTrainer:
     def __init__(self, model, minibatch, row_cap, edge_cap, mode=TRAIN):
         assert minibatch.num_ensemble == 1 and not minibatch.aug_feats, "the graphed step covers the single-branch, no-augmentation path"
+        assert minibatch.prediction_task == "node", "link prediction (two targets per subgraph) runs through the eager DeepGNN.step"
         pools = {rp.type_pool for rp in model.res_pool_layers}
         assert "sort" not in pools, "sort pooling has data-dependent shapes (repeat_interleave): use the eager DeepGNN.step"
         self._needs_sizes = pools != {"center"}

@@ -535,3 +535,68 @@ def test_fused_gat_layer_equals_composed_path(D, H, K, act, monkeypatch):
     close(res[1][1], res[0][1].cpu(), "fused GAT input gradient")
     for k in res[0][2]:
         close(res[1][2][k], res[0][2][k].cpu(), f"fused GAT grad of {k}")
+
+
+def test_link_task_epoch_matches_oracle_and_trains():
+    """link prediction through the device minibatch (shaDow/minibatch.py:281-304,373-377; fe/samplers_ensemble.py:184-210): positives + drawn
+    negatives, label 1 / 0, two roots per subgraph, include_target_conn off.  Every batch equals the block-diagonal collation of the oracle's
+    two-root subgraphs for the same edge order; negatives are non-edges; a link DeepGNN takes training steps on those batches."""
+    from oracle import oracle as O
+    from shadow_gnn_b200 import minibatch as MB
+    from shadow_gnn_b200.models import DeepGNN
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(1200, 10, 5)
+    N = indptr.size - 1
+    rows = np.repeat(np.arange(N), np.diff(indptr.astype(np.int64)))
+    und = np.stack([rows, indices.astype(np.int64)], 1)
+    und = und[und[:, 0] < und[:, 1]]
+    rng = np.random.default_rng(0)
+    pos = und[rng.permutation(und.shape[0])[:150]]
+    torch.manual_seed(5); np.random.seed(5)
+    feat = torch.randn(N, 12)
+    es = {0: {"pos": pos}, 1: {"pos": pos[:20], "neg": pos[20:40][:, ::-1].copy()}, 2: {"pos": pos[:20]}}
+    cfg = {"batch_size": 16, "configs": [{"method": "khop", "depth": [2], "budget": [4], "add_self_edge": [True], "include_target_conn": [True]}]}
+    mb = MB.MinibatchShallowExtractor("toy", None, {m: (indptr, indices) for m in range(3)}, es, cfg, {"drnls"}, None, feat, None, 12, True, 1, seed_cpp=7,
+                                      num_subg_per_batch=64)
+    assert mb.prediction_task == "link"
+    mb.epoch_start_reset(0, MB.TRAIN)
+    mb.shuffle_entity(MB.TRAIN)
+    edges = mb.entity_epoch[MB.TRAIN]
+    lab = mb.label_epoch[MB.TRAIN].cpu().numpy()[:, 0]
+    assert edges.shape == (300, 2) and lab.sum() == 150
+    key = lambda e: e[:, 0] * N + e[:, 1]
+    posk = set(key(pos).tolist()) | set(key(pos[:, ::-1]).tolist())
+    negs = edges[lab == 0]
+    assert len(set(key(negs).tolist())) == 150 and not (set(key(negs).tolist()) & posk) and np.all(negs[:, 0] != negs[:, 1])
+    assert set(key(edges[lab == 1]).tolist()) == set(key(pos).tolist())
+    o = O.OracleSampler(indptr, indices, 64, 1, 7)
+    o.shuffle_targets(edges.reshape(-1).astype(np.uint32))
+    want = []
+    while True:
+        want.extend(o.sample(O.make_cfg("khop", num_roots=2, depth=2, budget=4, add_self_edge=True, include_target_conn=False, aug=("drnls",))).subgraphs())
+        if o.get_idx_root() == 0:
+            break
+    arch = dict(num_layers=2, num_cls_layers=1, heads=1, branch_sharing=False, dim=32, act="relu", layer_norm="norm_feat", feature_augment_ops="sum",
+                aggr="sage", residue="none", pooling="center", loss="sigmoid", ensemble_act="leakyrelu")
+    model = DeepGNN(12, 12, 1, 0, arch, [("drnls", mb.get_aug_dim("drnls"))], 1, dict(dropout=0.0, dropedge=0.0, lr=0.01, ensemble_dropout="none"), "link").cuda()
+    seen, losses = 0, []
+    while not mb.is_end_epoch(MB.TRAIN):
+        b = mb.one_batch(MB.TRAIN, ret_raw_idx=True)
+        bs = b.label.shape[0]
+        col = O.cat_to_block_diagonal(want[seen:seen + bs])
+        adj = b.adj_ens[0]
+        span = adj.row_span.cpu().numpy().astype(np.int64)
+        assert np.array_equal(span[:, 1] - span[:, 0], np.diff(col["indptr"]))
+        colidx = np.concatenate([adj.col.cpu().numpy()[s:e] - adj.col_off for s, e in span])
+        assert np.array_equal(colidx, col["indices"])
+        tgt = b.target_ens[0].cpu().numpy()
+        assert tgt.size == 2 * bs and np.array_equal(tgt, col["target"])
+        node = b.idx_raw[0].cpu().numpy().view(np.uint32)
+        assert np.array_equal(node, col["node"]) and np.array_equal(node[tgt].reshape(-1, 2), edges[seen:seen + bs])
+        assert np.array_equal(b.label.cpu().numpy()[:, 0], lab[seen:seen + bs])
+        losses.append(float(model.step(MB.TRAIN, "running", b)["loss"].detach()))
+        seen += bs
+    assert seen == 300 and all(np.isfinite(losses))
+    mb.epoch_end_reset(MB.TRAIN)
+    mb.epoch_start_reset(0, MB.VALID); mb.shuffle_entity(MB.VALID)          # given negatives are used as they are
+    assert mb.entity_epoch[MB.VALID].shape == (40, 2) and int(mb.label_epoch[MB.VALID].sum()) == 20
