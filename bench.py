@@ -56,11 +56,17 @@ def parse():
     ap.add_argument("--graph", default="S-products")
     ap.add_argument("--arch", default="sage", choices=["sage", "gat", "gcn", "gin"], help="aggregator of the 5-layer model (BASELINE configs[2]: sage; configs[3]: gat, --batch 64)")
     ap.add_argument("--batch", type=int, default=32, help="targets per step and GPU")
+    ap.add_argument("--ppr-k", type=int, default=150, help="PPR sampler budget k (BASELINE configs[4], papers100M: 400)")
+    ap.add_argument("--ppr-threshold", type=float, default=0.0, help="PPR relative score threshold (papers100M: 0.002)")
     ap.add_argument("--no-clustered", action="store_true", help="skip the secondary measurement on the clustered stand-in S-products-c")
     ap.add_argument("--cpu-sample", type=int, default=4000, help="roots of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    global PPR_K
+    PPR_K = a.ppr_k
+    SAMPLER_CFG.update(k=str(a.ppr_k), threshold=str(a.ppr_threshold))
     TRAIN_CFG["batch"] = a.batch
+    TRAIN_CFG["threshold"] = a.ppr_threshold
     if a.arch == "gat":          # config_train/products/vanilla/gat_5_ppr.yml (BASELINE configs[3])
         TRAIN_CFG.update(dropout=0.35, dropedge=0.1, lr=0.001)
         ARCH.update(aggr="gat", heads=4)
@@ -251,7 +257,7 @@ ARCH = dict(num_layers=5, num_cls_layers=1, heads=1, branch_sharing=False, dim=2
 class _Workload:
     def format(self, g):
         name = {"sage": "GraphSAGE", "gat": "GAT (4 heads)", "gcn": "GCN", "gin": "GIN"}[ARCH["aggr"]]
-        return (f"{g} 5-layer {name}-256, PPR(k=150,eps=1e-5) sampler, batch {TRAIN_CFG['batch']} per GPU, dropout {TRAIN_CFG['dropout']}, "
+        return (f"{g} 5-layer {name}-256, PPR(k={PPR_K},eps=1e-5,threshold={TRAIN_CFG.get('threshold', 0.0)}) sampler, batch {TRAIN_CFG['batch']} per GPU, dropout {TRAIN_CFG['dropout']}, "
                 f"dropedge {TRAIN_CFG['dropedge']}, Adam lr {TRAIN_CFG['lr']}, clip 5: sample + block-diagonal batch + feature gather + forward + backward + optimizer step")
 
 
@@ -459,7 +465,7 @@ def train_phase(ctx, steps, warmup):
     labels = torch.from_numpy(np.random.default_rng(7).integers(0, C, ctx.N)).to(dev)
     B = TRAIN_CFG["batch"]
     share = ctx.share.numpy()
-    cfg = {"batch_size": B, "configs": [{"method": "ppr", "k": [PPR_K], "threshold": [0.0], "epsilon": [PPR_EPS]}]}
+    cfg = {"batch_size": B, "configs": [{"method": "ppr", "k": [PPR_K], "threshold": [TRAIN_CFG.get("threshold", 0.0)], "epsilon": [PPR_EPS]}]}
     adjs = {m: (ctx.g["indptr"], ctx.g["indices"]) for m in range(3)}
     # the timed region must contain sampling whatever --steps is: at least 4 super-batch refills (sampler + gather + canonical CSR) fall inside it
     sb_train = max(B, min(args.superbatch_train, B * max(1, steps // 4)))

@@ -90,6 +90,42 @@ def powerlaw_graph_torch(n, nnz_target, seed, dmax, device, community=None):
     return indptr, indices
 
 
+def stratified_csr_torch(n, nnz_target, seed, device, rows_per_chunk=2_000_000):
+    """Directed CSR with sorted, duplicate-free rows for SCALE tests (billions of edges: the sort / unique of the recipe above does not fit
+    CUB's 2^31-element limit).  Row i gets a power-law degree d_i and the neighbours lo_j + floor(u_j (hi_j - lo_j)), lo_j = floor(j n / d_i), hi_j = lo_{j+1}, u_j ~ U[0,1): one
+    stratified draw per slot, so a row is sorted and unique by construction.  Returns (indptr int64 [n+1], indices int32 [nnz])."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = torch.rand(n, generator=g, device=device, dtype=torch.float64).clamp_min(1e-12)
+    raw = u.pow(-1.0 / 1.6) - 1.0
+    c = 1.0
+    dmax = min(n // 4, 100_000)
+    for _ in range(30):
+        deg = torch.clamp(torch.floor(raw * c) + 1, max=dmax)
+        c *= nnz_target / float(deg.sum())
+    deg = torch.clamp(torch.floor(raw * c) + 1, max=dmax).long()
+    del u, raw
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    E = int(indptr[-1])
+    indices = torch.empty(E, dtype=torch.int32, device=device)
+    for r0 in range(0, n, rows_per_chunk):
+        r1 = min(n, r0 + rows_per_chunk)
+        d = deg[r0:r1]
+        e0, e1 = int(indptr[r0]), int(indptr[r1])
+        rows = torch.repeat_interleave(torch.arange(r1 - r0, device=device), d)
+        j = torch.arange(e1 - e0, device=device, dtype=torch.int64) - (indptr[r0:r1][rows] - e0)
+        dd = d[rows].double()
+        lo = torch.floor(j.double() * (n / dd)).long()                       # integer strata [lo_j, hi_j): disjoint because n / d >= 1
+        hi = torch.floor((j.double() + 1.0) * (n / dd)).long().clamp_(max=n)
+        ids = (lo + torch.floor(torch.rand(e1 - e0, generator=g, device=device, dtype=torch.float64) * (hi - lo).double()).long()).clamp_(max=n - 1)
+        del lo, hi
+        indices[e0:e1] = ids.to(torch.int32)
+        del rows, j, dd, ids
+    return indptr, indices
+
+
 def small_parity_graph(n=2000, avg_deg=12, seed=0, self_loops=0):
     """Small graph for parity tests: power-law + optional pre-existing self loops + tail component."""
     indptr, indices = powerlaw_graph(n, n * avg_deg, seed, dmax=max(8, n // 10), tail=True)
