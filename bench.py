@@ -491,7 +491,12 @@ def train_phase(ctx, steps, warmup):
         return model.step(MB.TRAIN, "running", b)["loss"].detach(), b.batch_size
     for _ in range(warmup):
         one_step()
-    log("train phase: warmup done")
+    # one-time allocations must not leak into the timed region: both result buffers of the sampler's ring (and the allocator blocks of the
+    # gathered features) exist only after the third sampler call, so the warm-up runs on until then (untimed, like the --warmup steps)
+    extra = 0
+    while mb.num_sampler_calls < 3 and extra < 4096:
+        one_step(); extra += 1
+    log("train phase: warmup done", f"({warmup} + {extra} steps, {mb.num_sampler_calls} sampler calls)")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.barrier()
     ev0.record()
@@ -532,10 +537,31 @@ def train_phase(ctx, steps, warmup):
     ctx.barrier()
     e2e_s = time.perf_counter() - t0
     (ms_all, e2e_all), (n_all, ne_all) = ctx.reduce([ms, e2e_s], [nsamp, ne2e])
-    mine = 38       # fill, dropedge, row-normalise, 5 x (spmm + 2 act_norm) fwd, classifier norm, 5 spmm^T + 11 act_norm bwd, 3 optimizer launches
+    # launches of THIS repo's kernels, counted (CUPTI through torch.profiler, outside the timed regions): one training step and one sampler call
+    ours = ("ppr_", "sample_induce", "scan_counts", "scan_edge_counts", "canonicalize", "gather_rows", "spmm_", "act_norm", "colsum_finish", "linear_tc", "wgrad_",
+            "gemm_tf32x3", "tf32_split", "gat_", "fill_edge_vals", "dropedge_kernel", "row_normalize", "row_degree", "sym_", "segment_pool", "adam_clip", "sqnorm_kernel",
+            "bump_step", "khop_")
+    from torch.profiler import profile, ProfilerActivity
+
+    def count_ours(fn):
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        return sum(e.count for e in prof.key_averages() if any(k in e.key for k in ours))
+    calls0 = mb.num_sampler_calls
+    per_step = None
+    for _ in range(8):                                   # a step that does not refill
+        c0 = mb.num_sampler_calls
+        k = count_ours(one_step)
+        if mb.num_sampler_calls == c0:
+            per_step = k
+            break
+    per_refill = count_ours(lambda: mb.par_graph_sample(MB.TRAIN))
+    mb.pool[MB.TRAIN][0].pop()                           # the counted call's super-batch is not consumed (its targets are skipped)
+    mine = per_step if per_step is not None else 0
     return dict(value=n_all / (ms_all * 1e-3), unit="samples/s", ms_per_step=ms_all / steps, nparams=nparams,
                 graph_steps=getattr(trainer, "graph_steps", 0), eager_steps=getattr(trainer, "eager_steps", steps),
-                gpu_launches=mine * steps + 7 * (steps * B // args.superbatch_train + 1),      # per super-batch: count, scan, fast path, redo, gather, 2 x canonical CSR
+                gpu_launches=int(mine * steps + per_refill * refills), launches_per_step=int(mine), launches_per_sampler_call=int(per_refill),
                 superbatch=sb_train, refills_in_timed_region=int(refills),
                 e2e={"value": ne_all / e2e_all, "unit": "samples/s", "h2d_bytes_per_step": B * 8 + B * 4, "d2h_bytes_per_step": 4,
                      "note": "labels from pinned host memory each step, loss read back each step; the epoch's target ids are uploaded once per epoch (4 B per target)"})
