@@ -147,6 +147,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M;
   const int num_kb = (P.debug & 1) ? 0 : (P.K + BLOCK_K - 1) / BLOCK_K;
+  // column split (gridDim.z = 2): this CTA owns output columns [n0, n0 + bn) -- half the MMA work and half the epilogue per CTA, twice the CTAs
+  // (a 4,832-row batch is only 38 row tiles).  Only without norm_feat: its row statistics need every column of the row.
+  const int bn = BLOCK_N / (int)gridDim.z, n0 = (int)blockIdx.z * bn;
+  const int b_tile = bn * BLOCK_K * 4;
   const CUtensorMap *map_x = blockIdx.y ? &map_x1 : &map_x0, *map_w = blockIdx.y ? &map_w1 : &map_w0;
   const CUtensorMap *map_z = blockIdx.y ? &map_z1 : &map_z0, *map_o = blockIdx.y ? &map_o1 : &map_o0, *map_wl = blockIdx.y ? &map_wl1 : &map_wl0;
   const LinearBranch B = P.br[blockIdx.y];
@@ -163,10 +167,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < BLOCK_N; i += NUM_THREADS) {
-    const bool in = i < P.N;
-    vecs[i] = (in && B.bias) ? B.bias[i] : 0.f;
-    vecs[BLOCK_N + i] = (in && NORM) ? B.scale[i] : 1.f;
-    vecs[2 * BLOCK_N + i] = (in && NORM) ? B.offset[i] : 0.f;
+    const bool in = n0 + i < P.N && i < bn;
+    vecs[i] = (in && B.bias) ? B.bias[n0 + i] : 0.f;
+    vecs[BLOCK_N + i] = (in && NORM) ? B.scale[n0 + i] : 1.f;
+    vecs[2 * BLOCK_N + i] = (in && NORM) ? B.offset[n0 + i] : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -180,16 +184,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
         const int s = kb % NSTAGES;
         mbar_wait(&empty[s], ((kb / NSTAGES) & 1) ^ 1);
         unsigned char *st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&full[s], A_TILE + (P.presplit ? 2 : 1) * B_TILE);
+        mbar_expect_tx(&full[s], A_TILE + (P.presplit ? 2 : 1) * b_tile);
         tma_load_2d(st, map_x, &full[s], kb * BLOCK_K, m0);                       // A     [128 rows][BLOCK_K]
-        tma_load_2d(st + 2 * A_TILE, map_w, &full[s], kb * BLOCK_K, 0);           // B (hi) [256 rows][BLOCK_K]
-        if (P.presplit) tma_load_2d(st + 2 * A_TILE + B_TILE, map_wl, &full[s], kb * BLOCK_K, 0);      // B lo
+        tma_load_2d(st + 2 * A_TILE, map_w, &full[s], kb * BLOCK_K, n0);          // B (hi) [bn rows][BLOCK_K]
+        if (P.presplit) tma_load_2d(st + 2 * A_TILE + B_TILE, map_wl, &full[s], kb * BLOCK_K, n0);     // B lo
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = umma_idesc_tf32(BLOCK_M, bn);
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % NSTAGES;
         mbar_wait(&ready[s], (kb / NSTAGES) & 1);
@@ -224,7 +228,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
       }
       if (!P.presplit)
 #pragma unroll 4
-      for (int i = t; i < B_TILE / 16; i += NUM_WORKERS) {
+      for (int i = t; i < b_tile / 16; i += NUM_WORKERS) {
         const float4 v = b_hi[i];
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -248,7 +252,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
     const int row_l = quad * 32 + lane;                // row inside the CTA tile
     const int row = m0 + row_l;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int N = P.N;
+    const int N = min(bn, P.N - n0);                     // this CTA's columns (local index c <-> global column n0 + c)
     const float *vb = vecs, *vs = vecs + BLOCK_N, *vo = vecs + 2 * BLOCK_N;
     float mean = 0.f, rstd = 1.f;
     uint32_t r[32];
@@ -300,9 +304,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_consta
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to TMA
       __syncwarp();
       if (lane == 0) {
-        if (B.Z) tma_store_2d(map_z, zb, c0, m0 + quad * 32);
-        if (P.out_mode == 0) tma_store_2d(map_o, ob, c0, m0 + quad * 32);
-        else tma_reduce_add_2d(map_o, ob, c0, m0 + quad * 32);
+        if (B.Z) tma_store_2d(map_z, zb, n0 + c0, m0 + quad * 32);
+        if (P.out_mode == 0) tma_store_2d(map_o, ob, n0 + c0, m0 + quad * 32);
+        else tma_reduce_add_2d(map_o, ob, n0 + c0, m0 + quad * 32);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
@@ -358,7 +362,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz0, const __grid_consta
   const CUtensorMap *map_dz = blockIdx.y ? &map_dz1 : &map_dz0, *map_x = blockIdx.y ? &map_x1 : &map_x0, *map_p = blockIdx.y ? &map_p1 : &map_p0;
   const int num_kb = WG_ROWS / WG_BK;
   const int halves = P.N_out > 128 ? 2 : 1;
-  const int n_mma = (P.K_in + 15) & ~15;             // MMA N: the gradient's columns
+  // column split (gridDim.z = 2): this CTA owns the gradient's columns [k0, k0 + kw): only that half of X is transposed and multiplied
+  const int kw_cap = 256 / (int)gridDim.z, k0 = (int)blockIdx.z * kw_cap, kw = min(kw_cap, P.K_in - k0);
+  const int n_mma = (kw + 15) & ~15;                 // MMA N: the gradient's columns of this CTA
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map_dz) : "memory");
@@ -382,9 +388,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz0, const __grid_consta
         const int s = kb % WG_STAGES;
         mbar_wait(&empty[s], ((kb / WG_STAGES) & 1) ^ 1);
         unsigned char *st = smem + s * WG_STAGE_BYTES;
-        mbar_expect_tx(&full[s], 2 * WG_RAW);
+        mbar_expect_tx(&full[s], WG_RAW + WG_RAW / (int)gridDim.z);
         tma_load_2d(st, map_dz, &full[s], 0, m0 + kb * WG_BK);                   // [16 rows][256 columns of dZ], out-of-range = 0
-        tma_load_2d(st + WG_RAW, map_x, &full[s], 0, m0 + kb * WG_BK);           // [16 rows][256 columns of X]
+        tma_load_2d(st + WG_RAW, map_x, &full[s], k0, m0 + kb * WG_BK);          // [16 rows][kw_cap columns of X from k0]
       }
     }
   } else if (warp == 1) {
@@ -396,7 +402,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz0, const __grid_consta
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = smem_u32(smem + s * WG_STAGE_BYTES + 2 * WG_RAW), a_lo = a_hi + WG_OP, b_hi = a_lo + WG_OP, b_lo = b_hi + WG_OP;
         for (int h = 0; h < halves; h++) {
-          const uint32_t ah = a_hi + h * (WG_OP / 2), al = a_lo + h * (WG_OP / 2), d = tmem_base + h * 256;
+          const uint32_t ah = a_hi + h * (WG_OP / 2), al = a_lo + h * (WG_OP / 2), d = tmem_base + h * kw_cap;
 #pragma unroll
           for (int k = 0; k < WG_BK / UMMA_K; k++) {
             const uint32_t ko = k * UMMA_K * 4;
@@ -419,11 +425,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz0, const __grid_consta
       unsigned char *st = smem + s * WG_STAGE_BYTES;
 #pragma unroll
       for (int op = 0; op < 2; op++) {
+        if (op == 1 && t >= kw_cap) continue;          // X: only this CTA's columns (raw tile rows are kw_cap floats wide)
         const float *raw = reinterpret_cast<const float *>(st + op * WG_RAW);
         unsigned char *hi = st + 2 * WG_RAW + op * 2 * WG_OP, *lo = hi + WG_OP;
+        const int rw = op ? kw_cap : 256;
         float v[WG_BK];
 #pragma unroll
-        for (int m = 0; m < WG_BK; m++) v[m] = raw[m * 256 + t];
+        for (int m = 0; m < WG_BK; m++) v[m] = raw[m * rw + t];
 #pragma unroll
         for (int q = 0; q < WG_BK / 4; q++) {
           float4 h4, l4;
@@ -447,8 +455,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz0, const __grid_consta
     uint32_t r[32];
     int it = 0;
     for (int h = 0; h < halves; h++) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + h * 256;
-      for (int c0 = half * 32; c0 < P.K_in; c0 += 64, it++) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + h * kw_cap;
+      for (int c0 = half * 32; c0 < kw; c0 += 64, it++) {
         tmem_ld32(taddr + c0, r);
         unsigned char *ob = stage_w + (size_t)(it & 1) * 4096;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -460,7 +468,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz0, const __grid_consta
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(map_p, ob, c0, h * 128 + quad * 32, slice);
+          tma_store_3d(map_p, ob, k0 + c0, h * 128 + quad * 32, slice);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -554,6 +562,14 @@ extern "C" int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbra
   if (out_mode < 0 || out_mode > 2) FAIL(SHADOW_EINVAL, "linear_tc: out_mode");
   CUtensorMap mx[2], mw[2], mz[2], mo[2], mwl[2];
   const bool presplit = br[0].W_lo != nullptr;
+  // two column halves per row tile when no row statistics are needed and the doubled grid still fits ONE wave (one CTA per SM: a 4,832-row
+  // pair launch is 76 CTAs, doubled it would be 152 > 148 and the four stragglers double the kernel's duration -- measured)
+  const int row_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  static const bool no_split = getenv("SHADOW_LTC_NOSPLIT") != nullptr;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int nsplit = (!do_norm && N > 128 && !no_split && row_tiles * nbranch * 2 <= sms) ? 2 : 1;
+  const int bn = BLOCK_N / nsplit;
   LinearParams P;
   for (int b = 0; b < 2; b++) {
     const shadow_linear_branch &s = br[b < nbranch ? b : 0];
@@ -562,10 +578,10 @@ extern "C" int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbra
     if (do_norm && (!s.scale || !s.offset)) FAIL(SHADOW_EINVAL, "linear_tc: norm_feat needs scale and offset");
     int rc = make_map(&mx[b], s.X, M, K, ldx, BLOCK_M);
     if (rc) return rc;
-    rc = make_map(&mw[b], s.W, N, K, ldw, BLOCK_N);
+    rc = make_map(&mw[b], s.W, N, K, ldw, bn);
     if (rc) return rc;
     if ((s.W_lo != nullptr) != presplit || ((uintptr_t)s.W_lo & 15)) FAIL(SHADOW_EINVAL, "linear_tc: W_lo must be given for all branches or none, 16-byte aligned");
-    rc = make_map(&mwl[b], presplit ? s.W_lo : s.W, N, K, ldw, BLOCK_N);
+    rc = make_map(&mwl[b], presplit ? s.W_lo : s.W, N, K, ldw, bn);
     if (rc) return rc;
     rc = make_map(&mo[b], s.out, M, N, ldo, 32, 32);                           // epilogue tiles: 32 rows x 32 columns, 128-byte swizzle
     if (rc) return rc;
@@ -585,7 +601,7 @@ extern "C" int shadow_linear_tc_f32(const shadow_linear_branch *br, int32_t nbra
   static bool attr_set[5][2] = {};
   const kern_t kern = kerns[act][do_norm ? 1 : 0];
   if (!attr_set[act][do_norm ? 1 : 0]) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_set[act][do_norm ? 1 : 0] = true; }
-  kern<<<dim3((M + BLOCK_M - 1) / BLOCK_M, nbranch), NUM_THREADS, SMEM_BYTES, (cudaStream_t)cuda_stream>>>(mx[0], mw[0], mx[1], mw[1], mz[0], mo[0], mz[1], mo[1], mwl[0], mwl[1], P);
+  kern<<<dim3(row_tiles, nbranch, nsplit), NUM_THREADS, SMEM_BYTES, (cudaStream_t)cuda_stream>>>(mx[0], mw[0], mx[1], mw[1], mz[0], mo[0], mz[1], mo[1], mwl[0], mwl[1], P);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -606,12 +622,12 @@ extern "C" int shadow_tf32_split_transpose_f32(const float *src, const int64_t *
 }
 
 namespace {
-int make_map_raw(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld) {      // box = [256 columns, 16 rows], no swizzle
+int make_map_raw(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld, int box_cols = 256) {      // box = [box_cols columns, 16 rows], no swizzle
   encode_tiled_fn enc = get_encode();
   if (!enc) FAIL(SHADOW_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {256, (cuuint32_t)WG_BK};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)WG_BK};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -643,13 +659,17 @@ extern "C" int shadow_wgrad_tc_f32(const float *dZ0, const float *X0, float *gra
   const float *dZ[2] = {dZ0, dZ1 ? dZ1 : dZ0}, *X[2] = {X0, X1 ? X1 : X0};
   float *grad[2] = {grad0, grad1 ? grad1 : grad0}, *scr[2] = {scratch0, scratch1 ? scratch1 : scratch0};
   const int slices = (M + WG_ROWS - 1) / WG_ROWS;
+  static const bool no_split = getenv("SHADOW_LTC_NOSPLIT") != nullptr;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int ksplit = (K_in > 128 && !no_split && slices * nb * 2 <= sms) ? 2 : 1;      // one wave only (see shadow_linear_tc_f32)
   CUtensorMap mdz[2], mx[2], mp[2];
   for (int b = 0; b < 2; b++) {
     if (!dZ[b] || !X[b] || !grad[b] || !scr[b]) FAIL(SHADOW_EINVAL, "wgrad_tc: NULL argument");
     if (((uintptr_t)dZ[b] | (uintptr_t)X[b] | (uintptr_t)grad[b] | (uintptr_t)scr[b]) & 15) FAIL(SHADOW_EINVAL, "wgrad_tc: pointers must be 16-byte aligned");
     int rc = make_map_raw(&mdz[b], dZ[b], M, N_out, N_out);
     if (rc) return rc;
-    rc = make_map_raw(&mx[b], X[b], M, K_in, K_in);
+    rc = make_map_raw(&mx[b], X[b], M, K_in, K_in, 256 / ksplit);
     if (rc) return rc;
     rc = make_map_partial(&mp[b], scr[b], slices, N_out, K_in);
     if (rc) return rc;
@@ -658,7 +678,7 @@ extern "C" int shadow_wgrad_tc_f32(const float *dZ0, const float *X0, float *gra
   P.M = M; P.N_out = N_out; P.K_in = K_in;
   static bool attr_set = false;
   if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM)); attr_set = true; }
-  wgrad_tc_kernel<<<dim3(slices, nb), NUM_THREADS, WG_SMEM, (cudaStream_t)cuda_stream>>>(mdz[0], mx[0], mdz[1], mx[1], mp[0], mp[1], P);
+  wgrad_tc_kernel<<<dim3(slices, nb, ksplit), NUM_THREADS, WG_SMEM, (cudaStream_t)cuda_stream>>>(mdz[0], mx[0], mdz[1], mx[1], mp[0], mp[1], P);
   CUDA_TRY(cudaGetLastError());
   const int n4 = N_out * K_in / 4;
   wgrad_finish_kernel<<<dim3((n4 + 255) / 256, nb), 256, 0, (cudaStream_t)cuda_stream>>>((const float4 *)scr[0], (const float4 *)scr[1], (float4 *)grad[0], (float4 *)grad[1],
