@@ -144,6 +144,11 @@ int shadow_sampler_batch_info(shadow_sampler *s, int branch, shadow_batch_info *
 /* diagnostics: how many subgraphs of the last validated launch did not fit the one-warp-per-subgraph PPR fast path's on-chip
  * staging and were rebuilt by the generic kernel (no reference counterpart; results are identical either way) */
 int64_t shadow_sampler_last_redo_count(const shadow_sampler *s);
+/* diagnostics: 1 when the last launch ran the symmetric-graph variant of the PPR fast path.  The first fast-path launch on a graph verifies
+ * that every edge has its reverse and that rows are strictly ascending (what fe/graph_utils.py:19-45 to_undirected guarantees); on such a
+ * graph only the upper part of every row is scanned and each kept edge also yields its mirror image through a reverse-slot index built by
+ * the same check.  Results are bit-identical to the full scan; SHADOW_NO_SYM=1 in the environment keeps the full scan. */
+int shadow_sampler_last_sym(const shadow_sampler *s);
 /* device pointer + count of 4-byte elements of one field of the latest batch (valid until num_ring further calls) */
 int shadow_sampler_batch_field_dev(shadow_sampler *s, int branch, int field, void **ptr_dev, int64_t *count);
 /* copy one field to the host; 4 bytes per element */

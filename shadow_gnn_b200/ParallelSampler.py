@@ -293,6 +293,10 @@ class ParallelSampler:
         """subgraphs of the last validated call that the one-warp PPR fast path handed to the generic kernel (diagnostics)"""
         return int(lib.shadow_sampler_last_redo_count(self._h))
 
+    def last_sym(self):
+        """True when the last call ran the symmetric-graph (upper-triangle scan + mirror) variant of the PPR fast path (diagnostics)"""
+        return bool(lib.shadow_sampler_last_sym(self._h) == 1)
+
     def set_stream(self, cuda_stream):
         """pin the sampler to one stream (default: whatever torch's current stream is at each call)"""
         self._user_stream = True

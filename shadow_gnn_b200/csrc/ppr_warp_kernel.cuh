@@ -130,7 +130,7 @@ __device__ __forceinline__ void scan_load(ScanStage &S, const uint32_t c0, const
 // staged stream (a per-warp scratch region in global memory that lives in L2).  Stream order = queue order (window, lane), then slot
 // = ascending full-graph slot = CSR order (PS.cpp:420-422).  Per-row facts (kept count; with a self-edge insertion also "kept entries
 // below v" and "v itself kept") are accumulated with one shared-memory atomic per lane.
-template <bool ADD_SELF>
+template <bool ADD_SELF, bool SYM>
 __device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t *cq_code, const uint32_t first, const uint32_t count,
                                             const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf, const uint32_t *nodes,
                                             const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row, uint32_t &cnt, const int lane,
@@ -140,7 +140,8 @@ __device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t
   uint32_t code = WARP_OFFMASK;
   if (active) { q = cq_keys[first + lane]; code = cq_code[first + lane]; }
   const uint32_t row = code >> WARP_OFFBITS, off0 = (code & WARP_OFFMASK) - 3u;
-  const uint2 r = rs[row];
+  uint2 r = rs[row];
+  if (SYM) r.y &= 0x7fffffffu;                         // bit 31 marks a row whose PS.cpp:401 slot was appended (resolve pass)
   const uint32_t nb[WARP_CS] = {q.x, q.y, q.z, q.w};
   bool hit[WARP_CS];
   uint32_t bal[WARP_CS], at = cnt, tot = 0, inc = 0;
@@ -159,12 +160,12 @@ __device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t
     hit[e] = hit[e] && (off0 + (uint32_t)e) < r.y;    // member of the node set, slot inside [s, s + len)
     bal[e] = __ballot_sync(0xffffffffu, hit[e]);
     at += __popc(bal[e] & lt); tot += __popc(bal[e]);
-    if (ADD_SELF) inc += hit[e] ? (1u + (nb[e] < v ? (1u << 14) : 0u) + (nb[e] == v ? (1u << 28) : 0u)) : 0u;
+    if (ADD_SELF) inc += hit[e] ? (1u + ((!SYM && nb[e] < v) ? (1u << 14) : 0u) + (nb[e] == v ? (1u << 28) : 0u)) : 0u;
     else inc += hit[e] ? 1u : 0u;
   }
 #pragma unroll
   for (int e = 0; e < WARP_CS; e++) {
-    if (hit[e]) { sc_ent[at] = make_uint2(nb[e], r.x + off0 + (uint32_t)e); if (ADD_SELF) sc_row[at] = (unsigned short)row; }
+    if (hit[e]) { sc_ent[at] = make_uint2(nb[e], r.x + off0 + (uint32_t)e); if (ADD_SELF || SYM) sc_row[at] = (unsigned short)row; }
     at += hit[e] ? 1u : 0u;
   }
   if (inc) atomicAdd(&rc[row], inc);
@@ -173,7 +174,7 @@ __device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t
 
 // Level 1 on one window: a lane ORs the Bloom verdicts of its 4 slots; ONE ballot appends the chunks that may hold a member to the queue,
 // a full warp of queued chunks is drained at once.
-template <bool ADD_SELF, int NF>
+template <bool ADD_SELF, int NF, bool SYM>
 __device__ __forceinline__ void scan_window(const uint32_t any, const uint4 q, const uint32_t code, uint4 *cq_keys, uint32_t *cq_code,
                                             uint32_t &qn, const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf,
                                             const uint32_t *nodes, const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
@@ -183,7 +184,7 @@ __device__ __forceinline__ void scan_window(const uint32_t any, const uint4 q, c
   qn += __popc(bal);
   if (qn >= 32u) {
     __syncwarp();
-    drain_batch<ADD_SELF>(cq_keys, cq_code, 0u, 32u, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+    drain_batch<ADD_SELF, SYM>(cq_keys, cq_code, 0u, 32u, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
     const uint32_t left = qn - 32u;                  // < 32: move the tail to the front
     uint4 tk = make_uint4(0u, 0u, 0u, 0u); uint32_t tc = 0;
     if ((uint32_t)lane < left) { tk = cq_keys[32 + lane]; tc = cq_code[32 + lane]; }
@@ -278,7 +279,14 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int *__restrict
 }
 
 // NF = Bloom words per lane (1: ncap <= 192, 2: <= 448, 4 above)
-template <bool ADD_SELF, int NF>
+// SYM = the graph was verified symmetric with strictly ascending rows when the sampler first used it (sym_build_kernel, sampler.cu).  Then
+// v in adj(u) <=> u in adj(v), so only the UPPER part of every row (neighbours >= the row's own id; its extent travels with the table entry,
+// ppr_supper) is scanned -- half the slots, half the probes.  A kept edge (u, v), u < v, found in row u also stands for the edge (v, u) of
+// row v: its full-graph slot comes from the reverse-slot index sym_rev[] (one 4-byte read per kept edge), and because rows are scanned in
+// ascending u the mirrored edges of a row arrive in ascending order, i.e. in CSR order, ahead of the row's own upper part (PS.cpp:420-422
+// emits a row in slot order = ascending neighbour id).  The PS.cpp:401 slot one past a row is a DIRECTED quirk: it is kept for its row and
+// never mirrored.  Output is bit-identical to the full scan (same parity tests); a graph that fails the check keeps the full scan.
+template <bool ADD_SELF, int NF, bool SYM>
 __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(const SampleParams P) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   uint32_t *const nodes = (uint32_t *)(smem_dyn + P.WL.nodes);
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
   uint32_t *const fw = (uint32_t *)(smem_dyn + P.WL.bloom);        // Bloom words while they are built (32 * NF)
   uint4 *const cq_keys = (uint4 *)(smem_dyn + P.WL.queue);         // chunk queue: the 4 keys of a chunk ...
   uint32_t *const cq_code = (uint32_t *)(cq_keys + WARP_QCAP);     // ... and row << 19 | offset of its first slot in the row + 3
-  uint32_t *const rlo = (uint32_t *)(smem_dyn + P.WL.rlo);         // ADD_SELF only: first staged entry / insert position / bug column per row
+  uint32_t *const rlo = (uint32_t *)(smem_dyn + P.WL.rlo);         // ADD_SELF: first staged entry / insert position / bug column per row; SYM: rlo = output offset of a row's staged run
   uint32_t *const rins = (uint32_t *)(smem_dyn + P.WL.rins);
   uint32_t *const rbug = (uint32_t *)(smem_dyn + P.WL.rbug);
   // staged kept edges {neighbour id, full-graph slot} (+ row), CSR order: per-warp scratch in global memory.  A warp reuses its few KB
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       const uint32_t m = __ballot_sync(FULL, selp), mb = __ballot_sync(FULL, selp && id < t), mr = __ballot_sync(FULL, sel && id == t);
       if (sel) {                                        // entries below the root keep their rank, the root's slot follows them, the rest shift by one
         const uint32_t at = run + __popc(m & lt) + ((selp && id > t) ? 1u : 0u);
-        nodes[at] = id; rs[at] = P.ppr_srow[off + i];
+        nodes[at] = id; rs[at] = SYM ? P.ppr_supper[off + i] : P.ppr_srow[off + i];
         P.orig_node[node_base + at] = id; P.ppr_out[node_base + at] = P.ppr_sscore[off + i];
       }
       run += __popc(m); n_below += __popc(mb); root_in |= (mr != 0);
@@ -353,8 +361,13 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       nodes[n_below] = t;
       P.orig_node[node_base + n_below] = t;
       P.ppr_out[node_base + n_below] = (size_neigh <= 1 && len_all > 0) ? P.ppr_scores[off] : -1.f;
-      const uint32_t s = P.indptr[t];
-      rs[n_below] = make_uint2(s, P.indptr[t + 1] - s);
+      uint32_t s = P.indptr[t];
+      const uint32_t e = P.indptr[t + 1];
+      if (SYM) {                                        // upper part of the root's row: first slot whose neighbour is >= t
+        uint32_t hi = e;
+        while (s < hi) { const uint32_t mid = s + ((hi - s) >> 1); if (__ldg(P.indices + mid) < t) s = mid + 1; else hi = mid; }
+      }
+      rs[n_below] = make_uint2(s, e - s);
     }
     const int n = (int)run + 1;                         // == node_ptr[p+1] - node_ptr[p]
 
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
           if (q < WARP_OVF_CAP) ovf[1 + q] = v;
         }
         uint2 r = rs[i];
-        if (ext && r.x + r.y < E) { r.y += 1; rs[i] = r; }                                       // the PS.cpp:401 slot joins the row
+        if (ext && r.x + r.y < E) { r.y += 1; rs[i] = make_uint2(r.x, SYM ? (r.y | 0x80000000u) : r.y); }      // the PS.cpp:401 slot joins the row
         ch = r.y ? (((r.x + r.y + (WARP_CS - 1)) >> WARP_CSH) - (r.x >> WARP_CSH)) : 1u;          // aligned chunks; every row owns >= 1
         rc[i] = 0;
       }
@@ -423,16 +436,32 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
           any[u] = (bloom_test<NF>(f, SA.q[u].x) | bloom_test<NF>(f, SA.q[u].y) | bloom_test<NF>(f, SA.q[u].z) | bloom_test<NF>(f, SA.q[u].w)) & 1u;
 #pragma unroll
         for (int u = 0; u < WARP_U; u++)
-          scan_window<ADD_SELF, NF>(any[u], SA.q[u], SA.code[u], cq_keys, cq_code, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+          scan_window<ADD_SELF, NF, SYM>(any[u], SA.q[u], SA.code[u], cq_keys, cq_code, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
 #if WARP_DB
 #pragma unroll
         for (int u = 0; u < WARP_U; u++) { SA.q[u] = SB.q[u]; SA.code[u] = SB.code[u]; }
 #endif
       }
-      if (!bail && qn) { __syncwarp(); drain_batch<ADD_SELF>(cq_keys, cq_code, 0u, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt); }
+      if (!bail && qn) { __syncwarp(); drain_batch<ADD_SELF, SYM>(cq_keys, cq_code, 0u, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt); }
     }
     __syncwarp();
     if (p_next < P.num_subg) { off_next = P.ppr_ptr[t_next]; row_end_next = P.ppr_ptr[t_next + 1]; }      // consumed before the emit
+    if (SYM && !bail) {
+      // resolve pass over the staged (upper-part) edges, all lanes busy: sub id of the neighbour, "does this edge have a mirror image",
+      // mirror count of the neighbour's row (bits 14..27 of rc[]); the entry is rewritten as row | sub << 13 | mirrored << 31
+#pragma unroll 1
+      for (uint32_t g = lane; g < cnt; g += 32) {
+        const uint2 ent = __ldcg(sc_ent + g);
+        const uint32_t row = __ldcg(sc_row + g);
+        const uint2 r = rs[row];
+        const uint32_t sv = sub_of(nodes, n, ent.x);
+        const bool is_ext = (r.y >> 31) && ent.y == r.x + (r.y & 0x7fffffffu) - 1u;               // the PS.cpp:401 slot: directed, no mirror image
+        const bool mir = !is_ext && ent.x > nodes[row];                                         // a self loop is its own mirror image
+        if (mir) atomicAdd(&rc[sv], 1u << 14);
+        sc_ent[g].x = row | (sv << 13) | (mir ? 0x80000000u : 0u);
+      }
+      __syncwarp();
+    }
 
     // ---------------- per-row counts -> local indptr (PS.cpp:428-431) ----------------
     uint32_t m = cnt;
@@ -444,7 +473,8 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
         uint32_t c_i = 0, k_i = 0;
         if (i < n) {
           const uint32_t w = rc[i];
-          if (!ADD_SELF) c_i = w;                       // nothing is inserted: the staged stream is the CSR
+          if (!ADD_SELF && SYM) { k_i = w & 0x3fffu; c_i = k_i + (w >> 14); }      // own upper part + mirrored lower part
+          else if (!ADD_SELF) c_i = w;                  // nothing is inserted: the staged stream is the CSR
           else {
             k_i = w & 0x3fffu;
             const bool present = (w >> 28) != 0;        // the row already holds its self loop (:386-400)
@@ -456,18 +486,24 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
                 if (probe2(hb, hshift, ovl, novf, nb)) bsub = sub_of(nodes, n, nb);
               }
             }
-            rins[i] = present ? NONE32 : ((w >> 14) & 0x3fffu); rbug[i] = bsub;
-            c_i = k_i + (present ? 0u : 1u) + (bsub != NONE32 ? 1u : 0u);
+            rins[i] = present ? NONE32 : ((w >> 14) & 0x3fffu); rbug[i] = bsub;                // SYM: bits 14..27 = mirrored edges, all below v
+            c_i = k_i + (present ? 0u : 1u) + (bsub != NONE32 ? 1u : 0u) + (SYM ? ((w >> 14) & 0x3fffu) : 0u);
           }
         }
         const uint32_t x = warp_incl_scan(c_i, lane);
         if (i < n) cp[i] = carry + x - c_i;
-        carry += __shfl_sync(FULL, x, 31);
-        if (ADD_SELF) {
+        if (ADD_SELF || SYM) {
           const uint32_t y = warp_incl_scan(k_i, lane);
-          if (i < n) rlo[i] = carry_k + y - k_i;
+          if (i < n) {
+            if (SYM) {                                  // staged entry g of this row goes to rlo + g; the mirrored edges fill the row's head, rc = their cursor
+              const uint32_t mcount = (rc[i] >> 14) & 0x3fffu;
+              rlo[i] = (carry + x - c_i) + mcount + ((ADD_SELF && rins[i] != NONE32) ? 1u : 0u) - (carry_k + y - k_i);
+              rc[i] = carry + x - c_i;
+            } else rlo[i] = carry_k + y - k_i;
+          }
           carry_k += __shfl_sync(FULL, y, 31);
         }
+        carry += __shfl_sync(FULL, x, 31);
       }
       if (lane == 0) cp[n] = carry;
       m = carry;
@@ -487,7 +523,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       if (o128 < ln * 4ull + 128ull) prefetch_l2((const char *)(P.ppr_sid + off_next) + o128);
       if (o128 < ln * 4ull + 128ull) prefetch_l2((const char *)(P.ppr_sscore + off_next) + o128);
       if (o128 < ln * 2ull + 128ull) prefetch_l2((const char *)(P.ppr_srank + off_next) + o128);
-      if (o128 < ln * 8ull + 128ull) prefetch_l2((const char *)(P.ppr_srow + off_next) + o128);
+      if (o128 < ln * 8ull + 128ull) prefetch_l2((const char *)((SYM ? P.ppr_supper : P.ppr_srow) + off_next) + o128);
     }
     edge_base = __shfl_sync(FULL, edge_base, 0);
     if (edge_base + (long long)m > P.cap_edges) {
@@ -501,6 +537,36 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) P.row_span[node_base + i] = make_int2((int)(edge_base + cp[i]), (int)(edge_base + cp[i + 1]));
     // ---------------- emit ----------------
+    if (SYM) {
+#pragma unroll 1
+      for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t g = base + lane;
+        const bool act = g < cnt;
+        uint2 ent = make_uint2(0u, 0u);
+        if (act) ent = __ldcg(sc_ent + g);
+        const uint32_t row = ent.x & 0x1fffu, sv = (ent.x >> 13) & 0x1fffu;
+        const bool mir = act && (ent.x >> 31);
+        uint32_t rv = 0;
+        if (mir) rv = __ldg(P.sym_rev + ent.y);         // full-graph slot of the mirror image (v, u)
+        if (act) {                                      // the edge itself: row u, in staged (= slot) order behind the row's mirrored head
+          const long long pos = edge_base + (long long)(rlo[row] + g);
+          P.indices_out[pos] = (int)(node_base + sv); P.orig_edge[pos] = ent.y;
+        }
+        if (__any_sync(FULL, mir)) {                    // mirror images: row v; entries of one row arrive in ascending u = CSR order
+          const uint32_t peers = __match_any_sync(FULL, mir ? sv : (0x2000u + (uint32_t)lane));
+          const uint32_t rank = __popc(peers & lt);
+          uint32_t cur = 0;
+          if (mir) cur = rc[sv];
+          __syncwarp();
+          if (mir && rank == 0) rc[sv] = cur + __popc(peers);
+          __syncwarp();
+          if (mir) {
+            const long long pos = edge_base + (long long)(cur + rank);
+            P.indices_out[pos] = (int)(node_base + row); P.orig_edge[pos] = rv;
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (uint32_t g = lane; g < cnt; g += 32) {
       const uint2 ent = __ldcg(sc_ent + g);
@@ -511,6 +577,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
       }
       P.indices_out[pos] = (int)(node_base + sub_of(nodes, n, ent.x));
       P.orig_edge[pos] = ent.y;                                                                   // :422
+    }
     }
     if (ADD_SELF) {
 #pragma unroll 1

@@ -105,7 +105,12 @@ struct shadow_sampler {
   long long ppr_maxlen = 0;
   int warp_ecap_mult = 16;                 // staged edges per node of the PPR fast path (grows when launches need many redos)
   DevBuf wscratch;                         // its per-warp staging scratch
+  // symmetric-graph variant of the fast path: 0 = not checked yet, 1 = graph is symmetric with strictly ascending rows (sym_rev valid), -1 = it is not
+  int sym_state = 0;
+  bool supper_valid = false;               // ppr_supper matches the installed tables
+  DevBuf sym_rev, ppr_supper;
   long long last_redo = 0;                 // subgraphs of the last validated launch that went through the redo kernel
+  bool last_sym = false;                   // the last launch ran the symmetric (upper-triangle) variant of the fast path
   std::vector<std::vector<Result>> ring;   // [num_ring][num_ens]
   DevBuf rand_stream, rand_off, gws;
   std::vector<uint32_t> rand_host;
@@ -187,7 +192,7 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
 }
 
 // per-warp workspace of the single-root PPR fast path (ppr_warp_kernel.cuh)
-static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, int ecap_mult, WarpLayout *W, int *w_ecap, int *w_nf, int *w_hbuckets, int *w_hshift) {
+static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, bool sym, int ecap_mult, WarpLayout *W, int *w_ecap, int *w_nf, int *w_hbuckets, int *w_hshift) {
   uint32_t off = 0;
   auto take = [&](size_t bytes) { uint32_t r = off; off = align16(off + (uint32_t)bytes); return r; };
   // staged edges per warp (global scratch, L2-resident): ecap_mult (16 to start with) per node + one full stage of head room.  A subgraph
@@ -213,16 +218,16 @@ static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, int ecap_mu
   W->ovf = take((1 + WARP_OVF_CAP) * 4);
   W->bloom = take((size_t)32 * nf * 4);                      // Bloom words while they are built
   const bool ins = c.add_self_edge != 0;
-  W->rlo = take(ins ? (size_t)caps.ncap * 4 : 0);
+  W->rlo = take((ins || sym) ? (size_t)caps.ncap * 4 : 0);
   W->rins = take(ins ? (size_t)caps.ncap * 4 : 0);
   W->rbug = take(ins ? (size_t)caps.ncap * 4 : 0);
   W->bytes = off;
 }
 
 typedef void (*warp_kernel_t)(const SampleParams);
-template <bool A>
+template <bool A, bool S>
 static warp_kernel_t pick_warp_kernel(int nf) {
-  return nf == 1 ? ppr_induce_warp_kernel<A, 1> : (nf == 2 ? ppr_induce_warp_kernel<A, 2> : ppr_induce_warp_kernel<A, 4>);
+  return nf == 1 ? ppr_induce_warp_kernel<A, 1, S> : (nf == 2 ? ppr_induce_warp_kernel<A, 2, S> : ppr_induce_warp_kernel<A, 4, S>);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,7 +345,7 @@ extern "C" int shadow_sampler_destroy(shadow_sampler *s) {
   if (s->owns_graph) { cudaFree(s->indptr); if (s->indices) cudaFree(s->indices); }
   s->targets.release(); s->ppr_ptr.release(); s->ppr_neighs.release(); s->ppr_scores.release();
   s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release(); s->ppr_srow.release();
-  s->rand_stream.release(); s->rand_off.release(); s->gws.release(); s->wscratch.release();
+  s->rand_stream.release(); s->rand_off.release(); s->gws.release(); s->wscratch.release(); s->sym_rev.release(); s->ppr_supper.release();
   for (auto &slot : s->ring) for (auto &r : slot) result_release(r);
   delete s;
   return 0;
@@ -388,6 +393,7 @@ extern "C" int shadow_sampler_drop_full_graph_info(shadow_sampler *s) {      // 
   s->indices = nullptr; s->graph_dropped = true;
   s->ppr_neighs.release(); s->ppr_scores.release(); s->ppr_ptr.release(); s->has_ppr = false;
   s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release(); s->ppr_srow.release(); s->ppr_sorted = false;
+  s->sym_rev.release(); s->ppr_supper.release(); s->sym_state = 0; s->supper_valid = false;
   return 0;
 }
 
@@ -434,6 +440,7 @@ extern "C" int shadow_sampler_set_ppr_tables(shadow_sampler *s, const uint64_t *
   CUDA_TRY(cudaMemcpy(s->ppr_scores.p, scores, (size_t)tot * 4, cudaMemcpyHostToDevice));
   s->has_ppr = true;
   s->ppr_sorted = false;
+  s->supper_valid = false;
   if (!getenv("SHADOW_NO_SORTED_PPR")) {
     if (s->ppr_sid.ensure((size_t)std::max<uint64_t>(tot, 1) * 4) || s->ppr_sscore.ensure((size_t)std::max<uint64_t>(tot, 1) * 4) ||
         s->ppr_srank.ensure((size_t)std::max<uint64_t>(tot, 1) * 2) || s->ppr_srow.ensure((size_t)std::max<uint64_t>(tot, 1) * 8))
@@ -465,6 +472,74 @@ extern "C" int shadow_sampler_get_ppr_row(shadow_sampler *s, uint32_t v, uint32_
     CUDA_TRY(cudaMemcpy(scores, (float *)s->ppr_scores.p + pr[0], (size_t)c * 4, cudaMemcpyDeviceToHost));
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// symmetric-graph variant of the warp fast path: one-time check + reverse-slot index, upper part of every table entry
+// ------------------------------------------------------------------------------------------------
+// One warp per row u: every slot (u, v) must have its image (v, u) (binary search in row v; rows strictly ascending, checked here too);
+// rev[slot of (u, v)] = slot of (v, u).  *bad != 0 => the graph is not symmetric / not strictly sorted: the full-scan kernels are used.
+__global__ void __launch_bounds__(256) sym_build_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ indices, uint32_t N,
+                                                        uint32_t *__restrict__ rev, int *bad) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < N; u += wpg) {
+    if ((u & 1023u) < wpg && *(volatile int *)bad) return;          // somebody found a counter-example: stop early
+    const uint32_t s = indptr[u], e = indptr[u + 1];
+    for (uint32_t slot = s + lane; slot < e; slot += 32) {
+      const uint32_t v = indices[slot];
+      bool ok = v < N && (slot + 1 >= e || indices[slot + 1] > v);
+      if (ok) {
+        uint32_t lo = indptr[v];
+        const uint32_t end = indptr[v + 1];
+        uint32_t hi = end;
+        while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (indices[mid] < u) lo = mid + 1; else hi = mid; }
+        ok = lo < end && indices[lo] == u;
+        if (ok) rev[slot] = lo;
+      }
+      if (!ok) *bad = 1;
+    }
+  }
+}
+// upper part of the row of every entry of the id-sorted PPR tables: {first slot whose neighbour is >= id, slots from there to the row end}
+__global__ void __launch_bounds__(256) ppr_upper_kernel(const uint32_t *__restrict__ sid, const uint2 *__restrict__ srow, unsigned long long total,
+                                                        const uint32_t *__restrict__ indices, uint2 *__restrict__ supper) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t id = sid[i];
+    const uint2 r = srow[i];
+    uint32_t lo = r.x, hi = r.x + r.y;
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (indices[mid] < id) lo = mid + 1; else hi = mid; }
+    supper[i] = make_uint2(lo, r.x + r.y - lo);
+  }
+}
+// true when the symmetric variant can run: graph verified (once per graph), tables' upper parts built (once per table install)
+static bool ensure_sym(shadow_sampler *s) {
+  if (s->sym_state == 0) {
+    s->sym_state = -1;
+    if (getenv("SHADOW_NO_SYM") || s->E == 0) return false;
+    if (s->sym_rev.ensure((size_t)s->E * 4)) { cudaGetLastError(); return false; }      // no room for the index: keep the full scan
+    int *flag = nullptr;
+    if (cudaMalloc(&flag, 4) != cudaSuccess) { cudaGetLastError(); s->sym_rev.release(); return false; }
+    cudaMemsetAsync(flag, 0, 4, s->stream);
+    sym_build_kernel<<<s->num_sms * 8, 256, 0, s->stream>>>(s->indptr, s->indices, s->N, (uint32_t *)s->sym_rev.p, flag);
+    int bad = 1;
+    cudaMemcpyAsync(&bad, flag, 4, cudaMemcpyDeviceToHost, s->stream);
+    const bool okc = cudaStreamSynchronize(s->stream) == cudaSuccess;
+    cudaFree(flag);
+    if (!okc || bad) { cudaGetLastError(); s->sym_rev.release(); return false; }
+    s->sym_state = 1;
+  }
+  if (s->sym_state != 1) return false;
+  if (!s->supper_valid) {
+    if (!s->ppr_sorted) return false;
+    unsigned long long tot = 0;
+    if (cudaMemcpy(&tot, (const unsigned long long *)s->ppr_ptr.p + s->N, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (s->ppr_supper.ensure((size_t)std::max<unsigned long long>(tot, 1) * 8)) { cudaGetLastError(); return false; }
+    if (tot) ppr_upper_kernel<<<s->num_sms * 8, 256, 0, s->stream>>>((const uint32_t *)s->ppr_sid.p, (const uint2 *)s->ppr_srow.p, tot, s->indices, (uint2 *)s->ppr_supper.p);
+    if (cudaGetLastError() != cudaSuccess) return false;
+    s->supper_valid = true;
+  }
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -586,11 +661,18 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   int w_ecap = 0;
   int w_nf = 1;
   if (fast) { long long d; int rcd = graph_dmax(s, &d); if (rcd) return rcd; fast = d + 8 < (1ll << WARP_OFFBITS); }      // packed candidate codes
-  if (fast) { plan_warp(caps, c, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024; }
+  bool sym = false;
+  if (fast) {
+    sym = ensure_sym(s);
+    plan_warp(caps, c, sym, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024;
+    if (sym) { K.ppr_supper = (const uint2 *)s->ppr_supper.p; K.sym_rev = (const uint32_t *)s->sym_rev.p; }
+  }
+  s->last_sym = fast && sym;
   if (P > 0) {
     if (use_gws) sample_induce_kernel<true><<<grid, SAMPLER_BLOCK, 0, s->stream>>>(K);
     else if (fast) {
-      warp_kernel_t kern = K.add_self ? pick_warp_kernel<true>(w_nf) : pick_warp_kernel<false>(w_nf);
+      warp_kernel_t kern = sym ? (K.add_self ? pick_warp_kernel<true, true>(w_nf) : pick_warp_kernel<false, true>(w_nf))
+                               : (K.add_self ? pick_warp_kernel<true, false>(w_nf) : pick_warp_kernel<false, false>(w_nf));
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.WL.bytes));
       int wps = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wps, kern, 32, K.WL.bytes));
@@ -800,6 +882,7 @@ extern "C" int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, in
 }
 
 extern "C" int64_t shadow_sampler_last_redo_count(const shadow_sampler *s) { return s ? s->last_redo : -1; }
+extern "C" int shadow_sampler_last_sym(const shadow_sampler *s) { return s ? (s->last_sym ? 1 : 0) : -1; }
 
 // hook for ppr_push.cu
 int shadow_internal_graph(shadow_sampler *s, const uint32_t **indptr, const uint32_t **indices, uint32_t *N, uint32_t *E,

@@ -54,6 +54,10 @@ struct SampleParams {
   const float *ppr_sscore;
   const unsigned short *ppr_srank;
   const uint2 *ppr_srow;             // {indptr[id], degree(id)} of every entry of the id-sorted rows (warp fast path)
+  // symmetric-graph variant of the warp fast path (verified once per graph, sym_build_kernel): upper part {first slot with neighbour >= id,
+  // slots to the row end} of every table entry, and the reverse-slot index rev[slot of (u,v)] = slot of (v,u)
+  const uint2 *ppr_supper;
+  const uint32_t *sym_rev;
   // random streams
   const uint32_t *rand_stream;       // glibc replay: pre-generated rand() outputs
   long long *rand_off;               // [num_subg+1] stream offset of each subgraph (written by the prepass)

@@ -356,6 +356,7 @@ def test_superbatch_8192_ppr_vs_oracle(se):
     assert np.array_equal(b.target.cpu().numpy().ravel().astype(np.int64) - node_ptr[:-1], w.target.astype(np.int64))
     assert b.ppr.cpu().numpy().tobytes() == w.ppr.tobytes()
     assert s.last_redo_count() < P // 4
+    assert s.last_sym(), "powerlaw_graph is symmetric with strictly ascending rows: the upper-triangle variant should have run"
 
 
 # ------------------------------------------------------------------------------------------------ graphed trainer with real pooling segments

@@ -317,7 +317,8 @@ def _ppr_tables(indptr, indices, k, eps=1e-5):
 
 
 @pytest.mark.parametrize("env", [dict(), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_WARP_NF=2, SHADOW_WARP_BUCKET_MULT=1),
-                                 dict(SHADOW_WARP_ECAP_MULT=1, SHADOW_WARP_NF=4), dict(SHADOW_NO_WARP_PPR=1)])
+                                 dict(SHADOW_WARP_ECAP_MULT=1, SHADOW_WARP_NF=4), dict(SHADOW_NO_WARP_PPR=1), dict(SHADOW_NO_SYM=1),
+                                 dict(SHADOW_NO_SYM=1, SHADOW_WARP_ECAP_MULT=0)])
 def test_ppr_warp_path_and_redo_vs_oracle(env):
     """the fast path, its staging-overflow and bucket-overflow hand-over (redo launch of the generic kernel) and the generic
     kernel alone all reproduce the oracle bit for bit: bug-compatible and fixed mode, self edge on/off, thresholds, k=1"""
@@ -332,6 +333,32 @@ def test_ppr_warp_path_and_redo_vs_oracle(env):
                        include_target_conn="false")
             t = rng.permutation(N - 2)[:300].astype(np.uint32)
             assert _oracle_vs_cuda(indptr, indices, t, 128, 2, cfg, (), ppr_tables=tables, fixed=fixed) == 300
+
+
+def test_ppr_sym_variant_is_selected_and_directed_graphs_fall_back():
+    """the symmetric-graph variant of the fast path (upper-triangle scan + mirrored edges through the reverse-slot index) runs on graphs that
+    pass the one-time check and only there: dropping reverse edges (a directed graph) or SHADOW_NO_SYM=1 selects the full scan; all three
+    reproduce the oracle bit for bit"""
+    from shadow_gnn_b200.synth import small_parity_graph
+    PS = _product()
+    indptr, indices = small_parity_graph(3000, 20, 21, self_loops=40)
+    N = indptr.size - 1
+    rows = np.repeat(np.arange(N), np.diff(indptr.astype(np.int64)))
+    keep = ~((rows > indices) & ((rows + indices) % 7 == 0))          # drop every 7th-ish lower-triangle edge: no longer symmetric
+    ip_d = np.zeros(N + 1, np.int64); np.cumsum(np.bincount(rows[keep], minlength=N), out=ip_d[1:])
+    directed = (ip_d.astype(np.uint32), indices[keep])
+    rng = np.random.default_rng(4)
+    for (ip, ix), env, want_sym in (((indptr, indices), dict(), True), ((indptr, indices), dict(SHADOW_NO_SYM=1), False), (directed, dict(), False)):
+        tables = _ppr_tables(ip, ix, 80)
+        with _Env(**env):
+            for se, fixed in itertools.product([False, True], [False, True]):
+                cfg = dict(method="ppr", k="80", threshold="0.001", num_roots="1", add_self_edge="true" if se else "false", include_target_conn="false")
+                t = rng.permutation(N - 2)[:256].astype(np.uint32)
+                assert _oracle_vs_cuda(ip, ix, t, 128, 2, cfg, (), ppr_tables=tables, fixed=fixed) == 256
+            s = PS.ParallelSampler(ip, ix, [], 64, 1, True, True, [], 1, "", "", "", 1)
+            s.set_ppr_tables(*tables); s.shuffle_targets(t)
+            s.sample_to_device([cfg], [set()])
+            assert s.last_sym() == want_sym, (env, want_sym)
 
 
 def test_ppr_warp_redo_is_exercised():
