@@ -4,10 +4,11 @@ set -e
 cd "$(dirname "$0")/../shadow_gnn_b200"
 rm -rf variants; mkdir -p variants
 build() { name=$1; shift; OUT=../variants/lib_$name.so EXTRA="$*" PTXAS_V=1 bash csrc/build.sh 2>&1 | grep -A2 "ppr_induce_warp" | grep "Used" | head -1 | sed "s/^/$name: /"; }
-build k64u2m28 -DWARP_K=64 -DWARP_U=2 -DWARP_MIN_BLOCKS=28 &
-build k128u2m28 -DWARP_K=128 -DWARP_U=2 -DWARP_MIN_BLOCKS=28 &
-build k128u4m24 -DWARP_K=128 -DWARP_U=4 -DWARP_MIN_BLOCKS=24 &
-build k256u4m20 -DWARP_K=256 -DWARP_U=4 -DWARP_MIN_BLOCKS=20 &
-build k128u4m16 -DWARP_K=128 -DWARP_U=4 -DWARP_MIN_BLOCKS=16 &
+build u4 -DWARP_U=4 &
+build u8 -DWARP_U=8 &
+build u4m28 -DWARP_U=4 -DWARP_MIN_BLOCKS=28 &
+build u3m28 -DWARP_U=3 -DWARP_MIN_BLOCKS=28 &
+build u3db -DWARP_U=3 -DWARP_DB=1 &
+build u5 -DWARP_U=5 &
 wait
 ls -la variants

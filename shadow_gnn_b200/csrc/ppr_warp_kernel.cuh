@@ -32,6 +32,10 @@
 #ifndef WARP_U
 #define WARP_U 6               // chunk windows in flight per warp (32 chunks each)
 #endif
+#ifndef WARP_U_SYM
+#define WARP_U_SYM 4           // the same for the symmetric variant: half the slots per subgraph, shorter stages win (scripts/explore_variants.py)
+#endif
+#define WARP_U_MAX (WARP_U > WARP_U_SYM ? WARP_U : WARP_U_SYM)
 #ifndef WARP_MIN_BLOCKS
 #define WARP_MIN_BLOCKS 24     // one warp per CTA: resident warps per SM the register budget must allow
 #endif
@@ -96,17 +100,19 @@ __device__ __forceinline__ bool probe2(const uint2 *hb, const int hshift, const 
 
 #define WARP_OFFBITS 19                                // candidate code = row << 19 | (slot - row start + 3): rows < 8192, scanned length < 2^19 - 8
 #define WARP_OFFMASK ((1u << WARP_OFFBITS) - 1u)
+template <int U>
 struct ScanStage {
-  uint4 q[WARP_U];
-  uint32_t code[WARP_U];                             // code of the first slot of my chunk (WARP_OFFMASK for an idle lane: offset beyond any row)
+  uint4 q[U];
+  uint32_t code[U];                             // code of the first slot of my chunk (WARP_OFFMASK for an idle lane: offset beyond any row)
 };
 
 // The aligned 16-byte chunk that holds the last slot of the array may reach up to 12 bytes past indices[E-1]: still inside the allocation
 // (CUDA allocations are 256-byte granular and the array starts 16-byte aligned); those slots are >= E, outside every row range.
-__device__ __forceinline__ void scan_load(ScanStage &S, const uint32_t c0, const uint32_t total, int &rbase, const int n, const int lane,
+template <int U>
+__device__ __forceinline__ void scan_load(ScanStage<U> &S, const uint32_t c0, const uint32_t total, int &rbase, const int n, const int lane,
                                           const uint32_t le, const uint32_t *cp, const uint2 *rs, const uint4 *ind4) {
 #pragma unroll
-  for (int u = 0; u < WARP_U; u++) {
+  for (int u = 0; u < U; u++) {
     const uint32_t cw = c0 + 32u * u;
     S.q[u] = make_uint4(NONE32, NONE32, NONE32, NONE32);
     S.code[u] = WARP_OFFMASK;
@@ -211,6 +217,7 @@ __device__ __forceinline__ uint32_t ppr_cut(const SampleParams &P, const unsigne
   return __reduce_min_sync(0xffffffffu, cut);
 }
 
+#define PPR_COUNT_R 6          // table rows of up to 192 entries are counted from registers
 // node count (and score-rank cut) of every subgraph of the launch: |{entries with rank < cut, id != root}| + 1
 __global__ void __launch_bounds__(256) ppr_count_kernel(const SampleParams P, int *__restrict__ cnt, unsigned short *__restrict__ cut_out) {
   const int lane = threadIdx.x & 31;
@@ -219,12 +226,32 @@ __global__ void __launch_bounds__(256) ppr_count_kernel(const SampleParams P, in
     const unsigned long long off = P.ppr_ptr[t];
     const int len_all = (int)(P.ppr_ptr[t + 1] - off);
     const int size_neigh = len_all < P.k ? len_all : P.k;                                         // :576
-    const uint32_t cut = ppr_cut(P, off, len_all, size_neigh, lane);
-    uint32_t c = 0;
-    for (int base = 0; base < len_all; base += 32) {
-      const int i = base + lane;
-      const bool selp = i < len_all && P.ppr_srank[off + i] < cut && P.ppr_sid[off + i] != t;
-      c += __popc(__ballot_sync(0xffffffffu, selp));
+    uint32_t cut, c = 0;
+    if (len_all <= 32 * PPR_COUNT_R) {                   // the usual case: the whole row in registers, every load issued before the first use
+      uint32_t rk[PPR_COUNT_R], id[PPR_COUNT_R];
+      float sc[PPR_COUNT_R];
+#pragma unroll
+      for (int j = 0; j < PPR_COUNT_R; j++) {
+        const int i = 32 * j + lane;
+        rk[j] = NONE32; id[j] = t; sc[j] = 0.f;
+        if (i < len_all) { rk[j] = P.ppr_srank[off + i]; id[j] = P.ppr_sid[off + i]; sc[j] = P.ppr_sscore[off + i]; }
+      }
+      const float max_ppr = size_neigh > 1 ? P.ppr_scores[off + 1] : 0.f;                        // :578-579
+      cut = (uint32_t)size_neigh;
+#pragma unroll
+      for (int j = 0; j < PPR_COUNT_R; j++)
+        if (rk[j] < (uint32_t)size_neigh && (max_ppr == 0.f || __fdiv_rn(sc[j], max_ppr) < P.threshold)) cut = min(cut, rk[j]);
+      cut = __reduce_min_sync(0xffffffffu, cut);
+#pragma unroll
+      for (int j = 0; j < PPR_COUNT_R; j++) c += (rk[j] < cut && id[j] != t) ? 1u : 0u;
+      c = __reduce_add_sync(0xffffffffu, c);
+    } else {
+      cut = ppr_cut(P, off, len_all, size_neigh, lane);
+      for (int base = 0; base < len_all; base += 32) {
+        const int i = base + lane;
+        const bool selp = i < len_all && P.ppr_srank[off + i] < cut && P.ppr_sid[off + i] != t;
+        c += __popc(__ballot_sync(0xffffffffu, selp));
+      }
     }
     if (lane == 0) { cnt[p] = (int)c + 1; cut_out[p] = (unsigned short)cut; }
   }
@@ -342,18 +369,27 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     const int size_neigh = len_all < P.k ? len_all : P.k;                                         // :576
     uint32_t run = 0, n_below = 0;
     bool root_in = false;
+    // (the loads of round i+1 are issued before round i is consumed: the table row sits in L2, a round trip per round would be exposed)
+    const uint2 *const trow = SYM ? P.ppr_supper : P.ppr_srow;
+    uint32_t rk_n = NONE32, id_n = 0;
+    float sc_n = 0.f;
+    uint2 rw_n = make_uint2(0u, 0u);
+    if (lane < len_all) { rk_n = P.ppr_srank[off + lane]; id_n = P.ppr_sid[off + lane]; sc_n = P.ppr_sscore[off + lane]; rw_n = trow[off + lane]; }
 #pragma unroll 1
     for (int base = 0; base < len_all; base += 32) {
-      const int i = base + lane;
-      bool sel = false;
-      uint32_t id = 0;
-      if (i < len_all) { sel = P.ppr_srank[off + i] < cut; id = P.ppr_sid[off + i]; }
+      const uint32_t rk = rk_n, id = id_n;
+      const float scv = sc_n;
+      const uint2 rw = rw_n;
+      const int j = base + 32 + lane;
+      rk_n = NONE32;
+      if (j < len_all) { rk_n = P.ppr_srank[off + j]; id_n = P.ppr_sid[off + j]; sc_n = P.ppr_sscore[off + j]; rw_n = trow[off + j]; }
+      const bool sel = rk < cut;                        // NONE32 (beyond the row) never is
       const bool selp = sel && id != t;
       const uint32_t m = __ballot_sync(FULL, selp), mb = __ballot_sync(FULL, selp && id < t), mr = __ballot_sync(FULL, sel && id == t);
       if (sel) {                                        // entries below the root keep their rank, the root's slot follows them, the rest shift by one
         const uint32_t at = run + __popc(m & lt) + ((selp && id > t) ? 1u : 0u);
-        nodes[at] = id; rs[at] = SYM ? P.ppr_supper[off + i] : P.ppr_srow[off + i];
-        P.orig_node[node_base + at] = id; P.ppr_out[node_base + at] = P.ppr_sscore[off + i];
+        nodes[at] = id; rs[at] = rw;
+        P.orig_node[node_base + at] = id; P.ppr_out[node_base + at] = scv;
       }
       run += __popc(m); n_below += __popc(mb); root_in |= (mr != 0);
     }
@@ -416,10 +452,11 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     uint32_t cnt = 0, qn = 0;
     if (!bail) {
       int rbase = 0;                                    // cp[rbase] <= first chunk of the window <= cp[rbase+1]
-      const uint32_t step = 32u * WARP_U, room = 32u * (WARP_U + 1) * WARP_CS;      // what a stage can keep at most (incl. the queue's tail)
-      ScanStage SA;
+      constexpr int U = SYM ? WARP_U_SYM : WARP_U;
+      const uint32_t step = 32u * U, room = 32u * (U + 1) * WARP_CS;      // what a stage can keep at most (incl. the queue's tail)
+      ScanStage<U> SA;
 #if WARP_DB
-      ScanStage SB;
+      ScanStage<U> SB;
       scan_load(SA, 0u, total, rbase, n, lane, le, cp, rs, ind4);
 #endif
 #pragma unroll 1
@@ -430,35 +467,51 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
 #else
         scan_load(SA, c0, total, rbase, n, lane, le, cp, rs, ind4);
 #endif
-        uint32_t any[WARP_U];                           // all Bloom tests of the stage first: 4 * WARP_U independent SHFLs in flight
+        uint32_t any[U];                           // all Bloom tests of the stage first: 4 * WARP_U independent SHFLs in flight
 #pragma unroll
-        for (int u = 0; u < WARP_U; u++)
+        for (int u = 0; u < U; u++)
           any[u] = (bloom_test<NF>(f, SA.q[u].x) | bloom_test<NF>(f, SA.q[u].y) | bloom_test<NF>(f, SA.q[u].z) | bloom_test<NF>(f, SA.q[u].w)) & 1u;
 #pragma unroll
-        for (int u = 0; u < WARP_U; u++)
+        for (int u = 0; u < U; u++)
           scan_window<ADD_SELF, NF, SYM>(any[u], SA.q[u], SA.code[u], cq_keys, cq_code, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
 #if WARP_DB
 #pragma unroll
-        for (int u = 0; u < WARP_U; u++) { SA.q[u] = SB.q[u]; SA.code[u] = SB.code[u]; }
+        for (int u = 0; u < U; u++) { SA.q[u] = SB.q[u]; SA.code[u] = SB.code[u]; }
 #endif
       }
       if (!bail && qn) { __syncwarp(); drain_batch<ADD_SELF, SYM>(cq_keys, cq_code, 0u, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt); }
     }
     __syncwarp();
     if (p_next < P.num_subg) { off_next = P.ppr_ptr[t_next]; row_end_next = P.ppr_ptr[t_next + 1]; }      // consumed before the emit
+    // launch statistics for the host's choice between the full and the symmetric variant: staged edges, scanned chunks
+    if (!bail && lane == 0) { atomicAdd((unsigned long long *)&P.totals[4], (unsigned long long)cnt); atomicAdd((unsigned long long *)&P.totals[5], (unsigned long long)total); }
     if (SYM && !bail) {
       // resolve pass over the staged (upper-part) edges, all lanes busy: sub id of the neighbour, "does this edge have a mirror image",
       // mirror count of the neighbour's row (bits 14..27 of rc[]); the entry is rewritten as row | sub << 13 | mirrored << 31
+      // (two entries per lane and round: both scratch reads and both binary searches overlap)
 #pragma unroll 1
-      for (uint32_t g = lane; g < cnt; g += 32) {
-        const uint2 ent = __ldcg(sc_ent + g);
-        const uint32_t row = __ldcg(sc_row + g);
-        const uint2 r = rs[row];
-        const uint32_t sv = sub_of(nodes, n, ent.x);
-        const bool is_ext = (r.y >> 31) && ent.y == r.x + (r.y & 0x7fffffffu) - 1u;               // the PS.cpp:401 slot: directed, no mirror image
-        const bool mir = !is_ext && ent.x > nodes[row];                                         // a self loop is its own mirror image
-        if (mir) atomicAdd(&rc[sv], 1u << 14);
-        sc_ent[g].x = row | (sv << 13) | (mir ? 0x80000000u : 0u);
+      for (uint32_t g0 = lane; g0 < cnt; g0 += 64) {
+        const uint32_t g1 = g0 + 32;
+        const bool has1 = g1 < cnt;
+        const uint2 ent0 = __ldcg(sc_ent + g0);
+        const uint32_t row0 = __ldcg(sc_row + g0);
+        uint2 ent1 = ent0;
+        uint32_t row1 = row0;
+        if (has1) { ent1 = __ldcg(sc_ent + g1); row1 = __ldcg(sc_row + g1); }
+        int lo0 = 0, hi0 = n, lo1 = 0, hi1 = n;         // sub_of for both keys, interleaved
+        while (lo0 < hi0 || lo1 < hi1) {
+          if (lo0 < hi0) { const int mid = (lo0 + hi0) >> 1; if (nodes[mid] < ent0.x) lo0 = mid + 1; else hi0 = mid; }
+          if (lo1 < hi1) { const int mid = (lo1 + hi1) >> 1; if (nodes[mid] < ent1.x) lo1 = mid + 1; else hi1 = mid; }
+        }
+        const uint2 r0 = rs[row0], r1 = rs[row1];
+        const bool ext0 = (r0.y >> 31) && ent0.y == r0.x + (r0.y & 0x7fffffffu) - 1u;             // the PS.cpp:401 slot: directed, no mirror image
+        const bool ext1 = (r1.y >> 31) && ent1.y == r1.x + (r1.y & 0x7fffffffu) - 1u;
+        const bool mir0 = !ext0 && ent0.x > nodes[row0];                                        // a self loop is its own mirror image
+        const bool mir1 = has1 && !ext1 && ent1.x > nodes[row1];
+        if (mir0) { atomicAdd(&rc[lo0], 1u << 14); prefetch_l2(P.sym_rev + ent0.y); }           // the emit reads sym_rev[slot]: pull it into L2 now
+        if (mir1) { atomicAdd(&rc[lo1], 1u << 14); prefetch_l2(P.sym_rev + ent1.y); }
+        sc_ent[g0].x = row0 | ((uint32_t)lo0 << 13) | (mir0 ? 0x80000000u : 0u);
+        if (has1) sc_ent[g1].x = row1 | ((uint32_t)lo1 << 13) | (mir1 ? 0x80000000u : 0u);
       }
       __syncwarp();
     }
@@ -538,16 +591,20 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     for (int i = lane; i < n; i += 32) P.row_span[node_base + i] = make_int2((int)(edge_base + cp[i]), (int)(edge_base + cp[i + 1]));
     // ---------------- emit ----------------
     if (SYM) {
+      // (the staged entries of round i+1 and their reverse slots are requested before round i is written out)
+      uint2 ent_n = make_uint2(0u, 0u);
+      uint32_t rv_n = 0;
+      if ((uint32_t)lane < cnt) { ent_n = __ldcg(sc_ent + lane); if (ent_n.x >> 31) rv_n = __ldg(P.sym_rev + ent_n.y); }
 #pragma unroll 1
       for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t g = base + lane;
         const bool act = g < cnt;
-        uint2 ent = make_uint2(0u, 0u);
-        if (act) ent = __ldcg(sc_ent + g);
+        const uint2 ent = ent_n;
+        const uint32_t rv = rv_n;                       // full-graph slot of the mirror image (v, u)
+        ent_n = make_uint2(0u, 0u);
+        if (g + 32u < cnt) { ent_n = __ldcg(sc_ent + g + 32u); if (ent_n.x >> 31) rv_n = __ldg(P.sym_rev + ent_n.y); }
         const uint32_t row = ent.x & 0x1fffu, sv = (ent.x >> 13) & 0x1fffu;
         const bool mir = act && (ent.x >> 31);
-        uint32_t rv = 0;
-        if (mir) rv = __ldg(P.sym_rev + ent.y);         // full-graph slot of the mirror image (v, u)
         if (act) {                                      // the edge itself: row u, in staged (= slot) order behind the row's mirrored head
           const long long pos = edge_base + (long long)(rlo[row] + g);
           P.indices_out[pos] = (int)(node_base + sv); P.orig_edge[pos] = ent.y;

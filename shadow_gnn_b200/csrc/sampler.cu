@@ -75,7 +75,8 @@ struct Result {              // one ensemble branch of one call: SubgraphStructV
   bool canon_valid = false;
   long long cap_nodes = 0, cap_edges = 0;
   int cap_subg = 0;
-  long long *totals_host = nullptr;   // pinned mirror of totals[0..3] ([3] = subgraphs the warp fast path handed to the generic kernel)
+  long long *totals_host = nullptr;   // pinned mirror of totals[0..5] ([3] = subgraphs the warp fast path handed to the generic kernel, [4] / [5] = its staged edges / scanned chunks)
+  bool fast_launch = false;
   // description of the launch (for validation / re-run)
   shadow_sampler_cfg cfg;
   uint32_t idx_start = 0, idx_end = 0;
@@ -109,6 +110,10 @@ struct shadow_sampler {
   int sym_state = 0;
   bool supper_valid = false;               // ppr_supper matches the installed tables
   DevBuf sym_rev, ppr_supper;
+  // Every mirrored edge costs a sub-id search, a cursor update and a random 4-byte read of sym_rev[]: about twice a directly kept edge, while
+  // a scanned slot costs a sixth of one.  Measured break-even (S-products stand-ins, uniform vs planted partition): ~14 % of the scanned
+  // slots kept; the symmetric variant runs while the previous launch stayed below SHADOW_SYM_RATIO (default 0.12).
+  double kept_ratio = 0.0;
   long long last_redo = 0;                 // subgraphs of the last validated launch that went through the redo kernel
   bool last_sym = false;                   // the last launch ran the symmetric (upper-triangle) variant of the fast path
   std::vector<std::vector<Result>> ring;   // [num_ring][num_ens]
@@ -198,10 +203,11 @@ static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, bool sym, i
   // staged edges per warp (global scratch, L2-resident): ecap_mult (16 to start with) per node + one full stage of head room.  A subgraph
   // that overflows is not an error, it takes the redo launch; the multiplier grows when more than 2 % of a launch had to be redone
   const char *env = getenv("SHADOW_WARP_ECAP_MULT");
-  *w_ecap = (env ? std::max(0, atoi(env)) : ecap_mult) * caps.ncap + 32 * (WARP_U + 1) * WARP_CS;
+  *w_ecap = (env ? std::max(0, atoi(env)) : ecap_mult) * caps.ncap + 32 * ((sym ? WARP_U_SYM : WARP_U) + 1) * WARP_CS;
   // Bloom words per lane: 1,024 bits per word-register, 2 bits per key: ~7 bits per key keep the false-positive rate near 6 %
   const char *envf = getenv("SHADOW_WARP_NF");
-  int nf = caps.ncap <= 192 ? 1 : (caps.ncap <= 448 ? 2 : 4);
+  // (the symmetric variant scans half the slots, its exact stage weighs more: one more word per lane pays off already at k = 150)
+  int nf = caps.ncap <= (sym ? 96 : 192) ? 1 : (caps.ncap <= 448 ? 2 : 4);
   if (envf && (atoi(envf) == 1 || atoi(envf) == 2 || atoi(envf) == 4)) nf = atoi(envf);
   *w_nf = nf;
   // exact table: 2-key buckets, >= 3 buckets per key (4 KB for k = 150): 1-2 keys per subgraph overflow their bucket
@@ -218,7 +224,9 @@ static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, bool sym, i
   W->ovf = take((1 + WARP_OVF_CAP) * 4);
   W->bloom = take((size_t)32 * nf * 4);                      // Bloom words while they are built
   const bool ins = c.add_self_edge != 0;
-  W->rlo = take((ins || sym) ? (size_t)caps.ncap * 4 : 0);
+  // rlo is written after the scan, when the chunk queue is dead: it lives there when it fits (one more resident warp per SM at k = 150)
+  if ((ins || sym) && (size_t)caps.ncap * 4 <= (size_t)WARP_QCAP * 20) W->rlo = W->queue;
+  else W->rlo = take((ins || sym) ? (size_t)caps.ncap * 4 : 0);
   W->rins = take(ins ? (size_t)caps.ncap * 4 : 0);
   W->rbug = take(ins ? (size_t)caps.ncap * 4 : 0);
   W->bytes = off;
@@ -277,7 +285,7 @@ static int sampler_common_init(shadow_sampler *s, int per_batch, int num_ens, in
   s->rng.seed((uint32_t)seed);
   s->ring.assign(num_ring, std::vector<Result>(num_ens));
   for (auto &slot : s->ring)
-    for (auto &r : slot) CUDA_TRY(cudaMallocHost(&r.totals_host, 4 * sizeof(long long)));
+    for (auto &r : slot) CUDA_TRY(cudaMallocHost(&r.totals_host, 6 * sizeof(long long)));
   return 0;
 }
 
@@ -663,7 +671,8 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   if (fast) { long long d; int rcd = graph_dmax(s, &d); if (rcd) return rcd; fast = d + 8 < (1ll << WARP_OFFBITS); }      // packed candidate codes
   bool sym = false;
   if (fast) {
-    sym = ensure_sym(s);
+    const char *envr = getenv("SHADOW_SYM_RATIO");
+    sym = s->kept_ratio < (envr ? atof(envr) : 0.12) && ensure_sym(s);
     plan_warp(caps, c, sym, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024;
     if (sym) { K.ppr_supper = (const uint2 *)s->ppr_supper.p; K.sym_rev = (const uint32_t *)s->sym_rev.p; }
   }
@@ -695,7 +704,8 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     } else sample_induce_kernel<false><<<grid, SAMPLER_BLOCK, caps.L.bytes, s->stream>>>(K);
     CUDA_TRY(cudaGetLastError());
   }
-  CUDA_TRY(cudaMemcpyAsync(r.totals_host, K.totals, 4 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(r.totals_host, K.totals, 6 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+  r.fast_launch = fast && P > 0;
   r.pending = true; r.valid = false; r.rand_draws = 0; r.canon_valid = false;
   if (glibc) {                 // the host generator must advance by what this call consumed before the next call
     long long used = 0;
@@ -724,6 +734,8 @@ static int validate_branch(shadow_sampler *s, Result &r) {
     r.total_nodes = tn; r.total_edges = te; r.pending = false; r.valid = true;
     s->last_redo = r.num_subg ? (long long)(r.totals_host[3] & 0xffffffffll) : 0;
     if (s->last_redo * 50 > r.num_subg && s->warp_ecap_mult < 128) s->warp_ecap_mult *= 2;
+    // kept / scanned slots of this launch (the same for both variants: each sees half of both) steers the next launch's choice
+    if (r.fast_launch && r.num_subg >= 64 && r.totals_host[5] > 0) s->kept_ratio = (double)r.totals_host[4] / (4.0 * (double)r.totals_host[5]);
   }
   return 0;
 }
