@@ -233,3 +233,87 @@ def graph_to_device(raw_graph, device, mode_adj=None):
             cache[id(adj)] = (ip, ix)
         out[md] = cache[id(adj)]
     return out
+
+
+def standardize_torch(feats, fit_rows=None, chunk=1 << 20):
+    """`standardize` on the device that holds `feats` (float32 [N, F] tensor), in place: column mean / population variance of the fit rows
+    accumulated in float64 over row chunks, zero-variance columns only centred, transform in float32 (loader.py:104-112).  The float64
+    statistics are the ones sklearn computes; the float32 transform matches its float32-in / float32-out behaviour."""
+    import torch
+    n, dev = feats.shape[0], feats.device
+    rows = None if fit_rows is None else torch.as_tensor(np.asarray(fit_rows), device=dev).long()
+    cnt = n if rows is None else int(rows.numel())
+    s1 = torch.zeros(feats.shape[1], dtype=torch.float64, device=dev)
+    for a in range(0, cnt, chunk):
+        blk = feats[a:a + chunk] if rows is None else feats[rows[a:a + chunk]]
+        s1 += blk.double().sum(0)
+    mean = s1 / max(cnt, 1)
+    s2 = torch.zeros_like(s1)
+    for a in range(0, cnt, chunk):
+        blk = feats[a:a + chunk] if rows is None else feats[rows[a:a + chunk]]
+        d = blk.double() - mean
+        s2 += (d * d).sum(0)
+    scale = torch.sqrt(s2 / max(cnt, 1))
+    scale[scale < 10 * np.finfo(np.float64).eps] = 1.0
+    m32, s32 = mean.float(), scale.float()
+    for a in range(0, n, chunk):
+        feats[a:a + chunk] = (feats[a:a + chunk] - m32) / s32
+    return feats
+
+
+def load_data_device(prefix, dataset, config_data, device, printf=lambda txt, style=None: None):
+    """f-2, direct-to-HBM half: the files `load_data` reads (loader.py:18-121) go straight to `device` -- the raw adjacency's index arrays
+    through pinned staging, the undirected conversion (graph_utils.py:19-45) as ONE device sort/unique instead of the reference's per-row
+    Python loop, the StandardScaler on the device -- and come back in the form the device minibatch takes:
+        adjs[mode] = (indptr int32, indices int32) device tensors holding uint32 bit patterns (shared between modes when transductive),
+        feat_full float32 [N, F], label_full, node_set (host int64 arrays).
+    Same decisions as `load_data` (prestored undirected / normalised files win; transductive => one adjacency); node datasets only."""
+    import torch
+    d = f"{prefix['local']}/{dataset}"
+    for f in ("split.npy", "label_full.npy", "feat_full.npy"):
+        if not os.path.isfile(f"{d}/{f}"):
+            raise FileNotFoundError(f"{d}/{f} is missing")
+    role = np.load(f"{d}/split.npy", allow_pickle=True)
+    role = role[()] if isinstance(role, np.ndarray) else role
+    if not all(k in role for k in (TRAIN, VALID, TEST)):
+        raise NotImplementedError("link-prediction splits (edge sets) are not handled by this loader")
+    node_set = {k: np.asarray(role[k], dtype=np.int64) for k in (TRAIN, VALID, TEST)}
+    if "coalesce" in config_data and not config_data["coalesce"]:
+        raise NotImplementedError
+    dev = torch.device(device)
+    pin = dev.type == "cuda"
+
+    def up(a, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(a).astype(dtype, copy=False))
+        return (t.pin_memory() if pin else t).to(dev, non_blocking=pin)
+
+    def adj_dev(split_):
+        und = config_data["to_undirected"]
+        a = _load_adj(prefix["local"], dataset, "undirected" if und else "raw", split_)
+        if a is None and und:
+            raw = _load_adj(prefix["local"], dataset, "raw", split_)
+            if raw is None:
+                raise FileNotFoundError(f"{d}/adj_{split_}_raw.np[yz] is missing")
+            raw = raw.tocsr()
+            ip, ix = to_undirected_csr_torch(up(raw.indptr, np.int64), up(raw.indices, np.int64), device=dev)
+        elif a is None:
+            raise FileNotFoundError(f"{d}/adj_{split_}_raw.np[yz] is missing")
+        else:
+            a = a.tocsr()
+            ip, ix = up(a.indptr, np.int64), up(a.indices, np.int64).to(torch.int32)
+        assert int(ip[-1]) < 2 ** 32 and ip.numel() - 1 < 2 ** 32
+        ip32 = torch.where(ip >= 2 ** 31, ip - 2 ** 32, ip).to(torch.int32)        # uint32 bit patterns in int32 storage
+        return ip32, ix
+    full = adj_dev("full")
+    adjs = {VALID: full, TEST: full, TRAIN: full if config_data["transductive"] else adj_dev("train")}
+    mode_norm = "all" if config_data["transductive"] else "train"
+    if config_data["norm_feat"] and os.path.isfile(f"{d}/feat_full_norm_{mode_norm}.npy"):
+        feats = up(np.load(f"{d}/feat_full_norm_{mode_norm}.npy"), np.float32)
+    else:
+        feats = up(np.load(f"{d}/feat_full.npy"), np.float32)
+        if config_data["norm_feat"]:
+            standardize_torch(feats, None if config_data["transductive"] else node_set[TRAIN])
+    lab = np.load(f"{d}/label_full.npy")
+    label_full = up(lab, lab.dtype)
+    printf("Done loading training data to the device..")
+    return adjs, feats, label_full, node_set

@@ -41,6 +41,8 @@ class GraphedTrainer:
         # rows per subgraph of the loaded batch (max / mean / sum pooling segments; padding rows lie behind the last segment)
         self.sizes = torch.ones((1, self.B), dtype=torch.int64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.keep_preds = False                              # step_logged(): the captured step also leaves predict(preds) in a static buffer
+        self.preds = None
         self.graph = None
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -71,6 +73,12 @@ class GraphedTrainer:
         if handle is not None:
             handle.remove()
         loss = m._loss(preds, self.label)
+        if self.keep_preds:
+            with torch.no_grad():
+                p = m.predict(preds.detach())
+                if self.preds is None:
+                    self.preds = torch.zeros_like(p)
+                self.preds.copy_(p)
         loss.backward()
         if exchange:
             opt = m.optimizer
@@ -136,7 +144,20 @@ class GraphedTrainer:
         torch.sub(target, lo, out=self.target)
         return True
 
-    def step(self):
+    def step_logged(self):
+        """`step` for the trainer shell (main.one_epoch): the dict `DeepGNN.step` returns (models.py:209-237 of the reference) -- loss, labels
+        and predictions are device tensors (copies of the captured step's static buffers), nothing synchronises"""
+        if not self.keep_preds:
+            self.keep_preds, self.graph = True, None         # (re)capture with the prediction buffer
+        out = self.step(_full=True)
+        if isinstance(out, dict):                            # eager fallback batch
+            return out
+        lab = self.label
+        if lab.dim() == 1 and self.model.num_classes > 1:
+            lab = F.one_hot(lab.to(torch.int64), num_classes=self.model.num_classes)
+        return {"batch_size": self.B, "loss": self.loss.clone(), "labels": lab.clone(), "preds": self.preds.clone(), "emb_ens": None}
+
+    def step(self, _full=False):
         """one training step on the next batch of the epoch; returns the loss (a device scalar, no sync)"""
         mb, mode = self.mb, self.mode
         bs = mb._get_cur_batch_size(mode)
@@ -158,4 +179,5 @@ class GraphedTrainer:
                 return self.loss
             sb.cursor = cursor                               # did not fit: hand the batch to the eager path
         self.eager_steps += 1
-        return self.model.step(mode, "running", mb.one_batch(mode))["loss"].detach()
+        out = self.model.step(mode, "running", mb.one_batch(mode))
+        return out if _full else out["loss"].detach()
