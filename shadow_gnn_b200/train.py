@@ -20,7 +20,6 @@ from .parallel import allreduce_flat_gradients, allreduce_two_buckets, join_buck
 
 class GraphedTrainer:
     def __init__(self, model, minibatch, row_cap, edge_cap, mode=TRAIN):
-        assert minibatch.num_ensemble == 1 and not minibatch.aug_feats, "the graphed step covers the single-branch, no-augmentation path"
         assert minibatch.prediction_task == "node", "link prediction (two targets per subgraph) runs through the eager DeepGNN.step"
         pools = {rp.type_pool for rp in model.res_pool_layers}
         assert "sort" not in pools, "sort pooling has data-dependent shapes (repeat_interleave): use the eager DeepGNN.step"
@@ -30,16 +29,21 @@ class GraphedTrainer:
         self.B = minibatch._cfg_ensemble["batch_size"]
         dev, Fd = minibatch.dev_torch, minibatch.feat_full.shape[1]
         self.row_cap, self.edge_cap = int(row_cap), int(edge_cap)
-        self.rowptr = torch.zeros(self.row_cap + 1, dtype=torch.int32, device=dev)
-        self.span = torch.zeros((self.row_cap, 2), dtype=torch.int32, device=dev)
-        self.col = torch.zeros(self.edge_cap, dtype=torch.int32, device=dev)
-        self.val = torch.zeros(self.edge_cap, dtype=torch.float32, device=dev)
-        self.feat = torch.zeros((self.row_cap, Fd), dtype=torch.float32, device=dev)
-        self.target = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        # one set of static buffers per ensemble branch (subgraph ensemble, shaDow/layers.py:236-296); feature-augmentation one-hots
+        # (hops / pprs / drnls, shaDow/minibatch.py:469-477) get static buffers of their own
+        self.E = E = minibatch.num_ensemble
+        self.rowptr = [torch.zeros(self.row_cap + 1, dtype=torch.int32, device=dev) for _ in range(E)]
+        self.span = [torch.zeros((self.row_cap, 2), dtype=torch.int32, device=dev) for _ in range(E)]
+        self.col = [torch.zeros(self.edge_cap, dtype=torch.int32, device=dev) for _ in range(E)]
+        self.val = [torch.zeros(self.edge_cap, dtype=torch.float32, device=dev) for _ in range(E)]
+        self.feat = [torch.zeros((self.row_cap, Fd), dtype=torch.float32, device=dev) for _ in range(E)]
+        self.target = [torch.zeros(self.B, dtype=torch.int64, device=dev) for _ in range(E)]
+        self.aug = [{k: torch.zeros((self.row_cap, minibatch.get_aug_dim(k)), dtype=torch.float32, device=dev)
+                     for k in sorted(set(minibatch.aug_feats) & {"hops", "pprs", "drnls"})} for _ in range(E)]
         lf = minibatch.label_full
         self.label = torch.zeros((self.B,) + tuple(lf.shape[1:]), dtype=lf.dtype, device=dev)      # class ids [B] or multi-hot rows [B, C]
         # rows per subgraph of the loaded batch (max / mean / sum pooling segments; padding rows lie behind the last segment)
-        self.sizes = torch.ones((1, self.B), dtype=torch.int64, device=dev)
+        self.sizes = torch.ones((E, self.B), dtype=torch.int64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.keep_preds = False                              # step_logged(): the captured step also leaves predict(preds) in a static buffer
         self.preds = None
@@ -61,7 +65,7 @@ class GraphedTrainer:
     # ------------------------------------------------------------------
     def _fwd_bwd(self, exchange=False):
         m = self.model
-        adj = DeviceCSR(self.span, self.col, 0, self.val, row_ord=self.rowptr)
+        adjs = [DeviceCSR(self.span[i], self.col[i], 0, self.val[i], row_ord=self.rowptr[i]) for i in range(self.E)]
         handle = None
         if exchange and self._split > 0:
             opt = m.optimizer
@@ -69,7 +73,7 @@ class GraphedTrainer:
             def fire(module, inputs, output):                # the split layer's OUTPUT gradient exists <=> every later layer's backward is done
                 output[0].register_hook(lambda g: allreduce_two_buckets(opt.grad, self._split, self._side))
             handle = self._split_prev.register_forward_hook(fire)
-        preds, _ = m(self.mode, [self.feat], [adj], [self.target], self.sizes, [{}], m.dropedge)
+        preds, _ = m(self.mode, list(self.feat), adjs, list(self.target), self.sizes, self.aug, m.dropedge)
         if handle is not None:
             handle.remove()
         loss = m._loss(preds, self.label)
@@ -92,7 +96,7 @@ class GraphedTrainer:
         """tail bucket = conv layers [L - L//2 ..) + pooling + classifier (about the second half of the parameters, whose gradients are
         complete after the first ~half of the backward pass)"""
         convs = list(self.model.conv_layers[0])
-        if len(convs) < 2:
+        if len(convs) < 2 or self.E > 1:                     # several branches run their backward passes one after the other: one exchange at the end
             return
         k = len(convs) - max(1, len(convs) // 2)             # first layer of the tail bucket
         first = next(iter(convs[k].parameters()), None)
@@ -127,21 +131,24 @@ class GraphedTrainer:
                 opt.step(1.0 / self.world)
         # SHADOW_DP_GRAPH=0: the gradient all-reduce sits between the captured fwd/bwd and the (eager, 4-launch) optimizer step
 
-    def _load_static(self, sb, bs):
+    def _load_static(self, sb, bs, i=0):
         a = sb.cursor
         rowptr, indices, lo, e0, feat, target = sb.take_canonical(bs)
         n, e = rowptr.numel() - 1, indices.numel()
         if n > self.row_cap or e > self.edge_cap:
             return False
         if self._needs_sizes:
-            self.sizes.copy_(torch.from_numpy(np.diff(sb.node_ptr_host[a:a + bs + 1])).view(1, -1))
-        torch.sub(rowptr, e0, out=self.rowptr[:n + 1])
-        self.rowptr[n + 1:] = e                              # padding rows: empty
-        self.span[:, 0] = self.rowptr[:-1]
-        self.span[:, 1] = self.rowptr[1:]
-        torch.sub(indices, lo, out=self.col[:e])
-        self.feat[:n].copy_(feat)
-        torch.sub(target, lo, out=self.target)
+            self.sizes[i].copy_(torch.from_numpy(np.diff(sb.node_ptr_host[a:a + bs + 1])))
+        rp = self.rowptr[i]
+        torch.sub(rowptr, e0, out=rp[:n + 1])
+        rp[n + 1:] = e                                       # padding rows: empty
+        self.span[i][:, 0] = rp[:-1]
+        self.span[i][:, 1] = rp[1:]
+        torch.sub(indices, lo, out=self.col[i][:e])
+        self.feat[i][:n].copy_(feat)
+        for k, buf in self.aug[i].items():                   # padding rows keep stale one-hots: nothing reads their outputs
+            buf[:n].copy_(sb.aug[k][lo:lo + n])
+        torch.sub(target, lo, out=self.target[i])
         return True
 
     def step_logged(self):
@@ -163,10 +170,10 @@ class GraphedTrainer:
         bs = mb._get_cur_batch_size(mode)
         a = mb.idx_entity_evaluated[mode]
         label = mb.label_epoch[mode][a:a + bs]
-        sb = mb._front(mode, 0, bs)
+        sbs = [mb._front(mode, i, bs) for i in range(self.E)]
         if bs == self.B:
-            cursor = sb.cursor
-            if self._load_static(sb, bs):
+            cursors = [sb.cursor for sb in sbs]
+            if all(self._load_static(sb, bs, i) for i, sb in enumerate(sbs)):
                 self.label.copy_(label)
                 mb._update_batch_stat(mode, bs)
                 if self.graph is None:
@@ -177,7 +184,8 @@ class GraphedTrainer:
                     opt.step(allreduce_flat_gradients(opt.grad))
                 self.graph_steps += 1
                 return self.loss
-            sb.cursor = cursor                               # did not fit: hand the batch to the eager path
+            for sb, c in zip(sbs, cursors):                  # did not fit: hand the batch to the eager path
+                sb.cursor = c
         self.eager_steps += 1
         out = self.model.step(mode, "running", mb.one_batch(mode))
         return out if _full else out["loss"].detach()

@@ -395,3 +395,46 @@ def test_graphed_trainer_pooling_matches_eager(pooling):
         assert abs(a - b) <= 1e-3 * max(abs(a), 1e-3) + 1e-5, (res[0][0], res[1][0])
     for a, b in zip(res[0][1], res[1][1]):
         close(a, b.cpu(), f"parameters after one epoch ({pooling} pooling): graphed vs eager")
+
+
+@pytest.mark.parametrize("case", ["hops", "two_branches"])
+def test_graphed_trainer_aug_and_ensemble_match_eager(case):
+    """the whole-step CUDA graph with feature augmentation (every arxiv config: `feature_augment: hops`) and with two ensemble branches
+    (EnsembleAggregator, shaDow/layers.py:236-296) trains exactly like the eager DeepGNN.step"""
+    from shadow_gnn_b200 import minibatch as MB
+    from shadow_gnn_b200.models import DeepGNN
+    from shadow_gnn_b200.train import GraphedTrainer
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(2000, 12, 9)
+    N = indptr.size - 1
+    torch.manual_seed(0)
+    label = torch.randint(0, 4, (N,))
+    feat = torch.randn(N, 16)
+    train = np.arange(0, 256, dtype=np.int64)
+    if case == "hops":
+        cfg = {"batch_size": 32, "configs": [{"method": "khop", "depth": [2], "budget": [5]}]}
+        aug, E, aggr = {"hops"}, 1, "gcn"
+    else:
+        cfg = {"batch_size": 32, "configs": [{"method": "ppr", "k": [20], "threshold": [0.0], "epsilon": [1e-4]}, {"method": "khop", "depth": [1], "budget": [8]}]}
+        aug, E, aggr = set(), 2, "sage"
+    arch = dict(num_layers=2, num_cls_layers=1, heads=1, branch_sharing=False, dim=32, act="relu", layer_norm="norm_feat", feature_augment_ops="sum",
+                aggr=aggr, residue="sum", pooling="center", loss="softmax", ensemble_act="leakyrelu")
+    res = []
+    for graphed in (False, True):
+        torch.manual_seed(1); np.random.seed(1)
+        mb = MB.MinibatchShallowExtractor("toy", None, {m: (indptr, indices) for m in range(3)}, {0: train, 1: train[:64], 2: train[:64]}, cfg, aug, None,
+                                          feat, label, 16, True, 1, seed_cpp=1, num_subg_per_batch=128)
+        augs = [(k, mb.get_aug_dim(k)) for k in sorted(aug)]
+        model = DeepGNN(16, 16, 4, 0, arch, augs, E, dict(dropout=0.0, dropedge=0.0, lr=0.01, ensemble_dropout="none"), "node").cuda()
+        mb.epoch_start_reset(0, MB.TRAIN); mb.shuffle_entity(MB.TRAIN)
+        tr = GraphedTrainer(model, mb, row_cap=32 * 40, edge_cap=32 * 40 * 24) if graphed else None
+        losses = []
+        while not mb.is_end_epoch(MB.TRAIN):
+            losses.append(float(tr.step()) if graphed else float(model.step(MB.TRAIN, "running", mb.one_batch(MB.TRAIN))["loss"].detach()))
+        if graphed:
+            assert tr.graph_steps == 8 and tr.eager_steps == 0
+        res.append((losses, [p.detach().clone() for p in model.parameters()]))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert abs(a - b) <= 1e-3 * max(abs(a), 1e-3) + 1e-5, (res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        close(a, b.cpu(), f"parameters after one epoch ({case}): graphed vs eager")
