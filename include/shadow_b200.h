@@ -149,6 +149,11 @@ int64_t shadow_sampler_last_redo_count(const shadow_sampler *s);
  * graph only the upper part of every row is scanned and each kept edge also yields its mirror image through a reverse-slot index built by
  * the same check.  Results are bit-identical to the full scan; SHADOW_NO_SYM=1 in the environment keeps the full scan. */
 int shadow_sampler_last_sym(const shadow_sampler *s);
+/* diagnostics: duration (ms, CUDA events on the sampler's stream) of ppr_induce_warp_kernel alone in the last fast-path launch, without
+ * its helper launches (count, scan, redo); waits for that kernel; -1 when no fast-path launch has run */
+float shadow_sampler_last_kernel_ms(shadow_sampler *s);
+/* the same for all GPU work of that launch: state reset, ppr_count_kernel, scan_counts_kernel, the main kernel, the redo launch */
+float shadow_sampler_last_sequence_ms(shadow_sampler *s);
 /* device pointer + count of 4-byte elements of one field of the latest batch (valid until num_ring further calls) */
 int shadow_sampler_batch_field_dev(shadow_sampler *s, int branch, int field, void **ptr_dev, int64_t *count);
 /* copy one field to the host; 4 bytes per element */

@@ -297,6 +297,14 @@ class ParallelSampler:
         """True when the last call ran the symmetric-graph (upper-triangle scan + mirror) variant of the PPR fast path (diagnostics)"""
         return bool(lib.shadow_sampler_last_sym(self._h) == 1)
 
+    def last_sequence_ms(self):
+        """GPU time of all work of the last fast-path call: state reset, count, scan, main kernel, redo launch"""
+        return float(lib.shadow_sampler_last_sequence_ms(self._h))
+
+    def last_kernel_ms(self):
+        """duration of the fast path's main kernel alone in the last call (CUDA events inside the library; waits for the kernel)"""
+        return float(lib.shadow_sampler_last_kernel_ms(self._h))
+
     def set_stream(self, cuda_stream):
         """pin the sampler to one stream (default: whatever torch's current stream is at each call)"""
         self._user_stream = True

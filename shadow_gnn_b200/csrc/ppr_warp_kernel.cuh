@@ -257,52 +257,43 @@ __global__ void __launch_bounds__(256) ppr_count_kernel(const SampleParams P, in
   }
 }
 
-// exclusive prefix sum of cnt[0..P) into out[0..P] (one block; P is a few 10^4), total also to *total.  Thread i owns the contiguous
-// items [i*ipt, (i+1)*ipt), ipt a multiple of 4: all loads of a thread are issued as 16-byte vectors before the first add.
-#define SCAN_MAX_IPT 64
+// exclusive prefix sum of cnt[0..P) into out[0..P] (one block; P is 10^4 .. 10^5), total also to *total.  The array is walked in tiles of
+// 1024 x 16 items: thread i owns 16 contiguous items of the tile (four 16-byte loads issued before the first add), one block scan per tile,
+// the running total carries over.  cnt must be 16-byte aligned (the launcher pads P to a multiple of 4 ints in front of it).
+#define SCAN_IPT 16
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int *__restrict__ cnt, const int P, int *__restrict__ out, long long *total) {
   __shared__ uint32_t sums[1024];
   __shared__ uint32_t warp_sums[33];
-  const int ipt = ((P + 1023) / 1024 + 3) & ~3, b = threadIdx.x * ipt;
-  uint32_t s = 0;
-  if (ipt <= SCAN_MAX_IPT) {
-    int4 v[SCAN_MAX_IPT / 4];
+  uint32_t carry = 0;
+  for (int t0 = 0; t0 < P; t0 += 1024 * SCAN_IPT) {
+    const int b = t0 + threadIdx.x * SCAN_IPT;
+    int4 v[SCAN_IPT / 4];
+    uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < SCAN_MAX_IPT / 4; j++) {
+    for (int j = 0; j < SCAN_IPT / 4; j++) {
       v[j] = make_int4(0, 0, 0, 0);
       const int i = b + 4 * j;
-      if (4 * j < ipt && i < P) {
-        if (i + 3 < P) v[j] = *reinterpret_cast<const int4 *>(cnt + i);
-        else { v[j].x = cnt[i]; if (i + 1 < P) v[j].y = cnt[i + 1]; if (i + 2 < P) v[j].z = cnt[i + 2]; }
-      }
+      if (i + 3 < P) v[j] = *reinterpret_cast<const int4 *>(cnt + i);
+      else if (i < P) { v[j].x = cnt[i]; if (i + 1 < P) v[j].y = cnt[i + 1]; if (i + 2 < P) v[j].z = cnt[i + 2]; }
     }
 #pragma unroll
-    for (int j = 0; j < SCAN_MAX_IPT / 4; j++) s += (uint32_t)(v[j].x + v[j].y + v[j].z + v[j].w);
+    for (int j = 0; j < SCAN_IPT / 4; j++) s += (uint32_t)(v[j].x + v[j].y + v[j].z + v[j].w);
     sums[threadIdx.x] = s;
     __syncthreads();
     const uint32_t tot = block_exclusive_scan(sums, 1024, warp_sums);
-    uint32_t run = sums[threadIdx.x];
+    uint32_t run = carry + sums[threadIdx.x];
 #pragma unroll
-    for (int j = 0; j < SCAN_MAX_IPT / 4; j++) {
+    for (int j = 0; j < SCAN_IPT / 4; j++) {
       const int i = b + 4 * j;
-      if (4 * j < ipt && i < P) {
-        const int4 o = make_int4((int)run, (int)run + v[j].x, (int)run + v[j].x + v[j].y, (int)run + v[j].x + v[j].y + v[j].z);
-        if (i + 3 < P) *reinterpret_cast<int4 *>(out + i) = o;
-        else { out[i] = o.x; if (i + 1 < P) out[i + 1] = o.y; if (i + 2 < P) out[i + 2] = o.z; }
-        run += (uint32_t)(v[j].x + v[j].y + v[j].z + v[j].w);
-      }
+      const int4 o = make_int4((int)run, (int)run + v[j].x, (int)run + v[j].x + v[j].y, (int)run + v[j].x + v[j].y + v[j].z);
+      if (i + 3 < P) *reinterpret_cast<int4 *>(out + i) = o;
+      else if (i < P) { out[i] = o.x; if (i + 1 < P) out[i + 1] = o.y; if (i + 2 < P) out[i + 2] = o.z; }
+      run += (uint32_t)(v[j].x + v[j].y + v[j].z + v[j].w);
     }
-    if (threadIdx.x == 0) { out[P] = (int)tot; *total = (long long)tot; }
-  } else {                                              // very large launches: plain loops
-    const int e = min(P, b + ipt);
-    for (int i = b; i < e; i++) s += (uint32_t)cnt[i];
-    sums[threadIdx.x] = s;
-    __syncthreads();
-    const uint32_t tot = block_exclusive_scan(sums, 1024, warp_sums);
-    uint32_t run = sums[threadIdx.x];
-    for (int i = b; i < e; i++) { out[i] = (int)run; run += (uint32_t)cnt[i]; }
-    if (threadIdx.x == 0) { out[P] = (int)tot; *total = (long long)tot; }
+    carry += tot;
+    __syncthreads();                                    // sums[] / warp_sums[] are reused by the next tile
   }
+  if (threadIdx.x == 0) { out[P] = (int)carry; *total = (long long)carry; }
 }
 
 // NF = Bloom words per lane (1: ncap <= 192, 2: <= 448, 4 above)

@@ -86,6 +86,8 @@ struct Result {              // one ensemble branch of one call: SubgraphStructV
   uint32_t philox_epoch = 0;
 };
 
+struct KernCfg { const void *f; int threads; size_t smem; int bps; };
+
 struct shadow_sampler {
   int device = 0, num_sms = 0;
   cudaStream_t stream = nullptr;
@@ -116,12 +118,29 @@ struct shadow_sampler {
   double kept_ratio = 0.0;
   long long last_redo = 0;                 // subgraphs of the last validated launch that went through the redo kernel
   bool last_sym = false;                   // the last launch ran the symmetric (upper-triangle) variant of the fast path
+  cudaEvent_t kev0 = nullptr, kev1 = nullptr;   // around the last fast-path main kernel (diagnostics: shadow_sampler_last_kernel_ms)
+  cudaEvent_t sev0 = nullptr, sev1 = nullptr;   // around all GPU work of that launch (reset, count, scan, main kernel, redo)
+  bool kev_valid = false;
+  std::vector<KernCfg> kcache;
   std::vector<std::vector<Result>> ring;   // [num_ring][num_ens]
   DevBuf rand_stream, rand_off, gws;
   std::vector<uint32_t> rand_host;
 };
 
 static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// cudaFuncSetAttribute(max dynamic shared memory) + resident blocks per SM of a kernel, asked once per (kernel, block size, bytes): both are
+// host-side driver calls of several microseconds, and a sampler launch is a handful of short kernels the GPU would otherwise wait between
+static int kern_cfg(std::vector<KernCfg> &cache, const void *f, int threads, size_t smem, int *bps) {
+  for (const KernCfg &c : cache)
+    if (c.f == f && c.threads == threads && c.smem == smem) { if (bps) *bps = c.bps; return 0; }
+  CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int b = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, f, threads, smem));
+  cache.push_back(KernCfg{f, threads, smem, b});
+  if (bps) *bps = b;
+  return 0;
+}
 
 struct Caps { int ncap, ccap, ccap2, acap, acap2, hcap, hshift, ecap; WsLayout L; long long max_draws; };
 
@@ -355,6 +374,7 @@ extern "C" int shadow_sampler_destroy(shadow_sampler *s) {
   s->ppr_sid.release(); s->ppr_sscore.release(); s->ppr_srank.release(); s->ppr_srow.release();
   s->rand_stream.release(); s->rand_off.release(); s->gws.release(); s->wscratch.release(); s->sym_rev.release(); s->ppr_supper.release();
   for (auto &slot : s->ring) for (auto &r : slot) result_release(r);
+  if (s->kev0) { cudaEventDestroy(s->kev0); cudaEventDestroy(s->kev1); cudaEventDestroy(s->sev0); cudaEventDestroy(s->sev1); }
   delete s;
   return 0;
 }
@@ -628,9 +648,8 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     if (s->gws.ensure((size_t)K.gws_stride * grid)) FAIL(SHADOW_ECUDA, "cudaMalloc(global workspace) failed");
     K.gws = (unsigned char *)s->gws.p;
   } else {
-    CUDA_TRY(cudaFuncSetAttribute(sample_induce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)caps.L.bytes));
     int bps = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sample_induce_kernel<false>, SAMPLER_BLOCK, caps.L.bytes));
+    rc = kern_cfg(s->kcache, (const void *)sample_induce_kernel<false>, SAMPLER_BLOCK, caps.L.bytes, &bps); if (rc) return rc;
     grid = std::min(P, std::max(1, bps) * s->num_sms);
   }
 
@@ -645,6 +664,36 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     if (s->rand_stream.ensure((size_t)std::max<long long>(need, 1) * 4) || s->rand_off.ensure(((size_t)P + 1) * 8)) FAIL(SHADOW_ECUDA, "cudaMalloc(rand stream) failed");
     CUDA_TRY(cudaMemcpyAsync(s->rand_stream.p, s->rand_host.data(), (size_t)need * 4, cudaMemcpyHostToDevice, s->stream));
     K.rand_stream = (const uint32_t *)s->rand_stream.p; K.rand_off = (long long *)s->rand_off.p;
+  }
+  // single-root PPR without hop/drnl labels: one warp per subgraph (ppr_warp_kernel.cuh); whatever does not fit its on-chip
+  // staging is rebuilt by the generic kernel in redo mode, launched right behind (it exits at once when the list is empty)
+  bool fast = c.method == SHADOW_PPR && c.num_roots == 1 && s->ppr_sorted && !(c.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) && !use_gws &&
+              (((uintptr_t)s->indices & 15) == 0) && caps.ncap <= 8191 && !getenv("SHADOW_NO_WARP_PPR");
+  int w_ecap = 0;
+  int w_nf = 1;
+  if (fast) { long long d; int rcd = graph_dmax(s, &d); if (rcd) return rcd; fast = d + 8 < (1ll << WARP_OFFBITS); }      // packed candidate codes
+  bool sym = false;
+  if (fast) {
+    const char *envr = getenv("SHADOW_SYM_RATIO");
+    sym = s->kept_ratio < (envr ? atof(envr) : 0.12) && ensure_sym(s);
+    plan_warp(caps, c, sym, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024;
+    if (sym) { K.ppr_supper = (const uint2 *)s->ppr_supper.p; K.sym_rev = (const uint32_t *)s->sym_rev.p; }
+  }
+  s->last_sym = fast && sym;
+  warp_kernel_t kern = nullptr;
+  int gridw = 0;
+  if (fast && P > 0) {                                  // every host-side query happens BEFORE the first GPU operation of the launch
+    kern = sym ? (K.add_self ? pick_warp_kernel<true, true>(w_nf) : pick_warp_kernel<false, true>(w_nf))
+               : (K.add_self ? pick_warp_kernel<true, false>(w_nf) : pick_warp_kernel<false, false>(w_nf));
+    int wps = 0;
+    rc = kern_cfg(s->kcache, (const void *)kern, 32, K.WL.bytes, &wps); if (rc) return rc;
+    rc = kern_cfg(s->kcache, (const void *)sample_induce_kernel<false, true>, SAMPLER_BLOCK, caps.L.bytes, nullptr); if (rc) return rc;
+    gridw = std::min(P, std::max(1, wps) * s->num_sms);
+    K.w_scratch_stride = ((unsigned long long)w_ecap * 10ull + 255ull) & ~255ull;
+    if (s->wscratch.ensure((size_t)K.w_scratch_stride * gridw)) FAIL(SHADOW_ECUDA, "cudaMalloc(warp scratch) failed");
+    K.w_scratch = (unsigned char *)s->wscratch.p;
+    if (!s->kev0) { CUDA_TRY(cudaEventCreate(&s->kev0)); CUDA_TRY(cudaEventCreate(&s->kev1)); CUDA_TRY(cudaEventCreate(&s->sev0)); CUDA_TRY(cudaEventCreate(&s->sev1)); }
+    CUDA_TRY(cudaEventRecord(s->sev0, s->stream));
   }
   CUDA_TRY(cudaMemsetAsync(sync, 0, 64 + (size_t)P * 8, s->stream));
   if (glibc_st) {
@@ -662,33 +711,9 @@ static int launch_branch(shadow_sampler *s, Result &r) {
     }
     CUDA_TRY(cudaGetLastError());
   }
-  // single-root PPR without hop/drnl labels: one warp per subgraph (ppr_warp_kernel.cuh); whatever does not fit its on-chip
-  // staging is rebuilt by the generic kernel in redo mode, launched right behind (it exits at once when the list is empty)
-  bool fast = c.method == SHADOW_PPR && c.num_roots == 1 && s->ppr_sorted && !(c.aug & (SHADOW_AUG_HOPS | SHADOW_AUG_DRNLS)) && !use_gws &&
-              (((uintptr_t)s->indices & 15) == 0) && caps.ncap <= 8191 && !getenv("SHADOW_NO_WARP_PPR");
-  int w_ecap = 0;
-  int w_nf = 1;
-  if (fast) { long long d; int rcd = graph_dmax(s, &d); if (rcd) return rcd; fast = d + 8 < (1ll << WARP_OFFBITS); }      // packed candidate codes
-  bool sym = false;
-  if (fast) {
-    const char *envr = getenv("SHADOW_SYM_RATIO");
-    sym = s->kept_ratio < (envr ? atof(envr) : 0.12) && ensure_sym(s);
-    plan_warp(caps, c, sym, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024;
-    if (sym) { K.ppr_supper = (const uint2 *)s->ppr_supper.p; K.sym_rev = (const uint32_t *)s->sym_rev.p; }
-  }
-  s->last_sym = fast && sym;
   if (P > 0) {
     if (use_gws) sample_induce_kernel<true><<<grid, SAMPLER_BLOCK, 0, s->stream>>>(K);
     else if (fast) {
-      warp_kernel_t kern = sym ? (K.add_self ? pick_warp_kernel<true, true>(w_nf) : pick_warp_kernel<false, true>(w_nf))
-                               : (K.add_self ? pick_warp_kernel<true, false>(w_nf) : pick_warp_kernel<false, false>(w_nf));
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.WL.bytes));
-      int wps = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wps, kern, 32, K.WL.bytes));
-      const int gridw = std::min(P, std::max(1, wps) * s->num_sms);
-      K.w_scratch_stride = ((unsigned long long)w_ecap * 10ull + 255ull) & ~255ull;
-      if (s->wscratch.ensure((size_t)K.w_scratch_stride * gridw)) FAIL(SHADOW_ECUDA, "cudaMalloc(warp scratch) failed");
-      K.w_scratch = (unsigned char *)s->wscratch.p;
       K.redo_list = (int *)r.redo.p;
       const size_t P4 = ((size_t)P + 3) & ~(size_t)3;      // keeps the count array 16-byte aligned for scan_counts_kernel
       int *cnt = (int *)r.redo.p + P4;
@@ -697,10 +722,13 @@ static int launch_branch(shadow_sampler *s, Result &r) {
       ppr_count_kernel<<<(P + 7) / 8, 256, 0, s->stream>>>(K, cnt, (unsigned short *)K.w_cut);
       scan_counts_kernel<<<1, 1024, 0, s->stream>>>(cnt, P, K.node_ptr, K.totals);
       CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(s->kev0, s->stream));
       kern<<<gridw, 32, K.WL.bytes, s->stream>>>(K);
       CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaFuncSetAttribute(sample_induce_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)caps.L.bytes));
+      CUDA_TRY(cudaEventRecord(s->kev1, s->stream));
+      s->kev_valid = true;
       sample_induce_kernel<false, true><<<std::min(P, 2 * s->num_sms), SAMPLER_BLOCK, caps.L.bytes, s->stream>>>(K);
+      CUDA_TRY(cudaEventRecord(s->sev1, s->stream));
     } else sample_induce_kernel<false><<<grid, SAMPLER_BLOCK, caps.L.bytes, s->stream>>>(K);
     CUDA_TRY(cudaGetLastError());
   }
@@ -895,6 +923,18 @@ extern "C" int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, in
 
 extern "C" int64_t shadow_sampler_last_redo_count(const shadow_sampler *s) { return s ? s->last_redo : -1; }
 extern "C" int shadow_sampler_last_sym(const shadow_sampler *s) { return s ? (s->last_sym ? 1 : 0) : -1; }
+extern "C" float shadow_sampler_last_sequence_ms(shadow_sampler *s) {
+  if (!s || !s->kev_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaSetDevice(s->device) != cudaSuccess || cudaEventSynchronize(s->sev1) != cudaSuccess || cudaEventElapsedTime(&ms, s->sev0, s->sev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+  return ms;
+}
+extern "C" float shadow_sampler_last_kernel_ms(shadow_sampler *s) {
+  if (!s || !s->kev_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaSetDevice(s->device) != cudaSuccess || cudaEventSynchronize(s->kev1) != cudaSuccess || cudaEventElapsedTime(&ms, s->kev0, s->kev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+  return ms;
+}
 
 // hook for ppr_push.cu
 int shadow_internal_graph(shadow_sampler *s, const uint32_t **indptr, const uint32_t **indices, uint32_t *N, uint32_t *E,
