@@ -448,7 +448,10 @@ def sampler_phase(ctx, steps, warmup):
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("units_per_launch"):      # ncu capture of one launch of `units_per_launch` subgraphs, scaled to this run's average launch
-            traffic = int(tj.get("ppr_induce_warp_kernel_dram_bytes_per_launch") * units / tj["units_per_launch"])
+            if s.last_sym():
+                traffic = int(tj.get("ppr_induce_warp_kernel_dram_bytes_per_launch") * units / tj["units_per_launch"])
+            elif tj.get("units_per_launch_full_scan"):
+                traffic = int(tj.get("ppr_induce_warp_kernel_full_scan_dram_bytes_per_launch") * units / tj["units_per_launch_full_scan"])
     return dict(
         value=n_all / (ms_all * 1e-3), unit="subgraphs/s", ms_per_step=ms_all / steps, steps=steps, superbatch=P, per_gpu_targets=int(roots_host.size),
         avg_nodes_per_subgraph=avg_n, avg_edges_per_subgraph=avg_e, ppr_push_setup_s=t_ppr, gpu_launches=5 * steps,

@@ -415,6 +415,47 @@ def _linear_dgrad_pair(dZ0, w0, dZ1, w1):
     return _linear_dgrad(dZ0, w0), _linear_dgrad(dZ1, w1)
 
 
+# ---- weight gradients off the critical path ----
+# W.grad of a layer is needed by nobody until the backward pass is over (optimizer / gradient exchange), while its input gradient is what
+# the next node of the backward pass waits for.  The weight-gradient launches therefore go to a side stream that forks from the current
+# stream where dZ exists and joins it again (a) when the autograd engine finishes the pass (queue_callback) and (b) wherever gradients are
+# read earlier (the in-graph gradient exchange).  One wave of 76 CTAs each: wgrad and dgrad / SpMM^T / act-norm backward share the 148 SMs.
+# Inside a CUDA-graph capture the fork / join become graph edges.  SHADOW_WGRAD_OVERLAP=0 keeps everything on one stream.
+_WG_OVERLAP = os.environ.get("SHADOW_WGRAD_OVERLAP", "1") != "0"
+_WG_SIDE = {}                  # device index -> [side stream, tensors kept alive until the join, pending]
+
+
+def join_wgrad():
+    """make the current stream wait for every weight-gradient launch issued so far (no-op when none is pending)"""
+    for st in _WG_SIDE.values():
+        if st[2]:
+            torch.cuda.current_stream(st[0].device).wait_stream(st[0])
+            st[1].clear()
+            st[2] = False
+
+
+def _wgrad_async(fn, keep):
+    if not _WG_OVERLAP or not keep[0].is_cuda:
+        fn()
+        return
+    dev = keep[0].device
+    st = _WG_SIDE.get(dev.index)
+    if st is None:
+        st = _WG_SIDE[dev.index] = [torch.cuda.Stream(device=dev), [], False]
+    if not st[2]:
+        st[2] = True
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join_wgrad)        # end of this backward pass
+        except RuntimeError:                               # not inside a backward pass (direct call): run in line
+            st[2] = False
+            fn()
+            return
+    st[0].wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(st[0]):
+        fn()
+    st[1].extend(keep)
+
+
 def _accum_wgrad_pair(w0, dZ0, x0, w1, dZ1, x1):
     if w0.shape == w1.shape and _wgrad_tc([w0, w1], [dZ0, dZ1], [x0, x1]):
         return
@@ -565,8 +606,10 @@ class _SageLayer(torch.autograd.Function):
         else:
             dZs = _act_norm_bwd_raw(dOut, Zs, scale, offset, bs, 0, mean_s, rstd_s, act, do_norm)
             dZn = _act_norm_bwd_raw(dOut, Zn, scale, offset, bn, 1, mean_n, rstd_n, act, do_norm)
-        _accum_wgrad_pair(ws, dZs, x, wn, dZn, agg)
-        if not ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0]:
+            _wgrad_async(lambda: _accum_wgrad_pair(ws, dZs, x, wn, dZn, agg), (dZs, dZn, x, agg))
+        else:                                              # first layer: nothing left to overlap with
+            _accum_wgrad_pair(ws, dZs, x, wn, dZn, agg)
             return (None,) * 10
         r = _dgrad_tc_pair([dZs, dZn], [ws, wn]) if _LINEAR == "tc" and ws.shape == wn.shape and dZs.shape[0] > 0 else None
         dX, dAgg = r if r is not None else _linear_dgrad_pair(dZs, ws, dZn, wn)
@@ -678,7 +721,10 @@ class _GATLayer(torch.autograd.Function):
         dZs, dZn = torch.empty_like(h_self), torch.empty_like(h_self)
         check(lib.shadow_gat_pre_bwd_f32(_p(dh_self), _p(dh_neigh), _p(h_self), _p(h_neigh), _p(s_self), _p(s_neigh), _p(da_self), _p(da_neigh), _p(att.detach()),
                                          _p(dZs), _p(dZn), _p(_grad_of(att)), _p(_grad_of(b0)), _p(_grad_of(b1)), M, heads, d, act, _p(scratch), scratch.numel(), st))
-        _accum_wgrad_pair(w0, dZs, x, w1, dZn, x)
+        if ctx.needs_input_grad[0]:
+            _wgrad_async(lambda: _accum_wgrad_pair(w0, dZs, x, w1, dZn, x), (dZs, dZn, x))
+        else:
+            _accum_wgrad_pair(w0, dZs, x, w1, dZn, x)
         dX = None
         if ctx.needs_input_grad[0]:
             dX = torch.zeros((M, K), dtype=torch.float32, device=dev)

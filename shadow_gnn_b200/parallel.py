@@ -10,6 +10,11 @@ import torch
 import torch.distributed as dist
 
 
+def _join_wgrad():
+    from .ops import join_wgrad          # (ops imports the CUDA library: resolved at call time so the gloo / CPU tests can import this module)
+    join_wgrad()
+
+
 def world_info():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -36,6 +41,7 @@ def allreduce_flat_gradients(flat_grad):
     """one collective per step over the whole gradient bucket; returns the factor the optimizer has to apply (1/world)"""
     _, world = world_info()
     if world > 1:
+        _join_wgrad()
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
     return 1.0 / world
 
@@ -43,6 +49,7 @@ def allreduce_flat_gradients(flat_grad):
 def allreduce_two_buckets(flat_grad, split, side_stream):
     """inside a stream capture: the tail bucket flat_grad[split:] (the layers whose backward is already done) is reduced on `side_stream`
     while the rest of the backward pass runs on the current stream; returns nothing -- finish with `join_buckets`"""
+    _join_wgrad()                                          # weight gradients of the tail layers run on ops' side stream
     cur = torch.cuda.current_stream()
     side_stream.wait_stream(cur)
     with torch.cuda.stream(side_stream):
@@ -51,6 +58,7 @@ def allreduce_two_buckets(flat_grad, split, side_stream):
 
 def join_buckets(flat_grad, split, side_stream):
     """the head bucket on the current stream, then wait for the tail bucket"""
+    _join_wgrad()
     if split > 0:
         dist.all_reduce(flat_grad[:split], op=dist.ReduceOp.SUM)
     torch.cuda.current_stream().wait_stream(side_stream)

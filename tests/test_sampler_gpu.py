@@ -361,6 +361,21 @@ def test_ppr_sym_variant_is_selected_and_directed_graphs_fall_back():
             assert s.last_sym() == want_sym, (env, want_sym)
 
 
+def test_ppr_k400_papers_config_vs_oracle():
+    """BASELINE configs[4] sampler parameters (papers100M: k = 400, threshold 0.002; node capacity 401 > the 320 up to which the symmetric
+    variant's row offsets share the chunk queue's shared memory, 2 Bloom words per lane) against the oracle, self edge on and off"""
+    from oracle import oracle as O
+    from shadow_gnn_b200.synth import small_parity_graph
+    indptr, indices = small_parity_graph(8000, 40, 5, self_loops=50)
+    N = indptr.size - 1
+    t = np.random.default_rng(3).permutation(N - 2)[:192].astype(np.uint32)
+    nb, sc, ln = O.ppr_push(indptr, indices, t, 400, 0.85, 1e-5, 8)
+    tables = O.ppr_rows_to_csr(N, t, nb, sc, ln)
+    for se, thr in (("false", "0.002"), ("true", "0")):
+        cfg = dict(method="ppr", k="400", threshold=thr, num_roots="1", add_self_edge=se, include_target_conn="false")
+        assert _oracle_vs_cuda(indptr, indices, t, 64, 2, cfg, (), ppr_tables=tables) == 192
+
+
 def test_ppr_warp_redo_is_exercised():
     """with a staging area of just one scan stage every subgraph that needs a second stage goes through the redo launch (and still matches)"""
     from shadow_gnn_b200.synth import small_parity_graph
