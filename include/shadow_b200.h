@@ -250,6 +250,13 @@ int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, const float *Z0
                                  float *dZ0, float *dZ1, int32_t lddz, float *dscale0, float *doffset0, float *dbias0, float *dscale1,
                                  float *doffset1, float *dbias1, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
                                  int64_t scratch_floats, void *cuda_stream);
+/* the same without the final column-sum launch (two branches with norm_feat only): the caller runs shadow_colsum_finish_f32 over `scratch`
+ * (shadow_act_norm_bwd_pair_nparts(n) parts) on a stream of its own choice -- parameter gradients are off the backward pass's critical path */
+int shadow_act_norm_bwd_pair_nofinish_f32(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
+                                          const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
+                                          float *dZ0, float *dZ1, int32_t lddz, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
+                                          int64_t scratch_floats, void *cuda_stream);
+int32_t shadow_act_norm_bwd_pair_nparts(int32_t n);
 /* GAT._aggregate_attention for all heads (layers.py:560-582): a_self/a_neigh [n,heads] already through LeakyReLU(0.2) */
 int shadow_gat_fwd_f32(const int32_t *row_span, const int32_t *col, int32_t col_off, const float *val, const float *a_self,
                        const float *a_neigh, const float *H, float *out, float *rowmax, float *denom, int32_t n, int32_t heads,

@@ -52,7 +52,7 @@ SYMBOLS = [
     "shadow_sampler_sample", "shadow_sampler_batch_info", "shadow_sampler_batch_field_dev",
     "shadow_sampler_batch_field_host", "shadow_sampler_last_redo_count", "shadow_sampler_last_sym", "shadow_sampler_last_kernel_ms", "shadow_sampler_last_sequence_ms", "shadow_gather_rows_f32",
     "shadow_edge_vals_fill", "shadow_edge_vals_dropedge", "shadow_edge_vals_row_normalize", "shadow_edge_vals_sym_normalize",
-    "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32", "shadow_act_norm_bwd_pair_f32",
+    "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32", "shadow_act_norm_bwd_pair_f32", "shadow_act_norm_bwd_pair_nofinish_f32", "shadow_act_norm_bwd_pair_nparts",
     "shadow_gat_fwd_f32", "shadow_gat_bwd_f32", "shadow_segment_pool_fwd_f32", "shadow_segment_pool_bwd_f32",
     "shadow_adam_clip_step_f32", "shadow_gemm_tf32x3_f32", "shadow_gemm_tf32x3_pair_f32",
     "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32", "shadow_linear_tc_f32", "shadow_tf32_split_f32", "shadow_tf32_split_transpose_f32", "shadow_wgrad_tc_f32", "shadow_wgrad_tc_scratch_floats",
@@ -125,6 +125,9 @@ lib.shadow_gat_headnorm_fwd_f32.argtypes = [_vp] * 7 + [_i32, _i32, _i32, _i32, 
 lib.shadow_gat_headnorm_bwd_f32.argtypes = [_vp] * 10 + [_i32, _i32, _i32, _i32, _vp, _i64, _vp]
 lib.shadow_gat_pre_bwd_f32.argtypes = [_vp] * 14 + [_i32, _i32, _i32, _i32, _vp, _i64, _vp]
 lib.shadow_colsum_finish_f32.argtypes = [_vp, _i32, _i32] + [_vp] * 7
+lib.shadow_act_norm_bwd_pair_nofinish_f32.argtypes = [_vp, _i32, _vp, _vp, _i32] + [_vp] * 8 + [_i32] + [_i32, _i32, _i32, _i32, _vp, _i64, _vp]
+lib.shadow_act_norm_bwd_pair_nparts.argtypes = [_i32]
+lib.shadow_act_norm_bwd_pair_nparts.restype = _i32
 lib.shadow_wgrad_tc_scratch_floats.argtypes = [_i32, _i32, _i32]
 lib.shadow_wgrad_tc_scratch_floats.restype = _i64
 lib.shadow_wgrad_tc_f32.argtypes = [_vp] * 8 + [_i32, _i32, _i32, _vp]

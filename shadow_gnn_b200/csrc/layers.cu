@@ -784,20 +784,24 @@ extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const flo
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
-extern "C" int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
-                                            const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
-                                            float *dZ0, float *dZ1, int32_t lddz, float *dscale0, float *doffset0, float *dbias0, float *dscale1,
-                                            float *doffset1, float *dbias1, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
-                                            int64_t scratch_floats, void *stream) {
+static int anb_pair_parts(int n) {
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  return grid_for(n, WPB, 2 * sms);
+}
+extern "C" int32_t shadow_act_norm_bwd_pair_nparts(int32_t n) { return n <= 0 ? 0 : anb_pair_parts(n); }
+static int act_norm_bwd_pair_impl(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
+                                  const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
+                                  float *dZ0, float *dZ1, int32_t lddz, float *dscale0, float *doffset0, float *dbias0, float *dscale1,
+                                  float *doffset1, float *dbias1, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
+                                  int64_t scratch_floats, void *stream, bool finish) {
   if (n <= 0) return 0;
   if (D > 256) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair: D=%d exceeds 256", D);
   const int nb = Z1 ? 2 : 1;
   AnbPair A;
   A.Z[0] = Z0; A.Z[1] = Z1; A.scale[0] = scale0; A.scale[1] = scale1; A.mean[0] = mean0; A.mean[1] = mean1; A.rstd[0] = rstd0; A.rstd[1] = rstd1;
   A.dZ[0] = dZ0; A.dZ[1] = dZ1; A.dscale[0] = dscale0; A.dscale[1] = dscale1; A.doffset[0] = doffset0; A.doffset[1] = doffset1; A.dbias[0] = dbias0; A.dbias[1] = dbias1;
-  int sms = 148;
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int grid = grid_for(n, WPB, 2 * sms);
+  const int grid = anb_pair_parts(n);
   if (!scratch || scratch_floats < (int64_t)grid * nb * 3 * D) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair: scratch needs %lld floats", (long long)grid * nb * 3 * D);
   const size_t smem = (size_t)WPB * nb * 3 * D * sizeof(float);
   if ((D & 3) || (ldo & 3) || (ldz & 3) || (lddz & 3)) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair: D and the leading dimensions must be multiples of 4");
@@ -823,10 +827,29 @@ extern "C" int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, cons
 #undef LAUNCH_PAIR3
 #undef LAUNCH_PAIR4
   CUDA_TRY(cudaGetLastError());
+  if (!finish) return 0;
   const int cols = nb * 3 * D;
   colsum_finish_kernel<<<(cols + 31) / 32, 256, 0, ST(stream)>>>(scratch, grid, D, nb, A, do_norm);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+extern "C" int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
+                                            const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
+                                            float *dZ0, float *dZ1, int32_t lddz, float *dscale0, float *doffset0, float *dbias0, float *dscale1,
+                                            float *doffset1, float *dbias1, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
+                                            int64_t scratch_floats, void *stream) {
+  return act_norm_bwd_pair_impl(dOut, ldo, Z0, Z1, ldz, scale0, scale1, mean0, rstd0, mean1, rstd1, dZ0, dZ1, lddz, dscale0, doffset0, dbias0, dscale1,
+                                doffset1, dbias1, n, D, act, do_norm, scratch, scratch_floats, stream, true);
+}
+// the same without the final column-sum launch: the caller runs shadow_colsum_finish_f32 over `scratch` (shadow_act_norm_bwd_pair_nparts(n)
+// parts; two branches with norm_feat only) on a stream of its own choice -- the parameter gradients are off the backward pass's critical path
+extern "C" int shadow_act_norm_bwd_pair_nofinish_f32(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
+                                                     const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
+                                                     float *dZ0, float *dZ1, int32_t lddz, int32_t n, int32_t D, int32_t act, int32_t do_norm, float *scratch,
+                                                     int64_t scratch_floats, void *stream) {
+  if (!Z1 || !do_norm) FAIL(SHADOW_EINVAL, "act_norm_bwd_pair_nofinish: two branches with norm_feat only");
+  return act_norm_bwd_pair_impl(dOut, ldo, Z0, Z1, ldz, scale0, scale1, mean0, rstd0, mean1, rstd1, dZ0, dZ1, lddz, nullptr, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, n, D, act, do_norm, scratch, scratch_floats, stream, false);
 }
 // [parts][2][3][D] partial column sums -> dst[b][plane] += total (fixed order; NULL destinations are skipped).  Used by csrc/gat.cu.
 extern "C" int shadow_colsum_finish_f32(const float *partials, int32_t nparts, int32_t D, float *d00, float *d01, float *d02, float *d10, float *d11, float *d12,

@@ -423,6 +423,7 @@ def _linear_dgrad_pair(dZ0, w0, dZ1, w1):
 # Inside a CUDA-graph capture the fork / join become graph edges.  SHADOW_WGRAD_OVERLAP=0 keeps everything on one stream.
 _WG_OVERLAP = os.environ.get("SHADOW_WGRAD_OVERLAP", "1") != "0"
 _WG_SIDE = {}                  # device index -> [side stream, tensors kept alive until the join, pending]
+_ANB_POOL, _ANB_POOL_NEXT = {}, {}
 
 
 def join_wgrad():
@@ -432,12 +433,13 @@ def join_wgrad():
             torch.cuda.current_stream(st[0].device).wait_stream(st[0])
             st[1].clear()
             st[2] = False
+    _ANB_POOL_NEXT.clear()
 
 
 def _wgrad_async(fn, keep):
     if not _WG_OVERLAP or not keep[0].is_cuda:
         fn()
-        return
+        return False
     dev = keep[0].device
     st = _WG_SIDE.get(dev.index)
     if st is None:
@@ -449,11 +451,12 @@ def _wgrad_async(fn, keep):
         except RuntimeError:                               # not inside a backward pass (direct call): run in line
             st[2] = False
             fn()
-            return
+            return False
     st[0].wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(st[0]):
         fn()
     st[1].extend(keep)
+    return True
 
 
 def _accum_wgrad_pair(w0, dZ0, x0, w1, dZ1, x1):
@@ -508,6 +511,23 @@ def _act_norm_bwd_pair(dOut, Zs, scale, offset, biases, idxs, means, rstds, act,
     scratch = _ANB_SCRATCH[key]
     dZs = [torch.empty_like(Z) for Z in Zs]
     nb = len(Zs)
+    if nb == 2 and do_norm and _WG_OVERLAP and dOut.is_cuda and all(b is not None for b in biases):
+        # column sums (dscale / doffset / dbias) finish on the weight-gradient side stream: every call of a backward pass takes its own
+        # partial-sum buffer from a rotating pool (the next layer's kernel must not overwrite partials the side stream still reads)
+        pool = _ANB_POOL.setdefault(key, [])
+        idx = _ANB_POOL_NEXT.get(key, 0)                   # calls since the last join
+        while len(pool) <= idx:
+            pool.append(torch.empty_like(scratch))
+        part = pool[idx]
+        check(lib.shadow_act_norm_bwd_pair_nofinish_f32(_p(dOut), D, _p(Zs[0]), _p(Zs[1]), D, _p(scale.detach()[idxs[0]]), _p(scale.detach()[idxs[1]]),
+                                                        _p(means[0]), _p(rstds[0]), _p(means[1]), _p(rstds[1]), _p(dZs[0]), _p(dZs[1]), D, n, D, act, 1,
+                                                        _p(part), part.numel(), _stream(dOut)))
+        nparts = int(lib.shadow_act_norm_bwd_pair_nparts(n))
+        gs, go = _grad_of(scale), _grad_of(offset)
+        dsts = (gs[idxs[0]], go[idxs[0]], _grad_of(biases[0]), gs[idxs[1]], go[idxs[1]], _grad_of(biases[1]))
+        if _wgrad_async(lambda: check(lib.shadow_colsum_finish_f32(_p(part), nparts, D, *[_p(t) for t in dsts], _stream(part))), (part,)):
+            _ANB_POOL_NEXT[key] = idx + 1
+        return dZs
     sc = [scale.detach()[i] if do_norm else None for i in idxs]
     ds = [_grad_of(scale)[i] if do_norm else None for i in idxs]
     do = [_grad_of(offset)[i] if do_norm else None for i in idxs]
