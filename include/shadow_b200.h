@@ -164,6 +164,12 @@ int shadow_sampler_batch_field_host(shadow_sampler *s, int branch, int field, vo
 /* ---------------------------------------------------------------------------------------------- */
 int shadow_gather_rows_f32(const float *feat_dev, int64_t num_rows, int32_t dim, const uint32_t *ids_dev,
                            int64_t n, float *out_dev, void *cuda_stream);
+/* one training batch [row lo, lo+n) x [edge e0, e0+e) of a super-batch's canonical CSR -> static buffers of capacity row_cap rows (a slice in
+ * the sense of OneBatchSubgraph, shaDow/minibatch.py:428-487, rebased to row 0 / edge 0; rows >= n get empty adjacency rows): rowptr_dst
+ * int32[row_cap+1], span_dst int32[row_cap][2], col_dst int32[>= e], feat_dst float[row_cap][F] (first n rows written), tgt_dst int64[B] */
+int shadow_load_batch(const int32_t *rowptr_src, int32_t e0, int32_t n, int32_t e, int32_t row_cap, int32_t *rowptr_dst, int32_t *span_dst,
+                      const int32_t *idx_src, int32_t lo, int32_t *col_dst, const float *feat_src, int32_t F, float *feat_dst,
+                      const int32_t *tgt_src, int32_t B, int64_t *tgt_dst, void *cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* message-passing layers (shaDow/layers.py) on the RAW batch layout.  row_span = int32 pairs      */

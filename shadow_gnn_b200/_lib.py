@@ -50,7 +50,7 @@ SYMBOLS = [
     "shadow_sampler_shuffle_targets_dev", "shadow_sampler_reseed", "shadow_sampler_drop_full_graph_info",
     "shadow_sampler_set_ppr_tables", "shadow_sampler_preproc_ppr_approximate", "shadow_sampler_get_ppr_row",
     "shadow_sampler_sample", "shadow_sampler_batch_info", "shadow_sampler_batch_field_dev",
-    "shadow_sampler_batch_field_host", "shadow_sampler_last_redo_count", "shadow_sampler_last_sym", "shadow_sampler_last_kernel_ms", "shadow_sampler_last_sequence_ms", "shadow_gather_rows_f32",
+    "shadow_sampler_batch_field_host", "shadow_sampler_last_redo_count", "shadow_sampler_last_sym", "shadow_sampler_last_kernel_ms", "shadow_sampler_last_sequence_ms", "shadow_gather_rows_f32", "shadow_load_batch",
     "shadow_edge_vals_fill", "shadow_edge_vals_dropedge", "shadow_edge_vals_row_normalize", "shadow_edge_vals_sym_normalize",
     "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32", "shadow_act_norm_bwd_pair_f32", "shadow_act_norm_bwd_pair_nofinish_f32", "shadow_act_norm_bwd_pair_nparts",
     "shadow_gat_fwd_f32", "shadow_gat_bwd_f32", "shadow_segment_pool_fwd_f32", "shadow_segment_pool_bwd_f32",
@@ -97,6 +97,7 @@ lib.shadow_sampler_last_sequence_ms.argtypes = [_vp]
 lib.shadow_sampler_last_sequence_ms.restype = C.c_float
 lib.shadow_gather_rows_f32.argtypes = [_vp, _i64, C.c_int32, _vp, _i64, _vp, _vp]
 _i32 = C.c_int32
+lib.shadow_load_batch.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]
 lib.shadow_edge_vals_fill.argtypes = [_vp, _i32, _vp, _f, _vp]
 lib.shadow_edge_vals_dropedge.argtypes = [_vp, _vp, _i32, _f, _u32, _vp, _vp, _vp]
 lib.shadow_edge_vals_row_normalize.argtypes = [_vp, _i32, _i32, _vp, _vp]

@@ -205,12 +205,41 @@ static void launch_gemm(bool vec, dim3 grid, cudaStream_t st, const GemmPair &P,
   else gemm_tf32x3_kernel<TA, BKN, false><<<grid, 128, 0, st>>>(P, lda, ldb, ldc, M, N, K, kps, atomic_out);
 }
 
+// Small x W^T (+ bias): a handful of rows against a weight matrix (the 47-class classifier on the 32 pooled rows of a batch).  One tile
+// of the tensor-core kernel would walk K alone (13 us at K = 256: latency); here every output is one warp's dot product -- lanes stride
+// along K (coalesced in both operands), fixed-order shuffle reduction, plain fp32 FMA.
+__global__ void __launch_bounds__(256) small_linear_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B, int ldb, float *__restrict__ C, int ldc,
+                                                           const float *__restrict__ bias, int M, int N, int K, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)M * N;
+  for (long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); o < total; o += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int m = (int)(o / N), n = (int)(o - (long long)m * N);
+    const float *a = A + (long long)m * lda, *b = B + (long long)n * ldb;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(a[k], b[k], acc);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) {
+      float v = acc + (bias ? bias[n] : 0.f);
+      float *c = C + (long long)m * ldc + n;
+      *c = accumulate ? *c + v : v;
+    }
+  }
+}
+
 static int gemm_dispatch(const GemmPair &P, int32_t lda, int32_t trans_a, int32_t ldb, int32_t b_kn, int32_t ldc, int32_t M, int32_t N, int32_t K,
                          int32_t accumulate, int32_t split_k, void *cuda_stream) {
   for (int i = 0; i < P.nprob; i++)
     if (!P.A[i] || !P.B[i] || !P.C[i]) FAIL(SHADOW_EINVAL, "shadow_gemm_tf32x3: NULL operand");
   if (M < 0 || N < 0 || K < 0) FAIL(SHADOW_EINVAL, "shadow_gemm_tf32x3: negative dimension");
   if (M == 0 || N == 0) return 0;
+  if (P.nprob == 1 && !trans_a && !b_kn && split_k <= 1 && (long long)M * N <= 16384 && K > 0) {
+    const long long warps = (long long)M * N;
+    small_linear_kernel<<<(int)std::min<long long>((warps + 7) / 8, 4096), 256, 0, (cudaStream_t)cuda_stream>>>(P.A[0], lda, P.B[0], ldb, P.C[0], ldc, P.bias[0], M, N, K,
+                                                                                                             accumulate ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   int splits = std::max(1, split_k);
   int kps = ((K + splits - 1) / splits + GB_K - 1) / GB_K * GB_K;
   if (kps <= 0) kps = GB_K;

@@ -436,6 +436,12 @@ def join_wgrad():
     _ANB_POOL_NEXT.clear()
 
 
+def wgrad_stream(device):
+    """the side stream that currently holds un-joined weight-gradient launches of `device`, or None"""
+    st = _WG_SIDE.get(torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device())
+    return st[0] if st is not None and st[2] else None
+
+
 def _wgrad_async(fn, keep):
     if not _WG_OVERLAP or not keep[0].is_cuda:
         fn()

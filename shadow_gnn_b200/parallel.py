@@ -46,14 +46,17 @@ def allreduce_flat_gradients(flat_grad):
     return 1.0 / world
 
 
-def allreduce_two_buckets(flat_grad, split, side_stream):
-    """inside a stream capture: the tail bucket flat_grad[split:] (the layers whose backward is already done) is reduced on `side_stream`
+def allreduce_bucket(flat_grad, lo, hi, side_stream):
+    """inside a stream capture: the bucket flat_grad[lo:hi] (layers whose backward is already done) is reduced on `side_stream`
     while the rest of the backward pass runs on the current stream; returns nothing -- finish with `join_buckets`"""
-    _join_wgrad()                                          # weight gradients of the tail layers run on ops' side stream
     cur = torch.cuda.current_stream()
     side_stream.wait_stream(cur)
+    from .ops import wgrad_stream
+    ws = wgrad_stream(flat_grad.device)                    # weight gradients of the tail layers run on ops' side stream: the exchange waits
+    if ws is not None:                                     # for them there, the backward pass on the current stream does not
+        side_stream.wait_stream(ws)
     with torch.cuda.stream(side_stream):
-        dist.all_reduce(flat_grad[split:], op=dist.ReduceOp.SUM)
+        dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM)
 
 
 def join_buckets(flat_grad, split, side_stream):

@@ -14,8 +14,9 @@ import torch
 import torch.nn.functional as F
 
 from .minibatch import TRAIN
-from .ops import DeviceCSR
-from .parallel import allreduce_flat_gradients, allreduce_two_buckets, join_buckets
+from ._lib import check, lib
+from .ops import DeviceCSR, _p, _stream
+from .parallel import allreduce_flat_gradients, allreduce_bucket, join_buckets
 
 
 class GraphedTrainer:
@@ -59,23 +60,23 @@ class GraphedTrainer:
         # still in their backward pass; only the head bucket's exchange is exposed.  SHADOW_DP_GRAPH=0 keeps the exchange outside the graph.
         self.dp_in_graph = self.world > 1 and os.environ.get("SHADOW_DP_GRAPH", "1") != "0"
         self._side = None
-        self._split = 0
-        self._split_layer = None
+        self._split = 0                                      # first float of the lowest side-stream bucket (0: one exchange after the backward pass)
+        self._buckets = []                                   # [(layer whose output gradient fires the exchange, lo, hi)], hi = None: to the end
 
     # ------------------------------------------------------------------
     def _fwd_bwd(self, exchange=False):
         m = self.model
         adjs = [DeviceCSR(self.span[i], self.col[i], 0, self.val[i], row_ord=self.rowptr[i]) for i in range(self.E)]
-        handle = None
+        handles = []
         if exchange and self._split > 0:
             opt = m.optimizer
-
-            def fire(module, inputs, output):                # the split layer's OUTPUT gradient exists <=> every later layer's backward is done
-                output[0].register_hook(lambda g: allreduce_two_buckets(opt.grad, self._split, self._side))
-            handle = self._split_prev.register_forward_hook(fire)
+            for prev, lo, hi in self._buckets:
+                def fire(module, inputs, output, lo=lo, hi=hi):      # this layer's OUTPUT gradient exists <=> every later layer's backward is done
+                    output[0].register_hook(lambda g: allreduce_bucket(opt.grad, lo, hi, self._side))
+                handles.append(prev.register_forward_hook(fire))
         preds, _ = m(self.mode, list(self.feat), adjs, list(self.target), self.sizes, self.aug, m.dropedge)
-        if handle is not None:
-            handle.remove()
+        for h in handles:
+            h.remove()
         loss = m._loss(preds, self.label)
         if self.keep_preds:
             with torch.no_grad():
@@ -93,16 +94,22 @@ class GraphedTrainer:
         self.loss.copy_(loss.detach())
 
     def _plan_buckets(self, opt):
-        """tail bucket = conv layers [L - L//2 ..) + pooling + classifier (about the second half of the parameters, whose gradients are
-        complete after the first ~half of the backward pass)"""
+        """Three buckets over the layer-ordered flat gradient buffer.  A = conv layers [L - L//2 ..) + pooling + classifier: exchanged on a
+        side stream as soon as the first of those layers has finished its backward pass (about half of the pass is still to come); B = the
+        layers in between: exchanged when layer 1 is done, hidden behind layer 0's backward pass; C = layer 0 (and whatever precedes it):
+        the only exchange that is exposed, on the current stream after the pass (~0.2 MB: latency only)."""
         convs = list(self.model.conv_layers[0])
         if len(convs) < 2 or self.E > 1:                     # several branches run their backward passes one after the other: one exchange at the end
             return
-        k = len(convs) - max(1, len(convs) // 2)             # first layer of the tail bucket
-        first = next(iter(convs[k].parameters()), None)
-        if first is None or id(first) not in opt.offsets:
+        off = lambda layer: opt.offsets.get(id(next(iter(layer.parameters()), None)))
+        k = len(convs) - max(1, len(convs) // 2)             # first layer of bucket A
+        if off(convs[k]) is None:
             return
-        self._split, self._split_prev = opt.offsets[id(first)], convs[k - 1]
+        self._buckets = [(convs[k - 1], off(convs[k]), None)]
+        self._split = off(convs[k])
+        if k >= 2 and off(convs[1]) is not None and 0 < off(convs[1]) < off(convs[k]):
+            self._buckets.append((convs[0], off(convs[1]), off(convs[k])))
+            self._split = off(convs[1])
         self._side = torch.cuda.Stream()
 
     def _capture(self):
@@ -139,16 +146,11 @@ class GraphedTrainer:
             return False
         if self._needs_sizes:
             self.sizes[i].copy_(torch.from_numpy(np.diff(sb.node_ptr_host[a:a + bs + 1])))
-        rp = self.rowptr[i]
-        torch.sub(rowptr, e0, out=rp[:n + 1])
-        rp[n + 1:] = e                                       # padding rows: empty
-        self.span[i][:, 0] = rp[:-1]
-        self.span[i][:, 1] = rp[1:]
-        torch.sub(indices, lo, out=self.col[i][:e])
-        self.feat[i][:n].copy_(feat)
+        # one launch: CSR slice rebased to row 0 / edge 0, padding rows empty, feature rows copied, targets rebased (csrc/gather.cu)
+        check(lib.shadow_load_batch(_p(rowptr), e0, n, e, self.row_cap, _p(self.rowptr[i]), _p(self.span[i]), _p(indices) if e else None, lo, _p(self.col[i]),
+                                    _p(feat), feat.shape[1], _p(self.feat[i]), _p(target), target.numel(), _p(self.target[i]), _stream(feat)))
         for k, buf in self.aug[i].items():                   # padding rows keep stale one-hots: nothing reads their outputs
             buf[:n].copy_(sb.aug[k][lo:lo + n])
-        torch.sub(target, lo, out=self.target[i])
         return True
 
     def step_logged(self):
