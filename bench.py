@@ -622,7 +622,9 @@ def run_ours(args):
                         config={"workload": WORKLOAD.format(g=args.graph), "params": tr["nparams"], "global_batch": TRAIN_CFG["batch"] * world,
                                 "sampler_superbatch": tr["superbatch"], "sampler_refills_in_timed_region": tr["refills_in_timed_region"], "l2": l2,
                                 "step_execution": "eager" if args.eager else f"whole-step CUDA graph ({tr['graph_steps']} graph / {tr['eager_steps']} eager steps incl. warm-up)",
-                                "parallelism": f"dp{world}: targets partitioned, graph/PPR tables/features replicated, one NCCL all-reduce of the flat {tr['nparams'] * 4} B gradient bucket per step"})
+                                "parallelism": f"dp{world}: targets partitioned, graph/PPR tables/features replicated, one exchange of the flat {tr['nparams'] * 4} B gradient buffer per step, inside the captured step: " +
+                                               ("one-shot all-reduce over NVLink peer memory fused with the optimizer's norm pass (p2p_reduce_sqnorm_kernel)"
+                                                if os.environ.get("SHADOW_P2P", "1") != "0" and world > 1 else "NCCL all-reduce in buckets" if world > 1 else "none at 1 GPU")})
             if samp:
                 line["sampler"] = {k: samp[k] for k in ("value", "unit", "ms_per_step", "steps", "superbatch", "avg_nodes_per_subgraph", "avg_edges_per_subgraph",
                                                         "ppr_push_setup_s", "redo_last_launch", "symmetric_variant", "e2e")}
@@ -660,7 +662,11 @@ def run_ours(args):
             line["workload_clustered"] = run_clustered(ctx, args)
         print(json.dumps(line), flush=True)
     if ctx.world > 1:
-        torch.distributed.destroy_process_group()
+        # no teardown: the captured steps hold collectives / peer-mapped buffers whose destruction order across ranks is nobody's business here
+        torch.cuda.synchronize()
+        ctx.barrier()                                        # nobody unmaps its gradient buffer while a peer's last step may still read it
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

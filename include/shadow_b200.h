@@ -307,6 +307,22 @@ int shadow_segment_pool_bwd_f32(const float *dOut, const int32_t *seg, int32_t s
 int shadow_adam_clip_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float grad_scale,
                               float max_norm, float lr, float beta1, float beta2, float eps, int32_t *step_dev,
                               float *sqnorm_scratch, void *cuda_stream);
+/* Data-parallel exchange over NVLink peer memory, fused with the optimizer's norm pass (the all-reduce of the flat gradient bucket that follows
+ * loss.backward() in a DistributedDataParallel run of shaDow/models.py:209-237).  shadow_p2p_alloc: cudaMalloc'd, zeroed memory + its 64-byte
+ * CUDA IPC handle; shadow_p2p_open: a peer's allocation mapped into this process (peer access enabled lazily).  grad_ptrs / flag_ptrs: HOST
+ * arrays of `world` device pointers (index = rank; this rank's own allocations at [rank]); flags = uint32[32] per rank, zero-initialised;
+ * state = uint32[516] in local device memory, zero-initialised.  shadow_p2p_zero_grad_f32 waits until every peer has finished reading the
+ * previous step's gradients, then clears this rank's buffer; shadow_p2p_adam_clip_step_f32 = barrier + one-shot all-reduce into `gsum`
+ * (local, n floats) + squared norm, then the step of shadow_adam_clip_step_f32 on gsum (grad_scale = 1/world gives the mean).  Polls give
+ * up after ~2 s and set state[2] instead of hanging the GPU.  world <= 16. */
+int shadow_p2p_alloc(int64_t bytes, void **ptr_dev, unsigned char *handle64);
+int shadow_p2p_open(const unsigned char *handle64, void **ptr_dev);
+int shadow_p2p_close(void *ptr_dev);
+int shadow_p2p_free(void *ptr_dev);
+int shadow_p2p_zero_grad_f32(const uint64_t *grad_ptrs, const uint64_t *flag_ptrs, int32_t world, int32_t rank, int64_t n, uint32_t *state, void *cuda_stream);
+int shadow_p2p_adam_clip_step_f32(const uint64_t *grad_ptrs, const uint64_t *flag_ptrs, int32_t world, int32_t rank, float *param, float *gsum,
+                                  float *exp_avg, float *exp_avg_sq, int64_t n, float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                                  float eps, int32_t *step_dev, float *sqnorm_scratch, uint32_t *state, void *cuda_stream);
 
 #ifdef __cplusplus
 }

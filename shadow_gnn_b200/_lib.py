@@ -54,7 +54,8 @@ SYMBOLS = [
     "shadow_edge_vals_fill", "shadow_edge_vals_dropedge", "shadow_edge_vals_row_normalize", "shadow_edge_vals_sym_normalize",
     "shadow_spmm_csr_fwd_f32", "shadow_spmm_csr_bwd_f32", "shadow_act_norm_fwd_f32", "shadow_act_norm_bwd_f32", "shadow_act_norm_bwd_pair_f32", "shadow_act_norm_bwd_pair_nofinish_f32", "shadow_act_norm_bwd_pair_nparts",
     "shadow_gat_fwd_f32", "shadow_gat_bwd_f32", "shadow_segment_pool_fwd_f32", "shadow_segment_pool_bwd_f32",
-    "shadow_adam_clip_step_f32", "shadow_gemm_tf32x3_f32", "shadow_gemm_tf32x3_pair_f32",
+    "shadow_adam_clip_step_f32", "shadow_p2p_alloc", "shadow_p2p_open", "shadow_p2p_close", "shadow_p2p_free", "shadow_p2p_zero_grad_f32",
+    "shadow_p2p_adam_clip_step_f32", "shadow_gemm_tf32x3_f32", "shadow_gemm_tf32x3_pair_f32",
     "shadow_linear_umma_fwd_f32", "shadow_linear_umma_dgrad_f32", "shadow_linear_umma_wgrad_f32", "shadow_linear_tc_f32", "shadow_tf32_split_f32", "shadow_tf32_split_transpose_f32", "shadow_wgrad_tc_f32", "shadow_wgrad_tc_scratch_floats",
     "shadow_gat_supported", "shadow_gat_scratch_floats", "shadow_gat_logits_fwd_f32", "shadow_gat_agg_fwd_f32", "shadow_gat_agg_bwd_f32",
     "shadow_gat_headnorm_fwd_f32", "shadow_gat_headnorm_bwd_f32", "shadow_gat_pre_bwd_f32", "shadow_colsum_finish_f32",
@@ -145,3 +146,10 @@ def check(rc):
             raise ValueError(msg)
         raise ShadowError(f"libshadow_b200 error {rc}: {msg}")
     return rc
+
+lib.shadow_p2p_alloc.argtypes = [_i64, C.POINTER(_vp), _vp]
+lib.shadow_p2p_open.argtypes = [_vp, C.POINTER(_vp)]
+lib.shadow_p2p_close.argtypes = [_vp]
+lib.shadow_p2p_free.argtypes = [_vp]
+lib.shadow_p2p_zero_grad_f32.argtypes = [_vp, _vp, _i32, _i32, _i64, _vp, _vp]
+lib.shadow_p2p_adam_clip_step_f32.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp]

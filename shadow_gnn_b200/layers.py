@@ -302,27 +302,28 @@ class ResPool(nn.Module):
 
     def forward(self, feats_in_l, idx_targets, sizes_subg):
         idx_targets = torch.as_tensor(idx_targets, device=feats_in_l[-1].device).long()
+        # (index_select, not x[idx]: its backward is one index_add_ -- the roots of a batch are distinct rows -- instead of a sort + index_put)
         if self.type_pool == "center":
             if self.type_res == "none":
-                feat_in = feats_in_l[-1][idx_targets]
+                feat_in = feats_in_l[-1].index_select(0, idx_targets)
                 if self.prediction_task == "node":
                     return feat_in
             else:
-                feat_in = self.f_residue([f[idx_targets] for f in feats_in_l])
+                feat_in = self.f_residue([f.index_select(0, idx_targets) for f in feats_in_l])
             feat_in = self.aggr_target_emb(feat_in)
         elif self.type_pool in ("max", "mean", "sum"):
             if self.type_res == "none":
                 feat_pool = ops.segment_pool(feats_in_l[-1], sizes_subg, self.type_pool)
-                feat_root = feats_in_l[-1][idx_targets]
+                feat_root = feats_in_l[-1].index_select(0, idx_targets)
             else:
                 feat_pool = self.f_residue([ops.segment_pool(f, sizes_subg, self.type_pool) for f in feats_in_l])
-                feat_root = self.f_residue([f[idx_targets] for f in feats_in_l])
+                feat_root = self.f_residue([f.index_select(0, idx_targets) for f in feats_in_l])
             feat_in = torch.cat([self.aggr_target_emb(feat_root), feat_pool], dim=1)
         elif self.type_pool == "sort":
             if self.type_res == "none":
-                feat_pool_in, feat_root = feats_in_l[-1], feats_in_l[-1][idx_targets]
+                feat_pool_in, feat_root = feats_in_l[-1], feats_in_l[-1].index_select(0, idx_targets)
             else:
-                feat_pool_in, feat_root = self.f_residue(feats_in_l), self.f_residue([f[idx_targets] for f in feats_in_l])
+                feat_pool_in, feat_root = self.f_residue(feats_in_l), self.f_residue([f.index_select(0, idx_targets) for f in feats_in_l])
             feat_pool = self.nn_pool(_sort_pool(feat_pool_in, sizes_subg, self.k))
             feat_in = torch.cat([self.aggr_target_emb(feat_root), feat_pool], dim=1)
         else:

@@ -136,7 +136,9 @@ class DeepGNN(nn.Module):
             loss = self._loss(preds, label_targets)
             loss.backward()
             # one NCCL all-reduce of the flat gradient bucket; the clip then sees the averaged gradient
-            opt.step(grad_scale=allreduce_flat_gradients(opt.grad))
+            # the exchange: fused into the optimizer over NVLink peer memory (ops._P2PGrad), else one NCCL all-reduce of the flat bucket;
+            # either way the clip sees the averaged gradient
+            opt.step(grad_scale=1.0 if opt.p2p is not None else allreduce_flat_gradients(opt.grad))
         else:
             self.eval()
             with torch.no_grad():

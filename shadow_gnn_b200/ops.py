@@ -799,6 +799,55 @@ def segment_pool(X, sizes_subg, mode):
     return _SegPool.apply(X, seg, 0, {"sum": 0, "mean": 1, "max": 2}[mode])
 
 
+class _RawDev:
+    """zero-copy torch view of device memory owned by the library (`__cuda_array_interface__`)"""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class _P2PGrad:
+    """The flat gradient buffer of one rank in IPC-shareable device memory + every peer's buffer opened in this process (NVLink peer access),
+    for the fused exchange of csrc/layers.cu (p2p_reduce_sqnorm_kernel / p2p_wait_zero_kernel).  Handles travel through torch.distributed."""
+
+    def __init__(self, n, dev):
+        import torch.distributed as dist
+        self.world, self.rank, self.n = dist.get_world_size(), dist.get_rank(), n
+        own = []
+        for nbytes in (n * 4, 256):                          # gradient buffer, flag array
+            ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+            if lib.shadow_p2p_alloc(nbytes, C.byref(ptr), h) != 0:
+                own = None
+                break
+            own.append((ptr.value, bytes(h)))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, None if own is None else (own[0][1], own[1][1]))      # every rank gets here whatever happened above
+        if any(e is None for e in everyone):
+            raise RuntimeError("shadow_p2p_alloc failed on some rank")
+        self._own, self._opened = own, []
+        gp, fp = [], []
+        for r, (hg, hf) in enumerate(everyone):
+            if r == self.rank:
+                gp.append(own[0][0]); fp.append(own[1][0])
+                continue
+            ptrs = []
+            for h in (hg, hf):
+                ptr = C.c_void_p()
+                check(lib.shadow_p2p_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(ptr)))
+                ptrs.append(ptr.value)
+                self._opened.append(ptr.value)
+            gp.append(ptrs[0]); fp.append(ptrs[1])
+        self.grad_ptrs = (C.c_uint64 * self.world)(*gp)
+        self.flag_ptrs = (C.c_uint64 * self.world)(*fp)
+        self.grad = torch.as_tensor(_RawDev(own[0][0], n, "<f4"), device=dev)
+        self.state = torch.zeros(516, dtype=torch.int32, device=dev)
+        # (the caller's all-reduce of the success flags is the barrier: nobody launches the exchange before every peer has opened every buffer)
+
+    def error(self):
+        """True when a poll of the exchange gave up waiting for a peer (the results of that step are garbage)"""
+        return bool(int(self.state[2]))
+
+
 class FlatAdamClip:
     """clip_grad_norm_(params, max_norm) + torch.optim.Adam.step (models.py:223-224) as one fused pass over a flat fp32 buffer.
     Parameters and gradients of the module are re-pointed into two flat buffers: the gradient buffer is also what the
@@ -810,7 +859,23 @@ class FlatAdamClip:
         # every parameter starts on a 16-byte boundary (TMA descriptors of csrc/linear_tc.cu); the padding floats stay 0 in all four buffers
         n = sum((p.numel() + 3) // 4 * 4 for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        # data-parallel run on GPUs: the gradient buffer is shared with the peers over NVLink and the exchange is fused into step()
+        # (SHADOW_P2P=0: a local buffer, the caller all-reduces it with NCCL -- parallel.allreduce_flat_gradients / GraphedTrainer buckets)
+        import torch.distributed as dist
+        self.p2p = None
+        if dev.type == "cuda" and dist.is_available() and dist.is_initialized() and 1 < dist.get_world_size() <= 16 and \
+                os.environ.get("SHADOW_P2P", "1") != "0":
+            try:
+                self.p2p = _P2PGrad(n, dev)
+            except Exception as e:                           # no peer access / IPC on this box: every rank must fall back together
+                self.p2p, self._p2p_error = None, repr(e)
+            ok = torch.tensor([1 if self.p2p is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                self.p2p = None
+            else:
+                self.gsum = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = self.p2p.grad if self.p2p is not None else torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         self.offsets = {}                                    # id(parameter) -> first float of the parameter in the flat buffers
         for p in self.params:
@@ -828,9 +893,22 @@ class FlatAdamClip:
         self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
 
     def zero_grad(self):
-        self.grad.zero_()
+        if self.p2p is not None:                            # peers may still be reading the previous step's gradients
+            p = self.p2p
+            check(lib.shadow_p2p_zero_grad_f32(p.grad_ptrs, p.flag_ptrs, p.world, p.rank, self.grad.numel(), _p(p.state), _stream(self.grad)))
+        else:
+            self.grad.zero_()
 
     def step(self, grad_scale=1.0):
+        if self.p2p is not None:                            # barrier + one-shot all-reduce over peer memory + norm, then Adam on the sum
+            p = self.p2p
+            join_wgrad()
+            check(lib.shadow_p2p_adam_clip_step_f32(p.grad_ptrs, p.flag_ptrs, p.world, p.rank, _p(self.flat), _p(self.gsum), _p(self.exp_avg),
+                                                    _p(self.exp_avg_sq), self.flat.numel(), 1.0 / p.world, self.max_norm, self.lr, self.betas[0],
+                                                    self.betas[1], self.eps, _p(self.step_dev), _p(self.sqnorm), _p(p.state), _stream(self.flat)))
+            if self.planes is not None:
+                self.planes.refresh()
+            return
         check(lib.shadow_adam_clip_step_f32(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.flat.numel(), grad_scale,
                                             self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps, _p(self.step_dev), _p(self.sqnorm),
                                             _stream(self.flat)))

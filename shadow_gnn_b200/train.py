@@ -59,6 +59,7 @@ class GraphedTrainer:
         # classifier) is all-reduced on a side stream as soon as the layer's input gradient exists, i.e. while the earlier layers are
         # still in their backward pass; only the head bucket's exchange is exposed.  SHADOW_DP_GRAPH=0 keeps the exchange outside the graph.
         self.dp_in_graph = self.world > 1 and os.environ.get("SHADOW_DP_GRAPH", "1") != "0"
+        self.p2p = False                                     # set at capture time: the optimizer exchanges over peer memory, no NCCL buckets
         self._side = None
         self._split = 0                                      # first float of the lowest side-stream bucket (0: one exchange after the backward pass)
         self._buckets = []                                   # [(layer whose output gradient fires the exchange, lo, hi)], hi = None: to the end
@@ -85,7 +86,7 @@ class GraphedTrainer:
                     self.preds = torch.zeros_like(p)
                 self.preds.copy_(p)
         loss.backward()
-        if exchange:
+        if exchange and not self.p2p:
             opt = m.optimizer
             if self._split > 0:
                 join_buckets(opt.grad, self._split, self._side)
@@ -125,14 +126,17 @@ class GraphedTrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         opt.zero_grad()
-        if self.dp_in_graph:
+        self.p2p = opt.p2p is not None
+        if self.p2p:
+            self.dp_in_graph = True                          # the exchange is part of opt.step(): always inside the captured step
+        elif self.dp_in_graph:
             self._plan_buckets(opt)
             torch.distributed.all_reduce(torch.zeros(8, device=opt.grad.device))      # the communicator exists before the capture starts
             torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         # thread_local: NCCL's watchdog thread may touch the CUDA API while this thread captures
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            opt.grad.zero_()
+            opt.zero_grad()
             self._fwd_bwd(exchange=self.dp_in_graph)
             if self.world == 1 or self.dp_in_graph:
                 opt.step(1.0 / self.world)
