@@ -60,8 +60,8 @@ def worker():
 def main():
     vdir = os.path.join(ROOT, "shadow_gnn_b200", "variants")
     libs = [None] + sorted(os.path.join(vdir, f) for f in os.listdir(vdir) if f.endswith(".so")) if os.path.isdir(vdir) else [None]
-    knobs_default = json.loads(os.environ.get("EXPLORE_KNOBS_ALL", '[{}, {"SHADOW_WARP_NF": 2}, {"SHADOW_WARP_BUCKET_MULT": 1}]'))
-    jobs = [(None, 65536, knobs_default + [{"SHADOW_NO_SYM": 1}])] + [(lib, 65536, knobs_default) for lib in libs if lib]
+    knobs_default = json.loads(os.environ.get("EXPLORE_KNOBS_ALL", '[{}, {"SHADOW_WARP_NF": 1}]'))
+    jobs = [(None, 65536, knobs_default)] + [(lib, 65536, knobs_default) for lib in libs if lib]
     for lib, P_, kn in jobs:
         env = dict(os.environ)
         env["EXPLORE_WORKER"] = "1"
