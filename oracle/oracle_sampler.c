@@ -10,7 +10,7 @@
  * Parity status: PINNED.  The reference ships no tests or golden vectors of its own
  * (SURVEY.md 4.1), so this restatement is pinned against the reference itself: the unmodified
  * reference sources are compiled into oracle/_ref/ (oracle/Makefile) and compared bit-for-bit with
- * this file by tests/test_oracle_vs_ref.py (when /root/reference is present) and through the
+ * this file by tests/test_oracle.py (when oracle/_ref has been built, i.e. where /root/reference is present) and through the
  * committed fixtures under tests/golden/ (generated from oracle/_ref by tests/golden/make_golden.py).
  *
  * Abbreviations for citations: PS.cpp = backend/ParallelSampler.cpp, PS.h = backend/ParallelSampler.h,
