@@ -250,7 +250,7 @@ int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const float *Z, int3
                             const float *rstd, float *dZ, int32_t lddz, float *dscale, float *doffset, float *dbias, int32_t n,
                             int32_t D, int32_t act, int32_t do_norm, void *cuda_stream);   /* dscale/doffset/dbias (column sums of dZ, may be NULL) are ACCUMULATED */
 /* the same backward for one or two branches that share dOut (GraphSAGE: out = norm0(act(Z0)) + norm1(act(Z1)), layers.py:474-483; Z1 NULL = one
- * branch).  Column sums are reduced in two deterministic stages through `scratch` (>= 2 * SMs * branches * 3 * D floats): no atomics. D <= 256. */
+ * branch).  Column sums are reduced in two deterministic stages through `scratch` (>= shadow_act_norm_bwd_pair_nparts(n) * branches * 3 * D floats; 2 CTAs per SM by default): no atomics. D <= 256. */
 int shadow_act_norm_bwd_pair_f32(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,
                                  const float *scale1, const float *mean0, const float *rstd0, const float *mean1, const float *rstd1,
                                  float *dZ0, float *dZ1, int32_t lddz, float *dscale0, float *doffset0, float *dbias0, float *dscale1,

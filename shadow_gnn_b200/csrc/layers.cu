@@ -787,7 +787,9 @@ extern "C" int shadow_act_norm_bwd_f32(const float *dOut, int32_t ldo, const flo
 static int anb_pair_parts(int n) {
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  return grid_for(n, WPB, 2 * sms);
+  // CTAs (= partial column sums) per SM: the sums are finished off the critical path (side stream), so what counts is the row loop's latency
+  static const int mult = getenv("SHADOW_ANB_PAIR_MULT") ? std::min(8, std::max(1, atoi(getenv("SHADOW_ANB_PAIR_MULT")))) : 2;
+  return grid_for(n, WPB, mult * sms);
 }
 extern "C" int32_t shadow_act_norm_bwd_pair_nparts(int32_t n) { return n <= 0 ? 0 : anb_pair_parts(n); }
 static int act_norm_bwd_pair_impl(const float *dOut, int32_t ldo, const float *Z0, const float *Z1, int32_t ldz, const float *scale0,

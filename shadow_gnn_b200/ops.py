@@ -513,7 +513,7 @@ def _act_norm_bwd_pair(dOut, Zs, scale, offset, biases, idxs, means, rstds, act,
     key = (dev.index, D)
     if key not in _ANB_SCRATCH:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        _ANB_SCRATCH[key] = torch.empty(2 * sms * 2 * 3 * D, dtype=torch.float32, device=dev)
+        _ANB_SCRATCH[key] = torch.empty(8 * sms * 2 * 3 * D, dtype=torch.float32, device=dev)      # up to 8 CTAs per SM (SHADOW_ANB_PAIR_MULT)
     scratch = _ANB_SCRATCH[key]
     dZs = [torch.empty_like(Z) for Z in Zs]
     nb = len(Zs)
