@@ -217,6 +217,54 @@ __device__ __forceinline__ uint32_t ppr_cut(const SampleParams &P, const unsigne
   return __reduce_min_sync(0xffffffffu, cut);
 }
 
+// Hop labels (compute_hops, G.cpp:32-64): level-synchronous BFS from the root over the subgraph's OWN rows, as just written (inserted self
+// loops and PS.cpp:401 extras included), by the warp that built it.  The frontier's rows are flattened: 32 frontier nodes at a time, a warp
+// scan of their row lengths, then lane k takes edge k of the concatenation (owner found by a 5-step bisection over the lanes' prefix
+// values), so the root's ~140-edge row and a frontier of 140 two-edge rows both keep all lanes busy.  Distances are unique, so the
+// result does not depend on the order in which a level claims its nodes.  Unreachable nodes keep 0xFFFFFFFF like the generic kernel.
+__device__ __forceinline__ void warp_bfs_hops(const uint32_t *cp, const int *idx, const long long node_base, const int n, const uint32_t src, uint32_t *dist,
+                                              uint32_t *cur, uint32_t *nxt, uint32_t *cnt, const int lane) {
+  const uint32_t FULL = 0xffffffffu;
+  for (int i = lane; i < n; i += 32) dist[i] = NONE32;
+  if (lane == 0) *cnt = 0u;
+  __syncwarp();
+  if (lane == 0) { dist[src] = 0u; cur[0] = src; }
+  __syncwarp();
+  uint32_t ncur = 1;
+#pragma unroll 1
+  for (uint32_t lvl = 0; ncur > 0; lvl++) {
+#pragma unroll 1
+    for (uint32_t base = 0; base < ncur; base += 32) {
+      const uint32_t i = base + (uint32_t)lane;
+      uint32_t s = 0, len = 0;
+      if (i < ncur) { const uint32_t u = cur[i]; s = cp[u]; len = cp[u + 1] - s; }
+      const uint32_t incl = warp_incl_scan(len, lane), excl = incl - len;
+      const uint32_t tot = __shfl_sync(FULL, incl, 31);
+#pragma unroll 1
+      for (uint32_t kb = 0; kb < tot; kb += 32) {
+        const uint32_t k = kb + (uint32_t)lane;
+        int j = 0;                                      // largest lane whose exclusive prefix is <= k: the owner of edge k
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const uint32_t e = __shfl_sync(FULL, excl, (j + d) & 31);
+          if (j + d < 32 && e <= k) j += d;
+        }
+        const uint32_t sj = __shfl_sync(FULL, s, j), ej = __shfl_sync(FULL, excl, j);
+        if (k < tot) {
+          const uint32_t c = (uint32_t)((long long)__ldcg(idx + sj + (k - ej)) - node_base);
+          if (atomicCAS(&dist[c], NONE32, lvl + 1u) == NONE32) nxt[atomicAdd(cnt, 1u)] = c;
+        }
+      }
+    }
+    __syncwarp();
+    ncur = *cnt;
+    __syncwarp();
+    if (lane == 0) *cnt = 0u;
+    uint32_t *t = cur; cur = nxt; nxt = t;
+    __syncwarp();
+  }
+}
+
 #define PPR_COUNT_R 6          // table rows of up to 192 entries are counted from registers
 // node count (and score-rank cut) of every subgraph of the launch: |{entries with rank < cut, id != root}| + 1
 __global__ void __launch_bounds__(256) ppr_count_kernel(const SampleParams P, int *__restrict__ cnt, unsigned short *__restrict__ cut_out) {
@@ -639,6 +687,15 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
           P.indices_out[pos] = (int)(node_base + rbug[r]); P.orig_edge[pos] = rs[r].x + rs[r].y;
         }
       }
+    }
+    if (P.aug & SHADOW_AUG_HOPS) {                      // PS.cpp:433-436; rs[] / nodes[] / the overflow list are dead by now
+      __syncwarp();                                     // the warp's own stores to indices_out are ordered before its reads
+      const uint32_t tl = sub_of(nodes, n, t);
+      uint32_t *const dist = reinterpret_cast<uint32_t *>(rs);
+      __syncwarp();
+      warp_bfs_hops(cp, P.indices_out + edge_base, (long long)node_base, n, tl, dist, dist + n, nodes, ovf, lane);
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) P.hop[node_base + i] = dist[i];
     }
     } while (0);
     p = p_next; t = t_next; node_base = node_base_next; cut = cut_next; off = off_next; row_end = row_end_next;

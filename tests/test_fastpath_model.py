@@ -274,3 +274,49 @@ def test_sym_check_rejects_directed_and_unsorted_graphs():
     ind3[s] = (int(ind3[s]) + 1) if (s + 1 >= e or int(ind3[s]) + 1 < int(ind3[s + 1])) else int(ind3[s])
     if not np.array_equal(ind3, indices):                         # one endpoint changed: its reverse edge is missing
         assert build_rev(indptr, ind3) is None
+
+
+def _warp_bfs_model(indptr, indices, n, src):
+    """lane-level restatement of warp_bfs_hops (ppr_warp_kernel.cuh): 32 frontier nodes at a time, prefix of their row lengths, lane k takes
+    edge k of the concatenation, owner = largest lane whose exclusive prefix is <= k (5-step bisection)"""
+    dist = [NONE] * n
+    dist[src] = 0
+    cur, lvl = [src], 0
+    while cur:
+        nxt = []
+        for base in range(0, len(cur), 32):
+            s = [0] * 32; ln = [0] * 32
+            for lane in range(32):
+                if base + lane < len(cur):
+                    u = cur[base + lane]; s[lane] = int(indptr[u]); ln[lane] = int(indptr[u + 1]) - s[lane]
+            incl = list(np.cumsum(ln)); excl = [incl[i] - ln[i] for i in range(32)]
+            tot = incl[31]
+            for kb in range(0, tot, 32):
+                for lane in range(32):
+                    k = kb + lane
+                    j = 0
+                    for d in (16, 8, 4, 2, 1):
+                        if j + d < 32 and excl[(j + d) & 31] <= k: j += d
+                    if k < tot:
+                        assert excl[j] <= k < incl[j], (k, j, excl, incl)
+                        c = int(indices[s[j] + (k - excl[j])])
+                        if dist[c] == NONE:
+                            dist[c] = lvl + 1; nxt.append(c)
+        cur, lvl = nxt, lvl + 1
+    return dist
+
+
+def test_warp_bfs_model_matches_plain_bfs():
+    from collections import deque
+    rng = np.random.default_rng(5)
+    for n, avg in ((1, 0), (40, 1.5), (151, 2.0), (151, 20.0), (400, 3.0)):
+        deg = rng.poisson(avg, n) if avg else np.zeros(n, int)
+        deg[0] = min(n, 140)                                       # the root's long row
+        indptr = np.concatenate([[0], np.cumsum(deg)])
+        indices = rng.integers(0, n, int(indptr[-1]))
+        want = [NONE] * n; want[0] = 0; q = deque([0])
+        while q:
+            u = q.popleft()
+            for c in indices[indptr[u]:indptr[u + 1]]:
+                if want[c] == NONE: want[c] = want[u] + 1; q.append(int(c))
+        assert _warp_bfs_model(indptr, indices, n, 0) == want, (n, avg)

@@ -361,6 +361,30 @@ def test_ppr_sym_variant_is_selected_and_directed_graphs_fall_back():
             assert s.last_sym() == want_sym, (env, want_sym)
 
 
+@pytest.mark.parametrize("env", [dict(), dict(SHADOW_NO_SYM=1), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_NO_WARP_PPR=1)])
+def test_ppr_with_hop_labels_on_the_fast_path_vs_oracle(env):
+    """`feature_augment: hops` with a PPR sampler (46 of the reference's 61 configs): the one-warp fast path labels hops with a warp-level BFS
+    (both scan variants, the redo hand-over, and the generic kernel for comparison) -- every array incl. `hop` equals the oracle's"""
+    from shadow_gnn_b200.synth import small_parity_graph
+    PS = _product()
+    indptr, indices = small_parity_graph(5000, 20, 17, self_loops=60)
+    N = indptr.size - 1
+    tables = _ppr_tables(indptr, indices, 150)
+    rng = np.random.default_rng(6)
+    with _Env(**env):
+        for k, thr, se, fixed in itertools.product([1, 30, 150], [0, 0.01], [False, True], [False, True]):
+            cfg = dict(method="ppr", k=str(k), threshold=str(thr), num_roots="1", add_self_edge="true" if se else "false", include_target_conn="false")
+            t = rng.permutation(N - 2)[:192].astype(np.uint32)
+            t[0] = N - 1                              # a node of the 2-node tail component: most of its PPR scope is unreachable or tiny
+            assert _oracle_vs_cuda(indptr, indices, t, 96, 2, cfg, ("hops",), ppr_tables=tables, fixed=fixed) == 192
+        s = PS.ParallelSampler(indptr, indices, [], 64, 1, True, True, [], 1, "", "", "", 1)
+        s.set_ppr_tables(*tables); s.shuffle_targets(t)
+        b = s.sample_to_device([cfg], [{"hops"}])[0]
+        assert b.hop is not None and int(b.hop.numel()) == b.total_nodes
+        if not env:
+            assert s.last_sym(), "hop labels must not push a PPR config off the fast path"
+
+
 def test_ppr_k400_papers_config_vs_oracle():
     """BASELINE configs[4] sampler parameters (papers100M: k = 400, threshold 0.002; node capacity 401 > the 320 up to which the symmetric
     variant's row offsets share the chunk queue's shared memory, 2 Bloom words per lane) against the oracle, self edge on and off"""
