@@ -181,7 +181,8 @@ class LoggerBase:
 
 
 def one_epoch(ep, mode, model, minibatch, logger, status="running", pred_mat=None, emb_ens=None, trainer=None):
-    """shaDow/main.py:136-169.  `trainer` (a `train.GraphedTrainer`) replaces `one_batch` + `model.step` for running TRAIN epochs; its
+    """shaDow/main.py:136-169.  `trainer` (a `train.GraphedTrainer`, or a dict mode -> GraphedTrainer) replaces `one_batch` + `model.step`: running
+    TRAIN epochs through the captured training step, VALID / TEST epochs through a captured forward pass; its
     batches are logged through the same `update_batch` (loss kept on the device, labels / predictions of the captured step are static
     buffers, so they are cloned)."""
     assert status in ["running", "final"] and mode in [TRAIN, VALID, TEST]
@@ -190,7 +191,9 @@ def one_epoch(ep, mode, model, minibatch, logger, status="running", pred_mat=Non
     minibatch.shuffle_entity(mode)
     logger.epoch_start_reset(ep, mode, minibatch.entity_epoch[mode].shape[0])
     t1 = time.time()
-    graphed = trainer is not None and mode == TRAIN and status == "running"
+    if isinstance(trainer, dict):                          # {mode: GraphedTrainer}: evaluation epochs through a captured forward pass too
+        trainer = trainer.get(mode)
+    graphed = trainer is not None and trainer.mode == mode and (mode != TRAIN or status == "running")
     while not minibatch.is_end_epoch(mode):
         if graphed:
             output_batch = trainer.step_logged()
@@ -217,12 +220,12 @@ def train(model, minibatch, max_epoch, logger, nocache=None, trainer=None):
     e = -1
     for e in range(max_epoch):
         one_epoch(e, TRAIN, model, minibatch, logger, trainer=trainer)
-        one_epoch(e, VALID, model, minibatch, logger)
+        one_epoch(e, VALID, model, minibatch, logger, trainer=trainer)
         if logger.log_test_convergence > 0 and e % logger.log_test_convergence == 0:
-            one_epoch(int(e / logger.log_test_convergence), TEST, model, minibatch, logger)
+            one_epoch(int(e / logger.log_test_convergence), TEST, model, minibatch, logger, trainer=trainer)
         logger.update_best_model(e, model, model.optimizer)
     logger.printf("======================\nOptimization Finished!\n======================\n", style="red")
     logger.restore_model(model, optimizer=None)
     ep_final_test = 0 if logger.log_test_convergence <= 0 else int(e / logger.log_test_convergence) + 1
     ep_final = {TRAIN: e + 1, VALID: e + 1, TEST: ep_final_test}
-    return {md: one_epoch(ep_final[md], md, model, minibatch, logger, status="final") for md in [TRAIN, VALID, TEST]}
+    return {md: one_epoch(ep_final[md], md, model, minibatch, logger, status="final", trainer=trainer) for md in [TRAIN, VALID, TEST]}

@@ -75,6 +75,15 @@ class GraphedTrainer:
                 def fire(module, inputs, output, lo=lo, hi=hi):      # this layer's OUTPUT gradient exists <=> every later layer's backward is done
                     output[0].register_hook(lambda g: allreduce_bucket(opt.grad, lo, hi, self._side))
                 handles.append(prev.register_forward_hook(fire))
+        if self.mode != TRAIN:                               # evaluation epochs (shaDow/main.py:186-187): forward + loss + predictions only
+            with torch.no_grad():
+                preds, _ = m(self.mode, list(self.feat), adjs, list(self.target), self.sizes, self.aug, 0.0)
+                self.loss.copy_(m._loss(preds, self.label))
+                p = m.predict(preds)
+                if self.preds is None:
+                    self.preds = torch.zeros_like(p)
+                self.preds.copy_(p)
+            return
         preds, _ = m(self.mode, list(self.feat), adjs, list(self.target), self.sizes, self.aug, m.dropedge)
         for h in handles:
             h.remove()
@@ -113,8 +122,24 @@ class GraphedTrainer:
             self._split = off(convs[1])
         self._side = torch.cuda.Stream()
 
+    def _capture_eval(self):
+        m = self.model
+        m.eval()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self._fwd_bwd()
+
     def _capture(self):
         m = self.model
+        if self.mode != TRAIN:
+            return self._capture_eval()
         opt = m._ensure_optimizer()
         m.train()
         side = torch.cuda.Stream()
@@ -160,7 +185,7 @@ class GraphedTrainer:
     def step_logged(self):
         """`step` for the trainer shell (main.one_epoch): the dict `DeepGNN.step` returns (models.py:209-237 of the reference) -- loss, labels
         and predictions are device tensors (copies of the captured step's static buffers), nothing synchronises"""
-        if not self.keep_preds:
+        if not self.keep_preds and self.mode == TRAIN:
             self.keep_preds, self.graph = True, None         # (re)capture with the prediction buffer
         out = self.step(_full=True)
         if isinstance(out, dict):                            # eager fallback batch
@@ -185,7 +210,7 @@ class GraphedTrainer:
                 if self.graph is None:
                     self._capture()
                 self.graph.replay()
-                if self.world > 1 and not self.dp_in_graph:
+                if self.mode == TRAIN and self.world > 1 and not self.dp_in_graph:
                     opt = self.model.optimizer
                     opt.step(allreduce_flat_gradients(opt.grad))
                 self.graph_steps += 1
@@ -194,4 +219,6 @@ class GraphedTrainer:
                 sb.cursor = c
         self.eager_steps += 1
         out = self.model.step(mode, "running", mb.one_batch(mode))
+        if mode != TRAIN and self.graph is not None:
+            self.model.eval()
         return out if _full else out["loss"].detach()

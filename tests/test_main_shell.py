@@ -108,7 +108,9 @@ def test_train_shell_learns_a_planted_task(tmp_path, graphed):
     model = DeepGNN(Fd, Fd, C, 0, arch, [], 1, dict(dropout=0.1, dropedge=0.0, lr=0.01, ensemble_dropout="none"), "node").cuda()
     lg = LoggerBase("toy", False, metric="accuracy", dir_log=str(tmp_path), log_test_convergence=2)
     tr = GraphedTrainer(model, mb, row_cap=32 * 21, edge_cap=32 * 21 * 21) if graphed else None
-    final = train(model, mb, 4, lg, trainer=tr)
+    trainers = {TRAIN: tr, VALID: GraphedTrainer(model, mb, row_cap=32 * 21, edge_cap=32 * 21 * 21, mode=VALID),
+                TEST: GraphedTrainer(model, mb, row_cap=32 * 21, edge_cap=32 * 21 * 21, mode=TEST)} if graphed else None
+    final = train(model, mb, 4, lg, trainer=trainers)
     val = lg.info_epoch[VALID].acc["accuracy"]
     assert len(val) == 5 and max(val[:4]) > 0.6, val                      # chance = 1/6
     assert lg.info_epoch[TRAIN].loss[3] < lg.info_epoch[TRAIN].loss[0]
@@ -119,3 +121,9 @@ def test_train_shell_learns_a_planted_task(tmp_path, graphed):
     assert len(list(csv.reader(open(os.path.join(str(tmp_path), "final.csv"))))) == 1 + 3
     if graphed:
         assert tr.graph_steps == 4 * 32 and tr.eager_steps == 0
+        assert trainers[VALID].graph_steps == 5 * 16 and trainers[VALID].eager_steps == 0
+        # the captured forward pass evaluates exactly like the eager DeepGNN.step
+        lg2 = LoggerBase("toy", False, metric="accuracy")
+        a = one_epoch(0, VALID, model, mb, lg2, status="final", trainer=trainers)
+        b = one_epoch(1, VALID, model, mb, lg2, status="final")
+        assert a["accuracy"] == b["accuracy"] and abs(a["loss"] - b["loss"]) <= 1e-5 * max(1.0, abs(b["loss"]))
