@@ -893,6 +893,7 @@ class FlatAdamClip:
         self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
 
     def zero_grad(self):
+        join_wgrad()                                        # (a backward pass that died half-way leaves its side-stream work un-joined)
         if self.p2p is not None:                            # peers may still be reading the previous step's gradients
             p = self.p2p
             check(lib.shadow_p2p_zero_grad_f32(p.grad_ptrs, p.flag_ptrs, p.world, p.rank, self.grad.numel(), _p(p.state), _stream(self.grad)))
@@ -909,6 +910,7 @@ class FlatAdamClip:
             if self.planes is not None:
                 self.planes.refresh()
             return
+        join_wgrad()
         check(lib.shadow_adam_clip_step_f32(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.flat.numel(), grad_scale,
                                             self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps, _p(self.step_dev), _p(self.sqnorm),
                                             _stream(self.flat)))
