@@ -582,6 +582,9 @@ def train_phase(ctx, steps, warmup):
     per_refill = count_ours(lambda: mb.par_graph_sample(MB.TRAIN))
     mb.pool[MB.TRAIN][0].pop()                           # the counted call's super-batch is not consumed (its targets are skipped)
     mine = per_step if per_step is not None else 0
+    opt = getattr(model, "optimizer", None)
+    if opt is not None and getattr(opt, "p2p", None) is not None and opt.p2p.error():
+        raise RuntimeError("peer-memory gradient exchange: a poll gave up waiting for a peer (state[2] set); the measured steps are not valid")
     return dict(value=n_all / (ms_all * 1e-3), unit="samples/s", ms_per_step=ms_all / steps, nparams=nparams,
                 graph_steps=getattr(trainer, "graph_steps", 0), eager_steps=getattr(trainer, "eager_steps", steps),
                 gpu_launches=int(mine * steps + per_refill * refills), launches_per_step=int(mine), launches_per_sampler_call=int(per_refill),
