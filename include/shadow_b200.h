@@ -314,7 +314,7 @@ int shadow_adam_clip_step_f32(float *param, const float *grad, float *exp_avg, f
  * state = uint32[516] in local device memory, zero-initialised.  shadow_p2p_zero_grad_f32 waits until every peer has finished reading the
  * previous step's gradients, then clears this rank's buffer; shadow_p2p_adam_clip_step_f32 = barrier + one-shot all-reduce into `gsum`
  * (local, n floats) + squared norm, then the step of shadow_adam_clip_step_f32 on gsum (grad_scale = 1/world gives the mean).  Polls give
- * up after ~2 s and set state[2] instead of hanging the GPU.  world <= 16. */
+ * up after ~10 s and set state[2] instead of hanging the GPU.  world <= 16. */
 int shadow_p2p_alloc(int64_t bytes, void **ptr_dev, unsigned char *handle64);
 int shadow_p2p_open(const unsigned char *handle64, void **ptr_dev);
 int shadow_p2p_close(void *ptr_dev);

@@ -921,7 +921,7 @@ extern "C" int shadow_adam_clip_step_f32(float *param, const float *grad, float 
 //      forms bit-identical sums), accumulating the squared norm of the scaled sum for the clip on the way;
 //   3. the last CTA tells every peer "I am done reading your buffer" -- the peer's next zero_grad waits for that word.
 // No NCCL call, no staging copy, ~2.4 MB x (W-1) of NVLink reads per rank; the Adam kernel then runs on the reduced copy.
-// A rank that never shows up does not hang the GPU: the polls give up after ~2 s and raise an error flag the host can read.
+// A rank that never shows up does not hang the GPU: the polls give up after ~10 s and raise an error flag the host can read.
 // ------------------------------------------------------------------------------------------------
 #define P2P_MAX_WORLD 16
 struct P2PArgs {
@@ -935,10 +935,17 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
   return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool p2p_wait(const unsigned int *flag, unsigned int want, int *err) {
-  for (long long spin = 0; (int)(ld_acquire_sys(flag) - want) < 0; spin++) {
+  if ((int)(ld_acquire_sys(flag) - want) >= 0) return true;
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(100);
-    if (spin > 20000000ll) { *err = 1; return false; }
+    if (global_ns() - t0 > 10000000000ull) { *err = 1; return false; }      // 10 s: a peer is gone; do not hang the GPU
   }
   return true;
 }
