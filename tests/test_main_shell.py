@@ -127,3 +127,31 @@ def test_train_shell_learns_a_planted_task(tmp_path, graphed):
         a = one_epoch(0, VALID, model, mb, lg2, status="final", trainer=trainers)
         b = one_epoch(1, VALID, model, mb, lg2, status="final")
         assert a["accuracy"] == b["accuracy"] and abs(a["loss"] - b["loss"]) <= 1e-5 * max(1.0, abs(b["loss"]))
+
+
+@pytest.mark.gpu
+def test_yaml_config_to_training_run(tmp_path):
+    """a training config in the reference's YAML schema -> config.load_config -> config.instantiate -> main.train on the files of a dataset in
+    shaDow's on-disk format read straight into HBM (loader.load_data_device): the whole f-2 / f-4 chain in one run"""
+    from shadow_gnn_b200.config import instantiate, load_config
+    from shadow_gnn_b200.loader import load_data_device
+    from tests.golden.make_loader_golden import NAME, write_dataset
+    write_dataset(str(tmp_path))
+    yml = tmp_path / "gcn_2_khop.yml"
+    yml.write_text("""
+data: {transductive: True, to_undirected: True, norm_feat: True}
+architecture: {dim: 32, aggr: gcn, loss: softmax, num_layers: 2, act: relu, feature_augment: hops, residue: none, pooling: center}
+hyperparameter: {end: 2, lr: 0.01, dropout: 0.1, dropedge: 0.1, batch_size: 16}
+sampler:
+  - {method: khop, phase: train, depth: [2], budget: [5]}
+""")
+    params, pre, cfg_train, cfg_data, arch = load_config(str(yml))
+    adjs, feat, label, node_set = load_data_device({"local": str(tmp_path)}, NAME, cfg_data, torch.device("cuda:0"))
+    model, mb = instantiate(NAME, adjs, feat, label, node_set, params, arch, cfg_train, config_sampler_preproc=pre, seed_cpp=3, num_subg_per_batch=64)
+    assert mb.num_ensemble == 1 and cfg_train["configs"][0]["add_self_edge"] == [True]
+    is_sigmoid = label.dim() == 2 and arch["loss"] == "sigmoid"
+    lg = LoggerBase(NAME, is_sigmoid, metric="accuracy", dir_log=str(tmp_path / "log"))
+    final = train(model, mb, params["end"], lg)
+    assert set(final) == {TRAIN, VALID, TEST} and all(np.isfinite(final[m]["loss"]) for m in final)
+    assert len(lg.info_epoch[TRAIN].loss) == params["end"] + 1
+    assert os.path.isfile(os.path.join(str(tmp_path / "log"), "running.csv"))
