@@ -229,3 +229,53 @@ def train(model, minibatch, max_epoch, logger, nocache=None, trainer=None):
     ep_final_test = 0 if logger.log_test_convergence <= 0 else int(e / logger.log_test_convergence) + 1
     ep_final = {TRAIN: e + 1, VALID: e + 1, TEST: ep_final_test}
     return {md: one_epoch(ep_final[md], md, model, minibatch, logger, status="final", trainer=trainer) for md in [TRAIN, VALID, TEST]}
+
+
+def main(argv=None):
+    """`python -m shadow_gnn_b200.main --configs <yml> --dataset <name> --dir_data <root>`: the training entry of shaDow/main.py:344-449 for a
+    dataset in shaDow's on-disk format (`<root>/<name>/{adj_full_raw.npz, feat_full.npy, label_full.npy, split.npy, ...}`)."""
+    import argparse
+    ap = argparse.ArgumentParser(description="shaDow-GNN training on the B200 path")
+    ap.add_argument("--configs", required=True, help="training YAML (config_train/... of the reference)")
+    ap.add_argument("--dataset", required=True)
+    ap.add_argument("--dir_data", default="./data", help="root that holds <dataset>/ in shaDow's on-disk format")
+    ap.add_argument("--dir_log", default=None)
+    ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--epochs", type=int, default=None, help="override hyperparameter.end")
+    ap.add_argument("--seed", type=int, default=-1, help="sampler seed (-1: time-seeded like the reference)")
+    ap.add_argument("--eager", action="store_true", help="DeepGNN.step per batch instead of the whole-step CUDA graph")
+    ap.add_argument("--nocache", default=None)
+    ap.add_argument("--log_test_convergence", type=int, default=-1)
+    args = ap.parse_args(argv)
+    from .config import instantiate, load_config
+    from .loader import load_data_device
+    from .train import GraphedTrainer
+    torch.cuda.set_device(args.gpu)
+    dev = torch.device("cuda", args.gpu)
+    params, pre, cfg_train, cfg_data, arch = load_config(args.configs)
+    adjs, feat, label, node_set = load_data_device({"local": args.dir_data}, args.dataset, cfg_data, dev, printf=lambda t, style=None: print(t))
+    model, mb = instantiate(args.dataset, adjs, feat, label, node_set, params, arch, cfg_train, config_sampler_preproc=pre, seed_cpp=args.seed, device=dev,
+                            num_subg_per_batch=cfg_train["batch_size"] * 64, rng="philox" if args.seed < 0 else "glibc")
+    metric = "f1" if arch["loss"] == "sigmoid" else "accuracy"
+    logger = LoggerBase(args.dataset, arch["loss"] == "sigmoid", metric=metric, metric_win_size=params["term_window_size"], dir_log=args.dir_log,
+                        log_test_convergence=args.log_test_convergence, printf=lambda t, style=None: print(t))
+    trainers = None
+    pools = {rp.type_pool for rp in model.res_pool_layers}
+    if not args.eager and mb.prediction_task == "node" and "sort" not in pools:
+        def scope(c):                                       # upper bound of a subgraph's node count (a batch beyond the capacity takes the eager step)
+            if c["method"].startswith("ppr"):
+                return max(c.get("k", [0])) + 1
+            if c["method"] == "khop" and min(c.get("budget", [-1])) > 0:
+                return max(sum(b ** d for d in range(dep + 1)) for b, dep in zip(c["budget"], c["depth"]))
+            return 2048
+        k = min(4096, max(scope(c) for c in cfg_train["configs"]))
+        B = cfg_train["batch_size"]
+        trainers = {m: GraphedTrainer(model, mb, row_cap=B * k, edge_cap=B * k * 64, mode=m) for m in (TRAIN, VALID, TEST)}
+    final = train(model, mb, params["end"] if args.epochs is None else args.epochs, logger, nocache=args.nocache, trainer=trainers)
+    for m in (TRAIN, VALID, TEST):
+        print(MODE2STR[m], {k: v for k, v in final[m].items() if k not in ("mode",)})
+    return final
+
+
+if __name__ == "__main__":
+    main()

@@ -155,3 +155,22 @@ sampler:
     assert set(final) == {TRAIN, VALID, TEST} and all(np.isfinite(final[m]["loss"]) for m in final)
     assert len(lg.info_epoch[TRAIN].loss) == params["end"] + 1
     assert os.path.isfile(os.path.join(str(tmp_path / "log"), "running.csv"))
+
+
+@pytest.mark.gpu
+def test_cli_entry_runs_a_config(tmp_path, capsys):
+    """`python -m shadow_gnn_b200.main --configs ... --dataset ...` (shaDow/main.py:344-449): YAML + on-disk dataset -> captured train / eval epochs"""
+    from shadow_gnn_b200.main import main
+    from tests.golden.make_loader_golden import NAME, write_dataset
+    write_dataset(str(tmp_path))
+    yml = tmp_path / "sage_2_ppr.yml"
+    yml.write_text("""
+data: {transductive: True, to_undirected: True}
+architecture: {dim: 32, aggr: sage, loss: softmax, num_layers: 2, act: relu, feature_augment: hops, residue: none, pooling: center}
+hyperparameter: {end: 2, lr: 0.01, dropout: 0.1, batch_size: 20}
+sampler:
+  - {method: ppr, phase: train, k: [15], epsilon: [1e-4]}
+""")
+    final = main(["--configs", str(yml), "--dataset", NAME, "--dir_data", str(tmp_path), "--dir_log", str(tmp_path / "log"), "--seed", "5"])
+    assert all(np.isfinite(final[m]["loss"]) and 0.0 <= final[m]["accuracy"] <= 1.0 for m in (TRAIN, VALID, TEST))
+    assert "valid" in capsys.readouterr().out
