@@ -1,8 +1,8 @@
 // ppr_warp_kernel.cuh -- the single-root PPR fast path of the fused select + induce step: ONE WARP per subgraph.
 //
-// Same contract as sample_induce_kernel (sampler_kernels.cuh) for  method == ppr, one root per subgraph, no hop/drnl
-// labels  -- the configuration every PPR node-task run of the reference uses (shaDow/minibatch.py:373-375; PS.cpp:565-595
-// + PS.cpp:350-453).  What is different is the mapping to the machine:
+// Same contract as sample_induce_kernel (sampler_kernels.cuh) for  method == ppr, one root per subgraph, with or without hop labels
+// (no drnl labels)  -- the configuration every PPR node-task run of the reference uses (shaDow/minibatch.py:373-375; PS.cpp:565-595
+// + PS.cpp:350-453; `feature_augment: hops` in 46 of its 61 configs).  What is different is the mapping to the machine:
 //   * a warp owns a subgraph end to end, so there is no CTA barrier and no cross-warp scan anywhere;
 //   * the node set comes from the id-sorted PPR row, which also carries (row start, degree) of every neighbour -- captured once
 //     when the tables are installed -- so the random 8-byte indptr reads (a 64-byte DRAM fetch each) disappear;
