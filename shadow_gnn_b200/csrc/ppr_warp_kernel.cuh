@@ -98,6 +98,31 @@ __device__ __forceinline__ bool probe2(const uint2 *hb, const int hshift, const 
   return hit;
 }
 
+// ---- level 2 for large node sets (BIS): no hash table at all.  The 2-key-bucket table needs 3 buckets per key rounded up to a power of two:
+// 16 KB of shared memory per warp at k = 400 (papers100M), i.e. 8 resident warps per SM instead of 23.  The sorted node list is already in
+// shared memory; a branch-free lower bound over it (9 steps at n = 401, the 4 keys of a chunk interleaved) decides membership exactly, and
+// only the chunks that passed the Bloom filter ever get here.
+__device__ __forceinline__ void bisect4(const uint32_t *nodes, const int n, const uint32_t (&key)[4], bool (&hit)[4]) {
+  uint32_t base[4] = {0u, 0u, 0u, 0u};
+  int len = n;
+  while (len > 1) {
+    const int half = len >> 1;
+#pragma unroll
+    for (int e = 0; e < 4; e++) base[e] += nodes[base[e] + half - 1] < key[e] ? (uint32_t)half : 0u;
+    len -= half;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const uint32_t a = nodes[base[e]];
+    const uint32_t lb = base[e] + (a < key[e] ? 1u : 0u);
+    hit[e] = lb < (uint32_t)n && (a == key[e] || (a < key[e] && nodes[min(lb, (uint32_t)n - 1u)] == key[e]));
+  }
+}
+__device__ __forceinline__ bool bisect1(const uint32_t *nodes, const int n, const uint32_t key) {
+  const uint32_t lb = sub_of(nodes, n, key);
+  return lb < (uint32_t)n && nodes[lb] == key;
+}
+
 #define WARP_OFFBITS 19                                // candidate code = row << 19 | (slot - row start + 3): rows < 8192, scanned length < 2^19 - 8
 #define WARP_OFFMASK ((1u << WARP_OFFBITS) - 1u)
 template <int U>
@@ -136,9 +161,9 @@ __device__ __forceinline__ void scan_load(ScanStage<U> &S, const uint32_t c0, co
 // staged stream (a per-warp scratch region in global memory that lives in L2).  Stream order = queue order (window, lane), then slot
 // = ascending full-graph slot = CSR order (PS.cpp:420-422).  Per-row facts (kept count; with a self-edge insertion also "kept entries
 // below v" and "v itself kept") are accumulated with one shared-memory atomic per lane.
-template <bool ADD_SELF, bool SYM>
+template <bool ADD_SELF, bool SYM, bool BIS>
 __device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t *cq_code, const uint32_t first, const uint32_t count,
-                                            const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf, const uint32_t *nodes,
+                                            const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf, const uint32_t *nodes, const int n,
                                             const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row, uint32_t &cnt, const int lane,
                                             const uint32_t lt) {
   const bool active = (uint32_t)lane < count;
@@ -153,13 +178,16 @@ __device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t
   uint32_t bal[WARP_CS], at = cnt, tot = 0, inc = 0;
   uint32_t v = 0;
   if (ADD_SELF) v = nodes[row];
+  if (BIS) bisect4(nodes, n, nb, hit);
+  else {
 #pragma unroll
-  for (int e = 0; e < WARP_CS; e++) { const uint2 kk = hb[bloom_hash(nb[e]) >> hshift]; hit[e] = (kk.x == nb[e]) | (kk.y == nb[e]); }
+    for (int e = 0; e < WARP_CS; e++) { const uint2 kk = hb[bloom_hash(nb[e]) >> hshift]; hit[e] = (kk.x == nb[e]) | (kk.y == nb[e]); }
 #pragma unroll 1
-  for (uint32_t j = 0; j < novf; j++) {                // keys that did not fit their bucket (1-2 per subgraph)
-    const uint32_t kv = ovl[j];
+    for (uint32_t j = 0; j < novf; j++) {              // keys that did not fit their bucket (1-2 per subgraph)
+      const uint32_t kv = ovl[j];
 #pragma unroll
-    for (int e = 0; e < WARP_CS; e++) hit[e] |= kv == nb[e];
+      for (int e = 0; e < WARP_CS; e++) hit[e] |= kv == nb[e];
+    }
   }
 #pragma unroll
   for (int e = 0; e < WARP_CS; e++) {
@@ -180,17 +208,17 @@ __device__ __forceinline__ void drain_batch(const uint4 *cq_keys, const uint32_t
 
 // Level 1 on one window: a lane ORs the Bloom verdicts of its 4 slots; ONE ballot appends the chunks that may hold a member to the queue,
 // a full warp of queued chunks is drained at once.
-template <bool ADD_SELF, int NF, bool SYM>
+template <bool ADD_SELF, int NF, bool SYM, bool BIS>
 __device__ __forceinline__ void scan_window(const uint32_t any, const uint4 q, const uint32_t code, uint4 *cq_keys, uint32_t *cq_code,
                                             uint32_t &qn, const uint2 *hb, const int hshift, const uint32_t *ovl, const uint32_t novf,
-                                            const uint32_t *nodes, const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
+                                            const uint32_t *nodes, const int n, const uint2 *rs, uint32_t *rc, uint2 *sc_ent, unsigned short *sc_row,
                                             uint32_t &cnt, const int lane, const uint32_t lt) {
   const uint32_t bal = __ballot_sync(0xffffffffu, any != 0u);
   if (any) { const uint32_t at = qn + __popc(bal & lt); cq_keys[at] = q; cq_code[at] = code; }
   qn += __popc(bal);
   if (qn >= 32u) {
     __syncwarp();
-    drain_batch<ADD_SELF, SYM>(cq_keys, cq_code, 0u, 32u, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+    drain_batch<ADD_SELF, SYM, BIS>(cq_keys, cq_code, 0u, 32u, hb, hshift, ovl, novf, nodes, n, rs, rc, sc_ent, sc_row, cnt, lane, lt);
     const uint32_t left = qn - 32u;                  // < 32: move the tail to the front
     uint4 tk = make_uint4(0u, 0u, 0u, 0u); uint32_t tc = 0;
     if ((uint32_t)lane < left) { tk = cq_keys[32 + lane]; tc = cq_code[32 + lane]; }
@@ -352,7 +380,8 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int *__restrict
 // ascending u the mirrored edges of a row arrive in ascending order, i.e. in CSR order, ahead of the row's own upper part (PS.cpp:420-422
 // emits a row in slot order = ascending neighbour id).  The PS.cpp:401 slot one past a row is a DIRECTED quirk: it is kept for its row and
 // never mirrored.  Output is bit-identical to the full scan (same parity tests); a graph that fails the check keeps the full scan.
-template <bool ADD_SELF, int NF, bool SYM>
+// BIS = exact membership by bisection in the sorted node list instead of the 2-key-bucket table (large node sets, see bisect4).
+template <bool ADD_SELF, int NF, bool SYM, bool BIS>
 __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(const SampleParams P) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   uint32_t *const nodes = (uint32_t *)(smem_dyn + P.WL.nodes);
@@ -447,8 +476,10 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
     const int n = (int)run + 1;                         // == node_ptr[p+1] - node_ptr[p]
 
     // ---------------- B: Bloom filter + exact table, chunk prefix ----------------
+    if (!BIS) {
 #pragma unroll 1
-    for (uint32_t i = lane; i < nbuckets / 2; i += 32) reinterpret_cast<uint4 *>(hk)[i] = make_uint4(NONE32, NONE32, NONE32, NONE32);
+      for (uint32_t i = lane; i < nbuckets / 2; i += 32) reinterpret_cast<uint4 *>(hk)[i] = make_uint4(NONE32, NONE32, NONE32, NONE32);
+    }
 #pragma unroll
     for (int j = 0; j < NF; j++) fw[32 * j + lane] = 0u;
     if (lane == 0) ovf[0] = 0;
@@ -462,10 +493,12 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
         const uint32_t v = nodes[i];
         const uint32_t h = bloom_hash(v);
         atomicOr(&fw[bloom_word_index<NF>(h)], bloom_bits(h, bloom_hash2(v)));
-        const uint32_t b = h >> hshift;
-        if (atomicCAS(&hk[2 * b], NONE32, v) != NONE32 && atomicCAS(&hk[2 * b + 1], NONE32, v) != NONE32) {
-          const uint32_t q = atomicAdd(&ovf[0], 1u);
-          if (q < WARP_OVF_CAP) ovf[1 + q] = v;
+        if (!BIS) {
+          const uint32_t b = h >> hshift;
+          if (atomicCAS(&hk[2 * b], NONE32, v) != NONE32 && atomicCAS(&hk[2 * b + 1], NONE32, v) != NONE32) {
+            const uint32_t q = atomicAdd(&ovf[0], 1u);
+            if (q < WARP_OVF_CAP) ovf[1 + q] = v;
+          }
         }
         uint2 r = rs[i];
         if (ext && r.x + r.y < E) { r.y += 1; rs[i] = make_uint2(r.x, SYM ? (r.y | 0x80000000u) : r.y); }      // the PS.cpp:401 slot joins the row
@@ -512,13 +545,13 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
           any[u] = (bloom_test<NF>(f, SA.q[u].x) | bloom_test<NF>(f, SA.q[u].y) | bloom_test<NF>(f, SA.q[u].z) | bloom_test<NF>(f, SA.q[u].w)) & 1u;
 #pragma unroll
         for (int u = 0; u < U; u++)
-          scan_window<ADD_SELF, NF, SYM>(any[u], SA.q[u], SA.code[u], cq_keys, cq_code, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt);
+          scan_window<ADD_SELF, NF, SYM, BIS>(any[u], SA.q[u], SA.code[u], cq_keys, cq_code, qn, hb, hshift, ovl, novf, nodes, n, rs, rc, sc_ent, sc_row, cnt, lane, lt);
 #if WARP_DB
 #pragma unroll
         for (int u = 0; u < U; u++) { SA.q[u] = SB.q[u]; SA.code[u] = SB.code[u]; }
 #endif
       }
-      if (!bail && qn) { __syncwarp(); drain_batch<ADD_SELF, SYM>(cq_keys, cq_code, 0u, qn, hb, hshift, ovl, novf, nodes, rs, rc, sc_ent, sc_row, cnt, lane, lt); }
+      if (!bail && qn) { __syncwarp(); drain_batch<ADD_SELF, SYM, BIS>(cq_keys, cq_code, 0u, qn, hb, hshift, ovl, novf, nodes, n, rs, rc, sc_ent, sc_row, cnt, lane, lt); }
     }
     __syncwarp();
     if (p_next < P.num_subg) { off_next = P.ppr_ptr[t_next]; row_end_next = P.ppr_ptr[t_next + 1]; }      // consumed before the emit
@@ -575,7 +608,7 @@ __global__ void __launch_bounds__(32, WARP_MIN_BLOCKS) ppr_induce_warp_kernel(co
               const uint32_t e = rs[i].x + rs[i].y;
               if (e < E) {
                 const uint32_t nb = __ldg(P.indices + e);
-                if (probe2(hb, hshift, ovl, novf, nb)) bsub = sub_of(nodes, n, nb);
+                if (BIS ? bisect1(nodes, n, nb) : probe2(hb, hshift, ovl, novf, nb)) bsub = sub_of(nodes, n, nb);
               }
             }
             rins[i] = present ? NONE32 : ((w >> 14) & 0x3fffu); rbug[i] = bsub;                // SYM: bits 14..27 = mirrored edges, all below v

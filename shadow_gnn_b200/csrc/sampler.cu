@@ -216,7 +216,7 @@ static int plan_caps(shadow_sampler *s, const shadow_sampler_cfg &c, Caps *o) {
 }
 
 // per-warp workspace of the single-root PPR fast path (ppr_warp_kernel.cuh)
-static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, bool sym, int ecap_mult, WarpLayout *W, int *w_ecap, int *w_nf, int *w_hbuckets, int *w_hshift) {
+static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, bool sym, bool bis, int ecap_mult, WarpLayout *W, int *w_ecap, int *w_nf, int *w_hbuckets, int *w_hshift) {
   uint32_t off = 0;
   auto take = [&](size_t bytes) { uint32_t r = off; off = align16(off + (uint32_t)bytes); return r; };
   // staged edges per warp (global scratch, L2-resident): ecap_mult (16 to start with) per node + one full stage of head room.  A subgraph
@@ -234,7 +234,7 @@ static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, bool sym, i
   *w_hbuckets = std::max(16, next_pow2((envb ? std::max(1, atoi(envb)) : 3) * caps.ncap));
   int lg = 0; while ((1 << lg) < *w_hbuckets) lg++;
   *w_hshift = 32 - lg;
-  W->hkeys = take((size_t)*w_hbuckets * 8);
+  W->hkeys = take(bis ? 16 : (size_t)*w_hbuckets * 8);        // bisection variant: no exact table
   W->queue = take((size_t)WARP_QCAP * 20);                   // chunk queue: uint4 keys + packed (row, offset) codes
   W->rs = take((size_t)caps.ncap * 8);
   W->nodes = take((size_t)caps.ncap * 4);
@@ -252,10 +252,12 @@ static void plan_warp(const Caps &caps, const shadow_sampler_cfg &c, bool sym, i
 }
 
 typedef void (*warp_kernel_t)(const SampleParams);
-template <bool A, bool S>
+template <bool A, bool S, bool B>
 static warp_kernel_t pick_warp_kernel(int nf) {
-  return nf == 1 ? ppr_induce_warp_kernel<A, 1, S> : (nf == 2 ? ppr_induce_warp_kernel<A, 2, S> : ppr_induce_warp_kernel<A, 4, S>);
+  return nf == 1 ? ppr_induce_warp_kernel<A, 1, S, B> : (nf == 2 ? ppr_induce_warp_kernel<A, 2, S, B> : ppr_induce_warp_kernel<A, 4, S, B>);
 }
+template <bool A, bool S>
+static warp_kernel_t pick_warp_kernel(int nf, bool bis) { return bis ? pick_warp_kernel<A, S, true>(nf) : pick_warp_kernel<A, S, false>(nf); }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void max_degree_kernel(const uint32_t *indptr, uint32_t n, unsigned long long *out) {
@@ -674,19 +676,22 @@ static int launch_branch(shadow_sampler *s, Result &r) {
   int w_ecap = 0;
   int w_nf = 1;
   if (fast) { long long d; int rcd = graph_dmax(s, &d); if (rcd) return rcd; fast = d + 8 < (1ll << WARP_OFFBITS); }      // packed candidate codes
-  bool sym = false;
+  bool sym = false, bis = false;
   if (fast) {
     const char *envr = getenv("SHADOW_SYM_RATIO");
     sym = s->kept_ratio < (envr ? atof(envr) : 0.12) && ensure_sym(s);
-    plan_warp(caps, c, sym, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024;
+    // exact membership by bisection instead of the hash table once the table would cost resident warps (> 4 KB: more than ~170 nodes)
+    const char *envb = getenv("SHADOW_WARP_BISECT");
+    bis = envb ? atoi(envb) != 0 : caps.ncap > 200;
+    plan_warp(caps, c, sym, bis, s->warp_ecap_mult, &K.WL, &w_ecap, &w_nf, &K.w_hbuckets, &K.w_hshift); K.w_ecap = w_ecap; fast = K.WL.bytes <= 96 * 1024;
     if (sym) { K.ppr_supper = (const uint2 *)s->ppr_supper.p; K.sym_rev = (const uint32_t *)s->sym_rev.p; }
   }
   s->last_sym = fast && sym;
   warp_kernel_t kern = nullptr;
   int gridw = 0;
   if (fast && P > 0) {                                  // every host-side query happens BEFORE the first GPU operation of the launch
-    kern = sym ? (K.add_self ? pick_warp_kernel<true, true>(w_nf) : pick_warp_kernel<false, true>(w_nf))
-               : (K.add_self ? pick_warp_kernel<true, false>(w_nf) : pick_warp_kernel<false, false>(w_nf));
+    kern = sym ? (K.add_self ? pick_warp_kernel<true, true>(w_nf, bis) : pick_warp_kernel<false, true>(w_nf, bis))
+               : (K.add_self ? pick_warp_kernel<true, false>(w_nf, bis) : pick_warp_kernel<false, false>(w_nf, bis));
     int wps = 0;
     rc = kern_cfg(s->kcache, (const void *)kern, 32, K.WL.bytes, &wps); if (rc) return rc;
     rc = kern_cfg(s->kcache, (const void *)sample_induce_kernel<false, true>, SAMPLER_BLOCK, caps.L.bytes, nullptr); if (rc) return rc;

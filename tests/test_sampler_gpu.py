@@ -318,7 +318,8 @@ def _ppr_tables(indptr, indices, k, eps=1e-5):
 
 @pytest.mark.parametrize("env", [dict(), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_WARP_NF=2, SHADOW_WARP_BUCKET_MULT=1),
                                  dict(SHADOW_WARP_ECAP_MULT=1, SHADOW_WARP_NF=4), dict(SHADOW_NO_WARP_PPR=1), dict(SHADOW_NO_SYM=1),
-                                 dict(SHADOW_NO_SYM=1, SHADOW_WARP_ECAP_MULT=0)])
+                                 dict(SHADOW_NO_SYM=1, SHADOW_WARP_ECAP_MULT=0),
+                                 dict(SHADOW_WARP_BISECT=1), dict(SHADOW_WARP_BISECT=1, SHADOW_NO_SYM=1), dict(SHADOW_WARP_BISECT=0)])
 def test_ppr_warp_path_and_redo_vs_oracle(env):
     """the fast path, its staging-overflow and bucket-overflow hand-over (redo launch of the generic kernel) and the generic
     kernel alone all reproduce the oracle bit for bit: bug-compatible and fixed mode, self edge on/off, thresholds, k=1"""
@@ -361,7 +362,7 @@ def test_ppr_sym_variant_is_selected_and_directed_graphs_fall_back():
             assert s.last_sym() == want_sym, (env, want_sym)
 
 
-@pytest.mark.parametrize("env", [dict(), dict(SHADOW_NO_SYM=1), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_NO_WARP_PPR=1)])
+@pytest.mark.parametrize("env", [dict(), dict(SHADOW_NO_SYM=1), dict(SHADOW_WARP_ECAP_MULT=0), dict(SHADOW_NO_WARP_PPR=1), dict(SHADOW_WARP_BISECT=1)])
 def test_ppr_with_hop_labels_on_the_fast_path_vs_oracle(env):
     """`feature_augment: hops` with a PPR sampler (46 of the reference's 61 configs): the one-warp fast path labels hops with a warp-level BFS
     (both scan variants, the redo hand-over, and the generic kernel for comparison) -- every array incl. `hop` equals the oracle's"""
@@ -395,9 +396,11 @@ def test_ppr_k400_papers_config_vs_oracle():
     t = np.random.default_rng(3).permutation(N - 2)[:192].astype(np.uint32)
     nb, sc, ln = O.ppr_push(indptr, indices, t, 400, 0.85, 1e-5, 8)
     tables = O.ppr_rows_to_csr(N, t, nb, sc, ln)
-    for se, thr in (("false", "0.002"), ("true", "0")):
-        cfg = dict(method="ppr", k="400", threshold=thr, num_roots="1", add_self_edge=se, include_target_conn="false")
-        assert _oracle_vs_cuda(indptr, indices, t, 64, 2, cfg, (), ppr_tables=tables) == 192
+    for env in (dict(), dict(SHADOW_WARP_BISECT=0), dict(SHADOW_NO_SYM=1)):      # default at this size: exact membership by bisection (no hash table)
+        with _Env(**env):
+            for se, thr in (("false", "0.002"), ("true", "0")):
+                cfg = dict(method="ppr", k="400", threshold=thr, num_roots="1", add_self_edge=se, include_target_conn="false")
+                assert _oracle_vs_cuda(indptr, indices, t, 64, 2, cfg, (), ppr_tables=tables) == 192
 
 
 def test_ppr_warp_redo_is_exercised():
